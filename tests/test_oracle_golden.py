@@ -129,7 +129,7 @@ def test_lstp_matches_lsqr_lis(p):
         assert rel(t["rnorm"], row[2]) < tol, (itn, t["rnorm"], row[2])
         assert rel(t["anorm"], row[5]) < 6e-3 and rel(t["acond"], row[6]) < 6e-3   # 3 printed digits
     # exit iteration count: pinned only loosely -- the runs stop at atol = eps**0.99 (inside rounding noise)
-    assert abs(res["itn"] - p["itn"]) <= 12
+    assert abs(res["itn"] - p["itn"]) <= max(10, p["itn"] // 40)
     assert rel(res["anorm"], p["anorm"]) < 3e-2 and rel(res["rnorm"], p["rnorm"]) < 1e-5
     assert res["xcheck_inform"] == p["xcheck_inform"]
     # verdict (16 successes, the two expected failures lsqrtest_module.f90:109-115)
