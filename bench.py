@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py -- LSQR iterations/s and effective HBM GB/s on BASELINE.json's synthetic workloads.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C2|C3|C4|C5|auto] [--scale S]
+    python bench.py --impl reference ...     # the reference algorithm on the host CPU (oracle port)
+
+A "step" is one complete solve (initial bidiagonalisation + every LSQR iteration until the
+reference's own stopping rule fires, atol = btol = 1e-10, conlim = 1e8) of the named workload with
+the matrix already resident in HBM.  `value` = B_iter * iterations / time (effective HBM GB/s,
+B_iter = 24 nnz + 28 m + 68 n + 8 algorithmic bytes per iteration) with b and x in HBM;
+`iters_per_s` rides along.  `e2e` is the same quantity through the public host API with b in pinned
+host memory and x copied back to the host inside the timed region.  Multi-GPU: A is row-partitioned
+(strong scaling of one fixed problem), one process per GPU, one NCCL all-reduce per iteration.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+
+METRIC = "lsqr_effective_hbm_GBps"   # B_iter * LSQR iterations / s ; iters_per_s reported beside it
+UNIT = "GB/s"
+SOLVE_OPTS = dict(atol=1e-10, btol=1e-10, conlim=1e8, itnlim=100000)
+
+
+def parse_args():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=20)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--workload", default="auto", choices=["auto", "C2", "C3", "C4", "C5"])
+    p.add_argument("--scale", type=float, default=1.0, help="divide m and n by this factor")
+    p.add_argument("--cpu-scale", type=float, default=0.0, help="scale of the CPU-baseline sample (0 = auto)")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-graph", action="store_true")
+    return p.parse_args()
+
+
+def pick_workload(args) -> str:
+    if args.workload != "auto":
+        return args.workload
+    # configs[1] (C2) is the 1 x B200 configuration of BASELINE.json; the multi-GPU target is C5.
+    return "C2" if args.gpus == 1 else "C5"
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines: list[str] = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            f = [t.strip() for t in l.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the oracle port of the reference algorithm on the host CPU
+# ------------------------------------------------------------------------------------------------
+def cpu_sample_config(name: str, cpu_scale: float):
+    from lsqr_b200 import synth
+    auto = {"C2": 1.0, "C3": 25.0, "C4": 40.0, "C5": 100.0}[name]
+    scale = cpu_scale if cpu_scale > 0 else auto
+    return synth.scaled(name, scale), scale
+
+
+def run_cpu_reference(name: str, cpu_scale: float, steps: int, warmup: int, budget_s: float = 25.0):
+    """Times oracle solve_ez (serial, like the reference) on a bounded sample of the workload."""
+    from lsqr_b200 import synth
+    from oracle import oracle as O
+    cfg, scale = cpu_sample_config(name, cpu_scale)
+    m, n = cfg["m"], cfg["n"]
+    irow, icol, a = synth.coo_block(cfg["kind"], cfg["seed"], m, n, cfg["k"])
+    b = synth.rhs_block(irow, icol, a, m, synth.x_true(cfg["seed"], n), cfg["seed"])
+    s = O.SolverEz(m, n, a, irow, icol, SOLVE_OPTS["atol"], SOLVE_OPTS["btol"], SOLVE_OPTS["conlim"], SOLVE_OPTS["itnlim"])
+    for _ in range(max(0, min(warmup, 1))):
+        s.solve(b, cfg["damp"])
+    t0 = time.perf_counter()
+    itn = 0
+    done = 0
+    for _ in range(max(1, steps)):
+        r = s.solve(b, cfg["damp"])
+        itn += r.itn
+        done += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    bytes_iter = synth.b_iter_bytes(a.size, m, n)
+    return {
+        "value": bytes_iter * itn / dt / 1e9, "unit": UNIT, "cores": 1, "kind": "port",
+        "iters_per_s": itn / dt, "ms_per_step": 1e3 * dt / done, "steps_done": done, "itn_per_step": itn / done,
+        "sample": f"{name} at 1/{scale:g} scale: {m}x{n}, nnz={a.size}; {done} full solves, serial C port of "
+                  f"src/lsqr.f90 (no Fortran compiler in this image), gcc -O2 -ffp-contract=off",
+    }
+
+
+def reference_main(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    name = pick_workload(args)
+    res = run_cpu_reference(name, args.cpu_scale, args.steps, args.warmup, budget_s=120.0)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": res["steps_done"], "warmup": min(args.warmup, 1), "ms_per_step": res["ms_per_step"],
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "iters_per_s": res["iters_per_s"],
+        "config": {"workload": name, "sample": res["sample"]},
+        "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return reference_main(args)
+
+    import torch
+    import lsqr_b200
+    from lsqr_b200 import synth, dist as ldist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as td
+        td.init_process_group("nccl", device_id=dev)
+
+    name = pick_workload(args)
+    cfg = synth.scaled(name, args.scale) if args.scale != 1.0 else dict(synth.CONFIGS[name])
+    m, n = cfg["m"], cfg["n"]
+    row0, row1 = ldist.row_block(m, world, rank)
+    m_loc = row1 - row0
+
+    # ---- synthetic inputs (deterministic counter hash; generated on the device when the generator exists)
+    stream = torch.cuda.current_stream().cuda_stream
+    t_gen = time.perf_counter()
+    irow, icol, a = ldist.generate_block(cfg, row0, m_loc, dev)
+    nnz_loc = int(a.numel() if hasattr(a, "numel") else a.size)
+    t_gen = time.perf_counter() - t_gen
+
+    nccl_id = ldist.exchange_unique_id(world, rank) if world > 1 else None
+    torch.cuda.synchronize()
+    t_init = time.perf_counter()
+    solver = lsqr_b200.LsqrSolverEz().initialize(
+        m_loc, n, a, irow, icol, stream=stream, use_graph=not args.no_graph,
+        world_size=world, rank=rank, nccl_unique_id=nccl_id, m_global=m, **SOLVE_OPTS)
+    torch.cuda.synchronize()
+    t_init = time.perf_counter() - t_init
+    del irow, icol, a
+    torch.cuda.empty_cache()
+
+    # b = A x_true + 1e-3 noise, formed on the device with the engine's own Aprod
+    xt = torch.from_numpy(synth.x_true(cfg["seed"], n)).to(dev)
+    b_dev = torch.from_numpy(synth.noise(cfg["seed"], row0, m_loc)).to(dev)
+    solver.aprod(1, m_loc, n, xt, b_dev)
+    x_dev = torch.empty(n, dtype=torch.float64, device=dev)
+    b_host = b_dev.cpu().pin_memory()
+    x_host = torch.empty(n, dtype=torch.float64).pin_memory()
+
+    if world > 1:
+        import torch.distributed as td
+        tot = torch.tensor([nnz_loc], dtype=torch.int64, device=dev)
+        td.all_reduce(tot)
+        nnz = int(tot.item())
+    else:
+        nnz = nnz_loc
+    bytes_iter = synth.b_iter_bytes(nnz, m, n)
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as td
+            td.barrier()
+        torch.cuda.synchronize()
+
+    def timed(b, x, steps):
+        """K solves bracketed by barrier + synchronize; device time by CUDA events, max over ranks."""
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        itn = launches = 0
+        last = None
+        for _ in range(steps):
+            last = solver.solve(b, cfg["damp"], x=x)
+            itn += last.itn
+            launches += solver.kernel_times()["total_launches"]
+        e1.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            import torch.distributed as td
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            td.all_reduce(t, op=td.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, wall, itn, launches, last
+
+    # ---- warm-up, then the timed regions
+    for _ in range(max(args.warmup, 3)):
+        solver.solve(b_dev, cfg["damp"], x=x_dev)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms, wall, itn, launches, last = timed(b_dev, x_dev, args.steps)
+    clocks = sampler.stop() if rank == 0 else {}
+    for _ in range(2):
+        solver.solve(b_host, cfg["damp"], x=x_host)
+    ms_e2e, wall_e2e, itn_e2e, _, last_e2e = timed(b_host, x_host, args.steps)
+
+    # ---- roofline of the dominant kernel: CUDA-event pairs around every launch inside the real loop
+    solver.set_tolerances(profile=True)
+    solver.solve(b_dev, cfg["damp"], x=x_dev)
+    kt = solver.kernel_times()
+    solver.set_tolerances(profile=False)
+    peak, peak_src = measured_peak()
+    kb = {   # algorithmic bytes per launch on this rank
+        "aprod": 12 * nnz_loc + 4 * (m_loc + 1) + 8 * n + 16 * m_loc,
+        "atprod": 12 * nnz_loc + 4 * (n + 1) + 8 * m_loc + 16 * n,
+        "update": 40 * n,
+    }
+    kms = {"aprod": kt["aprod_ms"], "atprod": kt["atprod_ms"], "update": kt["update_ms"]}
+    dom = max(kms, key=lambda k: kms[k])
+    achieved = kb[dom] / (kms[dom] * 1e-3) / 1e9 if kms[dom] > 0 else 0.0
+    traffic = None
+    try:   # per-launch DRAM bytes from the committed ncu capture, if it was summarised for this workload
+        prof = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic.json")))
+        traffic = prof.get(name, {}).get(dom)
+    except Exception:
+        pass
+    roofline = {
+        "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+        "algorithmic_bytes_per_launch": kb[dom], "avg_launch_ms": kms[dom],
+        "per_kernel": {k: {"ms": kms[k], "GBps": (kb[k] / (kms[k] * 1e-3) / 1e9 if kms[k] > 0 else 0.0),
+                           "frac": (kb[k] / (kms[k] * 1e-3) / 1e9 / peak if kms[k] > 0 else 0.0)} for k in kms},
+        "loop_frac": (bytes_iter * last.itn / (kt["loop_ms"] * 1e-3) / 1e9) / (peak * world) if kt["loop_ms"] > 0 else None,
+    }
+
+    if rank != 0:
+        return
+    value = bytes_iter * itn / (ms * 1e-3) / 1e9
+    e2e_value = bytes_iter * itn_e2e / (ms_e2e * 1e-3) / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "iters_per_s": itn / (ms * 1e-3), "itn_per_step": itn / args.steps, "ms_per_iteration": ms / max(itn, 1),
+        "frac_of_hbm_roofline": value / (peak * world),
+        "config": {
+            "workload": f"{name}: {cfg['kind']} {m}x{n}, nnz={nnz}, damp={cfg['damp']}, via lsqr_solver_ez "
+                        f"(atol=btol=1e-10, conlim=1e8), row-partitioned over {world} GPU(s)",
+            "step": "one full solve: b -> x, all LSQR iterations to the reference's stopping rule",
+            "b_iter_bytes": bytes_iter, "istop": last.istop,
+            "l2_note": "inputs larger than L2: CSR(A)+CSR(A') = %.0f MB per GPU stream through every iteration"
+                       % (24 * nnz_loc / 1e6),
+            "wall_s": wall, "initialize_s": t_init, "generate_s": t_gen,
+        },
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * m_loc, "d2h_bytes_per_step": 8 * n,
+                "iters_per_s": itn_e2e / (ms_e2e * 1e-3), "ms_per_step": ms_e2e / args.steps, "wall_s": wall_e2e,
+                "api": "lsqr_b200_ez_solve with pinned host b and x (C ABI, via LsqrSolverEz.solve)"},
+        "gpu_launches": launches,
+        "roofline": roofline,
+        "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        cb = run_cpu_reference(name, args.cpu_scale, 3, 1, budget_s=20.0)
+        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "iters_per_s")}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as td
+        td.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,200 @@
+// build_csr.cu -- K0/K1/K2: on-device validation of the COO triplets and their conversion to
+// CSR (A) and a precomputed CSR of A' (so Atprod needs no atomics).
+//
+// The reference keeps the matrix as unsorted COO (src/lsqr.f90:113-118) and accumulates in COO
+// order (:168-172, :188-192).  The conversion is a STABLE key sort (LSD radix sort of
+// (key, COO position) pairs): inside a row / column the entries keep their COO order and
+// duplicates are kept, so every per-row / per-column sum visits the same terms in the same order
+// as the reference.  The result is bit-exact against oracle/csr_oracle.c (integer work + copies).
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include "build_csr.h"
+
+namespace lsqrb {
+
+namespace {
+
+constexpr int kT = 256;
+
+inline int grid_for(int64_t n, int per_sm = 8)
+{
+    int64_t blocks = (n + kT - 1) / kT;
+    int64_t cap = (int64_t)kNumSMs * per_sm;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+// K0: min / max of an index array (bounds checks of src/lsqr.f90:110-111, plus the lower bound)
+__global__ void __launch_bounds__(kT) minmax_kernel(int64_t nnz, const int32_t *__restrict__ a, int32_t *out /*[2]*/)
+{
+    int32_t lo = INT32_MAX, hi = INT32_MIN;
+    for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < nnz; i += (int64_t)gridDim.x * kT) {
+        const int32_t v = a[i];
+        lo = min(lo, v);
+        hi = max(hi, v);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(out + 0, lo);
+        atomicMax(out + 1, hi);
+    }
+}
+
+// is key[] already non-decreasing?  (row-sorted COO needs no sort for A)
+__global__ void __launch_bounds__(kT) unsorted_flag_kernel(int64_t nnz, const int32_t *__restrict__ key, int *flag)
+{
+    int bad = 0;
+    for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i + 1 < nnz; i += (int64_t)gridDim.x * kT)
+        bad |= (key[i] > key[i + 1]);
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
+}
+
+// counts[key-1] += 1   (integer atomics: order-independent, hence deterministic)
+__global__ void __launch_bounds__(kT) histogram_kernel(int64_t nnz, const int32_t *__restrict__ key, uint32_t *counts)
+{
+    for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < nnz; i += (int64_t)gridDim.x * kT)
+        atomicAdd(counts + (key[i] - 1), 1u);
+}
+
+__global__ void __launch_bounds__(kT) iota_kernel(int64_t nnz, uint32_t *p)
+{
+    for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < nnz; i += (int64_t)gridDim.x * kT) p[i] = (uint32_t)i;
+}
+
+// idx[p] = other[perm[p]] - 1 ; val[p] = a[perm[p]]
+__global__ void __launch_bounds__(kT)
+gather_kernel(int64_t nnz, const uint32_t *__restrict__ perm, const int32_t *__restrict__ other,
+              const double *__restrict__ a, int32_t *__restrict__ idx, double *__restrict__ val)
+{
+    for (int64_t p = (int64_t)blockIdx.x * kT + threadIdx.x; p < nnz; p += (int64_t)gridDim.x * kT) {
+        const uint32_t i = perm[p];
+        idx[p] = other[i] - 1;
+        val[p] = a[i];
+    }
+}
+
+// identity permutation: idx = other - 1 ; val = a
+__global__ void __launch_bounds__(kT)
+copy_kernel(int64_t nnz, const int32_t *__restrict__ other, const double *__restrict__ a,
+            int32_t *__restrict__ idx, double *__restrict__ val)
+{
+    for (int64_t p = (int64_t)blockIdx.x * kT + threadIdx.x; p < nnz; p += (int64_t)gridDim.x * kT) {
+        idx[p] = other[p] - 1;
+        val[p] = a[p];
+    }
+}
+
+int bits_for(int64_t nkeys)
+{
+    int b = 1;
+    while (((int64_t)1 << b) <= nkeys) ++b;   // keys are 1..nkeys
+    return b;
+}
+
+}  // namespace
+
+int coo_validate(cudaStream_t stream, int32_t m, int32_t n, int64_t nnz,
+                 const int32_t *d_irow, const int32_t *d_icol)
+{
+    if (nnz == 0) return LSQR_B200_OK;
+    int32_t *d_mm = nullptr;
+    LSQRB_CUDA(cudaMalloc(&d_mm, 4 * sizeof(int32_t)));
+    const int32_t init[4] = {INT32_MAX, INT32_MIN, INT32_MAX, INT32_MIN};
+    LSQRB_CUDA(cudaMemcpyAsync(d_mm, init, sizeof init, cudaMemcpyHostToDevice, stream));
+    minmax_kernel<<<grid_for(nnz), kT, 0, stream>>>(nnz, d_irow, d_mm);
+    minmax_kernel<<<grid_for(nnz), kT, 0, stream>>>(nnz, d_icol, d_mm + 2);
+    int32_t h[4];
+    LSQRB_CUDA(cudaMemcpyAsync(h, d_mm, sizeof h, cudaMemcpyDeviceToHost, stream));
+    LSQRB_CUDA(cudaStreamSynchronize(stream));
+    cudaFree(d_mm);
+    // same order as the reference: irow first (:110), then icol (:111)
+    if (h[1] > m) return LSQR_B200_ERR_IROW;
+    if (h[3] > n) return LSQR_B200_ERR_ICOL;
+    if (h[0] < 1 || h[2] < 1) {
+        set_last_error("irow/icol contain an index < 1 (undefined behaviour in the reference)");
+        return LSQR_B200_ERR_INDEX_LOW;
+    }
+    return LSQR_B200_OK;
+}
+
+int coo_to_csr_device(cudaStream_t stream, int64_t nkeys, int64_t nnz,
+                      const int32_t *d_key, const int32_t *d_other, const double *d_a, Csr *out)
+{
+    out->nrows = nkeys;
+    out->nnz = nnz;
+    out->was_sorted = 1;
+    LSQRB_CUDA(cudaMalloc(&out->ptr, sizeof(uint32_t) * (size_t)(nkeys + 1)));
+    const size_t nz = (size_t)(nnz > 0 ? nnz : 1);
+    LSQRB_CUDA(cudaMalloc(&out->idx, sizeof(int32_t) * nz));
+    LSQRB_CUDA(cudaMalloc(&out->val, sizeof(double) * nz));
+    LSQRB_CUDA(cudaMalloc(&out->perm, sizeof(uint32_t) * nz));
+    LSQRB_CUDA(cudaMemsetAsync(out->ptr, 0, sizeof(uint32_t) * (size_t)(nkeys + 1), stream));
+    if (nnz == 0) return LSQR_B200_OK;
+
+    // ptr: histogram of the keys, then an exclusive prefix sum
+    histogram_kernel<<<grid_for(nnz), kT, 0, stream>>>(nnz, d_key, out->ptr);
+    {
+        void *d_tmp = nullptr;
+        size_t tmp_bytes = 0;
+        LSQRB_CUDA(cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, out->ptr, out->ptr, nkeys + 1, stream));
+        LSQRB_CUDA(cudaMalloc(&d_tmp, tmp_bytes ? tmp_bytes : 1));
+        LSQRB_CUDA(cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, out->ptr, out->ptr, nkeys + 1, stream));
+        LSQRB_CUDA(cudaStreamSynchronize(stream));
+        cudaFree(d_tmp);
+    }
+
+    // already grouped by key?  then the stable sort is the identity
+    int *d_flag = nullptr, h_flag = 0;
+    LSQRB_CUDA(cudaMalloc(&d_flag, sizeof(int)));
+    LSQRB_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), stream));
+    unsorted_flag_kernel<<<grid_for(nnz), kT, 0, stream>>>(nnz, d_key, d_flag);
+    LSQRB_CUDA(cudaMemcpyAsync(&h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    LSQRB_CUDA(cudaStreamSynchronize(stream));
+    cudaFree(d_flag);
+
+    iota_kernel<<<grid_for(nnz), kT, 0, stream>>>(nnz, out->perm);
+    if (!h_flag) {
+        copy_kernel<<<grid_for(nnz), kT, 0, stream>>>(nnz, d_other, d_a, out->idx, out->val);
+        LSQRB_CUDA(cudaGetLastError());
+        return LSQR_B200_OK;
+    }
+    out->was_sorted = 0;
+
+    // stable LSD radix sort of (key, COO position); only the low bits_for(nkeys) bits are sorted
+    uint32_t *d_keys_out = nullptr, *d_iota = nullptr;
+    LSQRB_CUDA(cudaMalloc(&d_keys_out, sizeof(uint32_t) * nz));
+    LSQRB_CUDA(cudaMalloc(&d_iota, sizeof(uint32_t) * nz));
+    LSQRB_CUDA(cudaMemcpyAsync(d_iota, out->perm, sizeof(uint32_t) * nz, cudaMemcpyDeviceToDevice, stream));
+    void *d_tmp = nullptr;
+    size_t tmp_bytes = 0;
+    const uint32_t *keys_in = reinterpret_cast<const uint32_t *>(d_key);
+    LSQRB_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, keys_in, d_keys_out, d_iota, out->perm,
+                                               nnz, 0, bits_for(nkeys), stream));
+    LSQRB_CUDA(cudaMalloc(&d_tmp, tmp_bytes ? tmp_bytes : 1));
+    LSQRB_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, keys_in, d_keys_out, d_iota, out->perm,
+                                               nnz, 0, bits_for(nkeys), stream));
+    gather_kernel<<<grid_for(nnz), kT, 0, stream>>>(nnz, out->perm, d_other, d_a, out->idx, out->val);
+    LSQRB_CUDA(cudaGetLastError());
+    LSQRB_CUDA(cudaStreamSynchronize(stream));
+    cudaFree(d_tmp);
+    cudaFree(d_keys_out);
+    cudaFree(d_iota);
+    return LSQR_B200_OK;
+}
+
+void csr_free(Csr *c)
+{
+    if (!c) return;
+    cudaFree(c->ptr);
+    cudaFree(c->idx);
+    cudaFree(c->val);
+    cudaFree(c->perm);
+    *c = Csr{};
+}
+
+}  // namespace lsqrb

@@ -1,0 +1,162 @@
+// common.cuh -- shared declarations of the B200 LSQR engine (device state, helpers).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/lsqr_b200.h"
+
+namespace lsqrb {
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------------------------
+void set_last_error(const std::string &msg);
+
+#define LSQRB_CUDA(call)                                                                         \
+    do {                                                                                         \
+        cudaError_t err__ = (call);                                                              \
+        if (err__ != cudaSuccess) {                                                              \
+            ::lsqrb::set_last_error(std::string(#call) + ": " + cudaGetErrorString(err__) +      \
+                                    " (" __FILE__ ":" + std::to_string(__LINE__) + ")");         \
+            return LSQR_B200_ERR_CUDA;                                                           \
+        }                                                                                        \
+    } while (0)
+
+#define LSQRB_TRY(call)                                                                          \
+    do {                                                                                         \
+        int rc__ = (call);                                                                       \
+        if (rc__ != LSQR_B200_OK) return rc__;                                                   \
+    } while (0)
+
+constexpr int kNumSMs = 148;             // B200: 2 dies x 74 SMs
+constexpr int kMaxPartials = 148 * 16;   // upper bound on the grid of any reducing kernel
+constexpr int kRingSize = 256;           // per-iteration records in pinned mapped memory
+
+// ---------------------------------------------------------------------------------------------
+// Device-resident solver state: every scalar of the LSQR recurrence (src/lsqr.f90:566-575)
+// lives here, is advanced by the last block of the kernel that produces its inputs, and never
+// visits the host inside the loop.
+// ---------------------------------------------------------------------------------------------
+struct DevState {
+    // configuration (set by the host before the solve)
+    double damp, atol, btol, ctol;
+    int    itnlim, wantse, damped, dist;
+
+    // Golub-Kahan scalars
+    double alpha, beta, inv_alpha, inv_beta;
+    // coefficients consumed by the next vector kernel (lazy normalisation: u and v are stored
+    // unnormalised, the 1/beta and 1/alpha factors ride in these coefficients)
+    double ca_mat, ca_vec;   // Aprod : u' = ca_mat * (A v)  + ca_vec * u
+    double ct_mat, ct_vec;   // Atprod: v' = ct_mat * (A'u') + ct_vec * v
+    double t1, t2, t3;       // update: x += t1 w ; w' = inv_alpha * v' + t2 w ; se += (t3 w)^2
+    double wnorm2;           // sum(w^2) of the current w (gives dknorm = |t3| sqrt(wnorm2))
+    // coefficients of the operator-hook path, which keeps u and v normalised like the reference:
+    // dscal(u,-alpha) | dscal(u,1/beta) | dscal(v,-beta) | dscal(v,1/alpha)  (src/lsqr.f90:681,692,693,697)
+    double g_c0, g_c1, g_c2, g_c3;
+
+    // QR / estimate recurrences (src/lsqr.f90:597-617, 650-653)
+    double rhobar, phibar, bnorm, anorm, acond, dnorm, res2, psi, xnorm, xnorm1, cs2, sn2, z;
+    double rnorm, arnorm, dxmax;
+    // per-iteration print-only values
+    double phi, dknorm, dxk, alfopt, test1, test2, x1;
+
+    int itn, istop, nstop, maxdx;
+    int done;                // set after the x/w update of the stopping iteration
+    int pad0;
+
+    // completion counters of the "last block finishes the reduction" pattern
+    unsigned int counter[4];
+
+    // partial sums of the reducing kernels (fixed slot per block => deterministic final sum)
+    double partial[kMaxPartials];
+};
+
+// ---------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------
+
+// sqrt(a^2+b^2) with the reference's scaling, src/lsqr.f90:1164-1179
+__device__ __forceinline__ double d2norm(double a, double b)
+{
+    double scale = fabs(a) + fabs(b);
+    if (scale == 0.0) return 0.0;
+    double p = a / scale, q = b / scale;
+    return scale * sqrt(p * p + q * q);
+}
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Block-wide sum with a fixed reduction tree (deterministic).  Result valid in thread 0.
+template <int THREADS>
+__device__ __forceinline__ double block_sum(double v, double *smem /* >= THREADS/32 doubles */)
+{
+    v = warp_sum(v);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) smem[wid] = v;
+    __syncthreads();
+    double r = 0.0;
+    if (wid == 0) {
+        r = (lane < THREADS / 32) ? smem[lane] : 0.0;
+        r = warp_sum(r);
+    }
+    __syncthreads();
+    return r;
+}
+
+// Cache-policy helpers.  The matrix streams are read exactly once per kernel: keep them out of L1
+// (no_allocate) and mark them evict-first in L2 so the gathered dense vector (evict-last) stays
+// resident in the 126 MB L2.  sm_100a accepts the direct .L2::evict_* qualifier only on 256-bit
+// loads (LDG.E.256); narrower loads carry a createpolicy descriptor instead.
+__device__ __forceinline__ uint64_t l2_policy_evict_first()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ double ldg_stream_f64(const double *p, uint64_t pol)
+{
+    double r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(r) : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ int32_t ldg_stream_s32(const int32_t *p, uint64_t pol)
+{
+    int32_t r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(pol));
+    return r;
+}
+// 256-bit streaming loads (Blackwell LDG.E.256): 4 doubles / 8 int32 per thread, 32-byte aligned.
+__device__ __forceinline__ void ldg_stream_f64x4(const double *p, double (&v)[4])
+{
+    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.f64 {%0,%1,%2,%3}, [%4];"
+                 : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+}
+__device__ __forceinline__ void ldg_stream_s32x8(const int32_t *p, int32_t (&v)[8])
+{
+    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v8.s32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "l"(p));
+}
+// Gathered dense vector: read-only path, keep in L2.
+__device__ __forceinline__ double ldg_keep_f64(const double *p, uint64_t pol)
+{
+    double r;
+    asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(r) : "l"(p), "l"(pol));
+    return r;
+}
+
+}  // namespace lsqrb

@@ -1,0 +1,1222 @@
+// engine.cu -- host driver + C ABI of the B200 LSQR engine (include/lsqr_b200.h).
+//
+// One handle owns: CSR(A) and CSR(A') in HBM, the work vectors u(m), v,w,x,(se)(n), a
+// device-resident scalar state (DevState), and a ring of per-iteration records in pinned mapped
+// host memory.  The host never computes a scalar of the recurrence: it enqueues batches of
+// iterations (CUDA graph), and reads the records to learn when the device decided to stop.
+#include <dlfcn.h>
+#include <nccl.h>   // types only; the library is dlopen'ed so single-GPU use has no NCCL dependency
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "build_csr.h"
+#include "kernels.cuh"
+
+namespace lsqrb {
+
+// ---------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+void set_last_error(const std::string &msg) { g_last_error = msg; }
+
+static bool is_device_ptr(const void *p)
+{
+    if (!p) return false;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+static int env_int(const char *name, int dflt)
+{
+    const char *v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
+// ---------------------------------------------------------------------------------------------
+// NCCL, loaded at run time
+// ---------------------------------------------------------------------------------------------
+struct NcclApi {
+    void *lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+static NcclApi *nccl_api()
+{
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        // Prefer a copy that is already in the process (torch loads its bundled libnccl.so.2).
+        void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+        if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) return;
+        api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+        api.CommInitRank = (decltype(api.CommInitRank))dlsym(h, "ncclCommInitRank");
+        api.AllReduce = (decltype(api.AllReduce))dlsym(h, "ncclAllReduce");
+        api.CommDestroy = (decltype(api.CommDestroy))dlsym(h, "ncclCommDestroy");
+        api.GetErrorString = (decltype(api.GetErrorString))dlsym(h, "ncclGetErrorString");
+        if (api.GetUniqueId && api.CommInitRank && api.AllReduce && api.CommDestroy) api.lib = h;
+    });
+    return api.lib ? &api : nullptr;
+}
+
+#define LSQRB_NCCL(call)                                                                          \
+    do {                                                                                          \
+        ncclResult_t r__ = (call);                                                                \
+        if (r__ != ncclSuccess) {                                                                 \
+            NcclApi *a__ = nccl_api();                                                            \
+            set_last_error(std::string(#call) + ": " +                                            \
+                           ((a__ && a__->GetErrorString) ? a__->GetErrorString(r__) : "nccl error")); \
+            return LSQR_B200_ERR_NCCL;                                                            \
+        }                                                                                         \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// Fortran-style number formatting for the nout log (1PEw.d)
+// ---------------------------------------------------------------------------------------------
+static std::string fe(int w, int d, double v)
+{
+    char tmp[64];
+    snprintf(tmp, sizeof tmp, "%.*E", d, v);
+    std::string s(tmp);
+    size_t e = s.find('E');
+    if (e != std::string::npos && s.size() - (e + 2) >= 3) s.erase(e, 1);   // E+100 -> +100
+    if ((int)s.size() > w) return std::string((size_t)w, '*');
+    return std::string((size_t)w - s.size(), ' ') + s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Work: stream + device state + record ring, shared by the ez path and the operator-hook path
+// ---------------------------------------------------------------------------------------------
+struct Work {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    DevState *st = nullptr;                       // device
+    DevState h;                                   // host mirror (header part only is copied)
+    lsqr_b200_iter_record *ring_h = nullptr;      // pinned, mapped
+    lsqr_b200_iter_record *ring_d = nullptr;      // device alias of ring_h
+    int max_grid = kNumSMs * 8;
+    int64_t launches = 0;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+
+    int init(int dev, void *user_stream)
+    {
+        int count = 0;
+        if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+            cudaGetLastError();
+            set_last_error("no CUDA device is visible; this engine has no CPU path");
+            return LSQR_B200_ERR_NO_DEVICE;
+        }
+        if (dev < 0) LSQRB_CUDA(cudaGetDevice(&dev));
+        if (dev >= count) { set_last_error("device ordinal out of range"); return LSQR_B200_ERR_ARG; }
+        device = dev;
+        LSQRB_CUDA(cudaSetDevice(device));
+        if (user_stream) {
+            stream = (cudaStream_t)user_stream;
+        } else {
+            LSQRB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+            own_stream = true;
+        }
+        LSQRB_CUDA(cudaMalloc(&st, sizeof(DevState)));
+        LSQRB_CUDA(cudaMemsetAsync(st, 0, sizeof(DevState), stream));
+        LSQRB_CUDA(cudaHostAlloc(&ring_h, sizeof(lsqr_b200_iter_record) * kRingSize, cudaHostAllocMapped));
+        LSQRB_CUDA(cudaHostGetDevicePointer(&ring_d, ring_h, 0));
+        for (auto &e : ev) LSQRB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDefault));
+        int sms = 0;
+        LSQRB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+        max_grid = std::min(kMaxPartials, std::max(1, sms) * env_int("LSQR_B200_BLOCKS_PER_SM", 8));
+        return LSQR_B200_OK;
+    }
+
+    void destroy()
+    {
+        if (st) cudaFree(st);
+        if (ring_h) cudaFreeHost(ring_h);
+        for (auto &e : ev) if (e) cudaEventDestroy(e);
+        if (own_stream && stream) cudaStreamDestroy(stream);
+        st = nullptr; ring_h = nullptr; stream = nullptr;
+    }
+
+    int grid_for(int64_t items, int per_block) const
+    {
+        int64_t b = (items + per_block - 1) / per_block;
+        if (b < 1) b = 1;
+        return (int)std::min<int64_t>(b, max_grid);
+    }
+
+    // reset the scalar state for a new solve (src/lsqr.f90:597-617)
+    int reset_state(double damp, double atol, double btol, double conlim, int itnlim, int wantse, int dist)
+    {
+        memset(&h, 0, offsetof(DevState, partial));
+        h.damp = damp; h.atol = atol; h.btol = btol;
+        h.ctol = conlim > 0.0 ? 1.0 / conlim : 0.0;
+        h.itnlim = itnlim; h.wantse = wantse; h.damped = damp > 0.0; h.dist = dist;
+        h.cs2 = -1.0;
+        h.inv_alpha = h.inv_beta = 1.0;
+        h.g_c0 = h.g_c1 = h.g_c2 = h.g_c3 = 1.0;
+        LSQRB_CUDA(cudaMemcpyAsync(st, &h, offsetof(DevState, partial), cudaMemcpyHostToDevice, stream));
+        for (int i = 0; i < kRingSize; ++i) ring_h[i].itn = -1.0;
+        return LSQR_B200_OK;
+    }
+
+    int fetch_state()
+    {
+        LSQRB_CUDA(cudaMemcpyAsync(&h, st, offsetof(DevState, partial), cudaMemcpyDeviceToHost, stream));
+        LSQRB_CUDA(cudaStreamSynchronize(stream));
+        return LSQR_B200_OK;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// SpMV launch dispatch
+// ---------------------------------------------------------------------------------------------
+static int pick_lanes(const Csr &M, const char *env_name)
+{
+    int forced = env_int(env_name, 0);
+    if (forced == 1 || forced == 2 || forced == 4 || forced == 8 || forced == 16 || forced == 32) return forced;
+    const double mean = M.nrows > 0 ? (double)M.nnz / (double)M.nrows : 1.0;
+    int lanes = 2;
+    while (lanes < 32 && lanes * 3 < mean) lanes <<= 1;   // about three passes over a mean row
+    return lanes;
+}
+
+template <int EPI>
+static int launch_spmv(Work &wk, const Csr &M, int lanes, const double *x, double *out, double *aux)
+{
+    CsrView V{M.ptr, M.idx, M.val, M.nrows};
+    const int grid = wk.grid_for(M.nrows, kThreads / lanes);
+    switch (lanes) {
+    case 1:  spmv_rowgroup_kernel<1, EPI><<<grid, kThreads, 0, wk.stream>>>(V, x, out, wk.st, aux); break;
+    case 2:  spmv_rowgroup_kernel<2, EPI><<<grid, kThreads, 0, wk.stream>>>(V, x, out, wk.st, aux); break;
+    case 4:  spmv_rowgroup_kernel<4, EPI><<<grid, kThreads, 0, wk.stream>>>(V, x, out, wk.st, aux); break;
+    case 8:  spmv_rowgroup_kernel<8, EPI><<<grid, kThreads, 0, wk.stream>>>(V, x, out, wk.st, aux); break;
+    case 16: spmv_rowgroup_kernel<16, EPI><<<grid, kThreads, 0, wk.stream>>>(V, x, out, wk.st, aux); break;
+    default: spmv_rowgroup_kernel<32, EPI><<<grid, kThreads, 0, wk.stream>>>(V, x, out, wk.st, aux); break;
+    }
+    wk.launches++;
+    LSQRB_CUDA(cudaGetLastError());
+    return LSQR_B200_OK;
+}
+
+static inline int vec_ok(const void *a, const void *b, const void *c, const void *d)
+{
+    auto al = [](const void *p) { return p == nullptr || ((uintptr_t)p & 15u) == 0; };
+    return al(a) && al(b) && al(c) && al(d);
+}
+
+template <bool LAZY>
+static int launch_update(Work &wk, int64_t n, double *x, double *w, const double *v, double *se, bool wantse)
+{
+    const int grid = wk.grid_for((n + 1) / 2, kThreads);
+    const int vok = vec_ok(x, w, v, wantse ? se : nullptr);
+    if (wantse) xw_update_kernel<true, LAZY><<<grid, kThreads, 0, wk.stream>>>(n, x, w, v, se, wk.st, wk.ring_d, vok);
+    else        xw_update_kernel<false, LAZY><<<grid, kThreads, 0, wk.stream>>>(n, x, w, v, se, wk.st, wk.ring_d, vok);
+    wk.launches++;
+    LSQRB_CUDA(cudaGetLastError());
+    return LSQR_B200_OK;
+}
+
+// record 0 of the log (src/lsqr.f90:666-671): written once the first alpha, beta are known
+__global__ void record0_kernel(DevState *st, volatile lsqr_b200_iter_record *ring)
+{
+    volatile lsqr_b200_iter_record *r = ring;
+    r->istop = (double)st->istop;
+    r->x1 = 0.0;
+    r->rnorm = st->rnorm;
+    r->test1 = 1.0;
+    r->test2 = st->beta > 0.0 ? st->alpha / st->beta : 0.0;
+    r->anorm = 0.0; r->acond = 0.0; r->phi = 0.0; r->dknorm = 0.0; r->dxk = 0.0; r->alfopt = 0.0;
+    r->alpha = st->alpha; r->beta = st->beta; r->xnorm = 0.0; r->arnorm = st->arnorm;
+    __threadfence_system();
+    r->itn = 0.0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// nout log reconstruction on the host (formats of src/lsqr.f90:589-595,655-671,827-829,872-880)
+// ---------------------------------------------------------------------------------------------
+struct LogCtx {
+    lsqr_b200_log_fn log = nullptr;  void *log_user = nullptr;
+    lsqr_b200_iter_fn iter = nullptr; void *iter_user = nullptr;
+    int64_t m = 0, n = 0;
+    double damp = 0, atol = 0, btol = 0, conlim = 0, ctol = 0;
+    int itnlim = 0, wantse = 0;
+    double bnorm = 0;
+
+    void line(const std::string &s) const { if (log) log(log_user, s.c_str()); }
+
+    void header() const
+    {
+        if (!log) return;
+        char buf[160];
+        line(""); line("");
+        line(" Enter LSQR.       Least-squares solution of  Ax = b");
+        snprintf(buf, sizeof buf, " The matrix  A  has%7lld rows   and%7lld columns", (long long)m, (long long)n);
+        line(buf);
+        line(" damp   =" + fe(22, 14, damp) + "   wantse =" + std::string(9, ' ') + (wantse ? "T" : "F"));
+        line(" atol   =" + fe(10, 2, atol) + std::string(15, ' ') + "conlim =" + fe(10, 2, conlim));
+        snprintf(buf, sizeof buf, "%10d", itnlim);
+        line(" btol   =" + fe(10, 2, btol) + std::string(15, ' ') + "itnlim =" + buf);
+    }
+
+    void iter_line(const lsqr_b200_iter_record &r, int nvals) const
+    {
+        static const int w[10] = {17, 17, 10, 10, 10, 10, 9, 8, 8, 8};
+        static const int d[10] = {9, 9, 2, 2, 2, 2, 1, 1, 1, 1};
+        const double vals[10] = {r.x1, r.rnorm, r.test1, r.test2, r.anorm, r.acond, r.phi, r.dknorm, r.dxk, r.alfopt};
+        char buf[16];
+        snprintf(buf, sizeof buf, "%6d", (int)r.itn);
+        std::string s(buf);
+        for (int k = 0; k < nvals; ++k) s += fe(w[k], d[k], vals[k]);
+        line(s);
+    }
+
+    void record(const lsqr_b200_iter_record &r)
+    {
+        if (iter) iter(iter_user, &r);
+        if (!log) return;
+        const int itn = (int)r.itn;
+        if (itn == 0) {
+            bnorm = r.beta;
+            line(""); line("");
+            if (damp > 0.0) line("   Itn       x(1)           Function     Compatible   LS     Norm Abar Cond Abar");
+            else            line("   Itn       x(1)           Function     Compatible   LS        Norm A    Cond A");
+            line(std::string(80, ' ') + "    phi    dknorm   dxk  alfa_opt");
+            iter_line(r, 4);
+            line("");
+            return;
+        }
+        const double test3 = 1.0 / r.acond;
+        const double rtol = btol + atol * r.anorm * r.xnorm / bnorm;
+        const bool print_iter = (n <= 40) || (itn <= 10) || (itn >= itnlim - 10) || (itn % 10 == 0) ||
+                                (test3 <= 2.0 * ctol) || (r.test2 <= 10.0 * atol) ||
+                                (r.test1 <= 10.0 * rtol) || (r.istop != 0.0);
+        if (print_iter) iter_line(r, 10);
+    }
+
+    void footer(int istop, const DevState &h) const
+    {
+        if (!log) return;
+        static const char *const msg[6] = {
+            "The exact solution is x = 0                          ",
+            "A solution to Ax = b was found, given atol, btol     ",
+            "A least-squares solution was found, given atol       ",
+            "A damped least-squares solution was found, given atol",
+            "Cond(Abar) seems to be too large, given conlim       ",
+            "The iteration limit was reached                      "};
+        char buf[160];
+        const std::string ex = " Exit  LSQR.  ";
+        line(""); line("");
+        snprintf(buf, sizeof buf, "     istop  =%2d               itn    =%8d", istop, h.itn);
+        line(ex + buf);
+        line(ex + "     anorm  =" + fe(12, 5, h.anorm) + "     acond  =" + fe(12, 5, h.acond));
+        line(ex + "     bnorm  =" + fe(12, 5, h.bnorm) + "     xnorm  =" + fe(12, 5, h.xnorm));
+        line(ex + "     rnorm  =" + fe(12, 5, h.rnorm) + "     arnorm =" + fe(12, 5, h.arnorm));
+        snprintf(buf, sizeof buf, " occurred at itn %8d", h.maxdx);
+        line(ex + "     max dx =" + fe(8, 1, h.dxmax) + buf);
+        line(ex + "            =" + fe(8, 1, h.dxmax / (h.xnorm + 1.0e-20)) + "*xnorm");
+        line(ex + "     " + msg[istop]);
+    }
+};
+
+// Consume finished records in order; returns true once a record carries istop != 0.
+static bool drain_ring(Work &wk, LogCtx &lc, int &seen, int upto)
+{
+    bool stop = false;
+    while (seen < upto) {
+        const int k = seen + 1;
+        volatile lsqr_b200_iter_record *r = wk.ring_h + (k % kRingSize);
+        if (r->itn != (double)k) break;
+        lsqr_b200_iter_record rec;
+        memcpy(&rec, (const void *)r, sizeof rec);
+        lc.record(rec);
+        seen = k;
+        if (rec.istop != 0.0) { stop = true; break; }
+    }
+    return stop;
+}
+
+}  // namespace lsqrb
+
+using namespace lsqrb;
+
+// =============================================================================================
+// the ez handle
+// =============================================================================================
+struct lsqr_b200_ez {
+    Work wk;
+    int32_t m = 0, n = 0;
+    int64_t nnz = 0;
+    Csr A, AT;
+    int lanes_a = 4, lanes_at = 32;
+    lsqr_b200_options opt;
+    double *u = nullptr, *v = nullptr, *w = nullptr, *x = nullptr, *se = nullptr;
+    double *g = nullptr;          // multi-GPU: [ A_p'u_p (n) | sum(u_p^2) ]
+    double *tmp_m = nullptr, *tmp_n = nullptr;   // staging for lsqr_b200_ez_aprod with host vectors
+    ncclComm_t comm = nullptr;
+    int batch = 8;                // iterations per enqueue (per CUDA-graph launch)
+    cudaGraphExec_t graph_exec = nullptr;
+    int graph_wantse = -1;
+    lsqr_b200_kernel_times times;
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_t2 = nullptr;
+    std::vector<cudaEvent_t> prof_ev;   // profile mode: start/stop pairs
+    std::vector<int> prof_cls;
+};
+
+static void ez_free(lsqr_b200_ez *me)
+{
+    if (!me) return;
+    cudaSetDevice(me->wk.device);
+    if (me->wk.stream) cudaStreamSynchronize(me->wk.stream);
+    if (me->graph_exec) cudaGraphExecDestroy(me->graph_exec);
+    if (me->comm) { NcclApi *a = nccl_api(); if (a) a->CommDestroy(me->comm); }
+    csr_free(&me->A);
+    csr_free(&me->AT);
+    for (double *p : {me->u, me->v, me->w, me->x, me->se, me->g, me->tmp_m, me->tmp_n}) if (p) cudaFree(p);
+    for (auto e : {me->ev_t0, me->ev_t1, me->ev_t2}) if (e) cudaEventDestroy(e);
+    for (auto e : me->prof_ev) cudaEventDestroy(e);
+    me->wk.destroy();
+    delete me;
+}
+
+extern "C" {
+
+const char *lsqr_b200_error_message(int code)
+{
+    switch (code) {
+    case LSQR_B200_OK:            return "";
+    case LSQR_B200_ERR_SIZES:     return "invalid a,icol,irow sizes in initialize_ez";
+    case LSQR_B200_ERR_IROW:      return "invalid irow or m in initialize_ez";
+    case LSQR_B200_ERR_ICOL:      return "invalid icol or n in initialize_ez";
+    case LSQR_B200_ERR_NOINIT:    return "lsqr_solver_ez class not properly initialized";
+    case LSQR_B200_ERR_MODE:      return "invalid mode in aprod_ez";
+    case LSQR_B200_ERR_INDEX_LOW: return "irow or icol contains an index smaller than 1";
+    case LSQR_B200_ERR_NO_DEVICE: return "no CUDA device available (the engine has no CPU fallback)";
+    case LSQR_B200_ERR_CUDA:      return "CUDA runtime error";
+    case LSQR_B200_ERR_NCCL:      return "NCCL error";
+    case LSQR_B200_ERR_ARG:       return "invalid argument";
+    case LSQR_B200_ERR_TOO_LARGE: return "too many stored entries for one GPU (limit 2^32-2)";
+    case LSQR_B200_ERR_CALLBACK:  return "user aprod callback failed";
+    default:                      return "unknown error code";
+    }
+}
+
+const char *lsqr_b200_last_error(void) { return g_last_error.c_str(); }
+int lsqr_b200_version(void) { return LSQR_B200_VERSION; }
+
+int lsqr_b200_device_count(void)
+{
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return count;
+}
+
+void lsqr_b200_default_options(lsqr_b200_options *o)
+{
+    if (!o) return;
+    memset(o, 0, sizeof *o);
+    o->itnlim = 100;        // src/lsqr.f90:50
+    o->device = -1;
+    o->use_graph = 1;
+    o->world_size = 1;
+}
+
+int lsqr_b200_nccl_unique_id(void *out128)
+{
+    if (!out128) return LSQR_B200_ERR_ARG;
+    NcclApi *a = nccl_api();
+    if (!a) { set_last_error("libnccl.so.2 could not be loaded"); return LSQR_B200_ERR_NCCL; }
+    ncclUniqueId id;
+    LSQRB_NCCL(a->GetUniqueId(&id));
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    memcpy(out128, &id, 128);
+    return LSQR_B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// initialize_ez  (src/lsqr.f90:91-127)
+// ---------------------------------------------------------------------------------------------
+static int ez_initialize_impl(lsqr_b200_ez *me, int64_t nnz, const double *a, const int32_t *irow, const int32_t *icol)
+{
+    Work &wk = me->wk;
+    const size_t nz = (size_t)(nnz > 0 ? nnz : 1);
+    // deep copy of the triplets onto the GPU (src/lsqr.f90:113-118); host or device sources
+    int32_t *d_irow = nullptr, *d_icol = nullptr;
+    double *d_a = nullptr;
+    const bool dev_src = is_device_ptr(a) && is_device_ptr(irow) && is_device_ptr(icol);
+    if (dev_src) {
+        d_irow = const_cast<int32_t *>(irow);
+        d_icol = const_cast<int32_t *>(icol);
+        d_a = const_cast<double *>(a);
+    } else {
+        LSQRB_CUDA(cudaMalloc(&d_irow, sizeof(int32_t) * nz));
+        LSQRB_CUDA(cudaMalloc(&d_icol, sizeof(int32_t) * nz));
+        LSQRB_CUDA(cudaMalloc(&d_a, sizeof(double) * nz));
+        if (nnz > 0) {
+            LSQRB_CUDA(cudaMemcpyAsync(d_irow, irow, sizeof(int32_t) * nz, cudaMemcpyDefault, wk.stream));
+            LSQRB_CUDA(cudaMemcpyAsync(d_icol, icol, sizeof(int32_t) * nz, cudaMemcpyDefault, wk.stream));
+            LSQRB_CUDA(cudaMemcpyAsync(d_a, a, sizeof(double) * nz, cudaMemcpyDefault, wk.stream));
+        }
+    }
+    auto release = [&]() {
+        if (!dev_src) { cudaFree(d_irow); cudaFree(d_icol); cudaFree(d_a); }
+    };
+    int rc = coo_validate(wk.stream, me->m, me->n, nnz, d_irow, d_icol);
+    if (rc == LSQR_B200_OK) rc = coo_to_csr_device(wk.stream, me->m, nnz, d_irow, d_icol, d_a, &me->A);
+    if (rc == LSQR_B200_OK) rc = coo_to_csr_device(wk.stream, me->n, nnz, d_icol, d_irow, d_a, &me->AT);
+    if (rc == LSQR_B200_OK && cudaStreamSynchronize(wk.stream) != cudaSuccess) rc = LSQR_B200_ERR_CUDA;
+    release();
+    LSQRB_TRY(rc);
+
+    me->lanes_a = pick_lanes(me->A, "LSQR_B200_LANES_A");
+    me->lanes_at = pick_lanes(me->AT, "LSQR_B200_LANES_AT");
+
+    const size_t mm = (size_t)std::max<int32_t>(me->m, 1), nn = (size_t)std::max<int32_t>(me->n, 1);
+    LSQRB_CUDA(cudaMalloc(&me->u, sizeof(double) * mm));
+    LSQRB_CUDA(cudaMalloc(&me->v, sizeof(double) * nn));
+    LSQRB_CUDA(cudaMalloc(&me->w, sizeof(double) * nn));
+    LSQRB_CUDA(cudaMalloc(&me->x, sizeof(double) * nn));
+    if (me->opt.world_size > 1) LSQRB_CUDA(cudaMalloc(&me->g, sizeof(double) * (nn + 1)));
+    LSQRB_CUDA(cudaEventCreate(&me->ev_t0));
+    LSQRB_CUDA(cudaEventCreate(&me->ev_t1));
+    LSQRB_CUDA(cudaEventCreate(&me->ev_t2));
+    return LSQR_B200_OK;
+}
+
+int lsqr_b200_ez_initialize(lsqr_b200_ez **out, int32_t m, int32_t n,
+                            int64_t size_a, const double *a,
+                            int64_t size_irow, const int32_t *irow,
+                            int64_t size_icol, const int32_t *icol,
+                            const lsqr_b200_options *opts)
+{
+    if (!out) return LSQR_B200_ERR_ARG;
+    *out = nullptr;
+    // src/lsqr.f90:109 -- the three sizes must agree
+    if (size_a != size_irow || size_a != size_icol) return LSQR_B200_ERR_SIZES;
+    if (m < 0 || n < 0 || size_a < 0) { set_last_error("negative dimension"); return LSQR_B200_ERR_ARG; }
+    if (size_a > 0 && (!a || !irow || !icol)) { set_last_error("NULL triplet array"); return LSQR_B200_ERR_ARG; }
+    if (size_a > (int64_t)0xFFFFFFFEll) return LSQR_B200_ERR_TOO_LARGE;
+
+    lsqr_b200_ez *me = new lsqr_b200_ez();
+    if (opts) me->opt = *opts; else lsqr_b200_default_options(&me->opt);
+    if (me->opt.world_size < 1) me->opt.world_size = 1;
+    me->m = m; me->n = n; me->nnz = size_a;
+    memset(&me->times, 0, sizeof me->times);
+    me->batch = std::max(1, std::min(env_int("LSQR_B200_BATCH", 8), kRingSize / 4));
+
+    int rc = me->wk.init(me->opt.device, me->opt.stream);
+    if (rc == LSQR_B200_OK && me->opt.world_size > 1) {
+        NcclApi *api = nccl_api();
+        if (!api) { set_last_error("libnccl.so.2 could not be loaded"); rc = LSQR_B200_ERR_NCCL; }
+        else if (!me->opt.nccl_unique_id) { set_last_error("world_size > 1 needs nccl_unique_id"); rc = LSQR_B200_ERR_ARG; }
+        else {
+            ncclUniqueId id;
+            memcpy(&id, me->opt.nccl_unique_id, 128);
+            ncclResult_t r = api->CommInitRank(&me->comm, me->opt.world_size, id, me->opt.rank);
+            if (r != ncclSuccess) { set_last_error("ncclCommInitRank failed"); rc = LSQR_B200_ERR_NCCL; }
+        }
+        me->opt.nccl_unique_id = nullptr;   // the caller's buffer need not outlive this call
+    }
+    if (rc == LSQR_B200_OK) rc = ez_initialize_impl(me, size_a, a, irow, icol);
+    if (rc != LSQR_B200_OK) { ez_free(me); return rc; }
+    *out = me;
+    return LSQR_B200_OK;
+}
+
+void lsqr_b200_ez_destroy(lsqr_b200_ez *me) { ez_free(me); }
+
+int lsqr_b200_ez_set_options(lsqr_b200_ez *me, const lsqr_b200_options *o)
+{
+    if (!me || !o) return LSQR_B200_ERR_ARG;
+    me->opt.atol = o->atol; me->opt.btol = o->btol; me->opt.conlim = o->conlim; me->opt.itnlim = o->itnlim;
+    me->opt.log = o->log; me->opt.log_user = o->log_user; me->opt.iter = o->iter; me->opt.iter_user = o->iter_user;
+    me->opt.engine = o->engine; me->opt.use_graph = o->use_graph; me->opt.profile = o->profile;
+    return LSQR_B200_OK;
+}
+
+int64_t lsqr_b200_ez_nnz(const lsqr_b200_ez *me) { return me ? me->nnz : -1; }
+
+int lsqr_b200_ez_get_csr(lsqr_b200_ez *me, int32_t which, int64_t *ptr, int32_t *idx, double *val, int64_t *perm)
+{
+    if (!me || (which != 0 && which != 1)) return LSQR_B200_ERR_ARG;
+    LSQRB_CUDA(cudaSetDevice(me->wk.device));
+    const Csr &M = which == 0 ? me->A : me->AT;
+    if (ptr) {
+        std::vector<uint32_t> p((size_t)M.nrows + 1);
+        LSQRB_CUDA(cudaMemcpy(p.data(), M.ptr, sizeof(uint32_t) * p.size(), cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < p.size(); ++i) ptr[i] = (int64_t)p[i];
+    }
+    if (M.nnz > 0) {
+        if (idx) LSQRB_CUDA(cudaMemcpy(idx, M.idx, sizeof(int32_t) * (size_t)M.nnz, cudaMemcpyDeviceToHost));
+        if (val) LSQRB_CUDA(cudaMemcpy(val, M.val, sizeof(double) * (size_t)M.nnz, cudaMemcpyDeviceToHost));
+        if (perm) {
+            std::vector<uint32_t> p((size_t)M.nnz);
+            LSQRB_CUDA(cudaMemcpy(p.data(), M.perm, sizeof(uint32_t) * p.size(), cudaMemcpyDeviceToHost));
+            for (size_t i = 0; i < p.size(); ++i) perm[i] = (int64_t)p[i];
+        }
+    }
+    return LSQR_B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// aprod_ez  (src/lsqr.f90:134-200)
+// ---------------------------------------------------------------------------------------------
+int lsqr_b200_ez_aprod_device(void *handle, int32_t mode, int32_t m, int32_t n,
+                              double *x_dev, double *y_dev, void *stream)
+{
+    lsqr_b200_ez *me = (lsqr_b200_ez *)handle;
+    if (!me) return LSQR_B200_ERR_ARG;
+    if (m != me->m || n != me->n) return LSQR_B200_ERR_NOINIT;   // :152
+    Work &wk = me->wk;
+    cudaStream_t saved = wk.stream;
+    if (stream) wk.stream = (cudaStream_t)stream;
+    int rc;
+    if (mode == 1)      rc = launch_spmv<EPI_ACC>(wk, me->A, me->lanes_a, x_dev, y_dev, nullptr);    // y += A x
+    else if (mode == 2) rc = launch_spmv<EPI_ACC>(wk, me->AT, me->lanes_at, y_dev, x_dev, nullptr);  // x += A'y
+    else                rc = LSQR_B200_ERR_MODE;                                                     // :197
+    wk.stream = saved;
+    return rc;
+}
+
+int lsqr_b200_ez_aprod(lsqr_b200_ez *me, int32_t mode, int32_t m, int32_t n, double *x, double *y)
+{
+    if (!me) return LSQR_B200_ERR_ARG;
+    if (m != me->m || n != me->n) return LSQR_B200_ERR_NOINIT;
+    if (mode != 1 && mode != 2) return LSQR_B200_ERR_MODE;
+    if (!x || !y) return LSQR_B200_ERR_ARG;
+    Work &wk = me->wk;
+    LSQRB_CUDA(cudaSetDevice(wk.device));
+    double *dx = x, *dy = y;
+    const bool xdev = is_device_ptr(x), ydev = is_device_ptr(y);
+    if (!xdev) {
+        if (!me->tmp_n) LSQRB_CUDA(cudaMalloc(&me->tmp_n, sizeof(double) * (size_t)std::max<int32_t>(n, 1)));
+        dx = me->tmp_n;
+        LSQRB_CUDA(cudaMemcpyAsync(dx, x, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, wk.stream));
+    }
+    if (!ydev) {
+        if (!me->tmp_m) LSQRB_CUDA(cudaMalloc(&me->tmp_m, sizeof(double) * (size_t)std::max<int32_t>(m, 1)));
+        dy = me->tmp_m;
+        LSQRB_CUDA(cudaMemcpyAsync(dy, y, sizeof(double) * (size_t)m, cudaMemcpyHostToDevice, wk.stream));
+    }
+    LSQRB_TRY(lsqr_b200_ez_aprod_device(me, mode, m, n, dx, dy, nullptr));
+    if (mode == 1 && !ydev) LSQRB_CUDA(cudaMemcpyAsync(y, dy, sizeof(double) * (size_t)m, cudaMemcpyDeviceToHost, wk.stream));
+    if (mode == 2 && !xdev) LSQRB_CUDA(cudaMemcpyAsync(x, dx, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, wk.stream));
+    LSQRB_CUDA(cudaStreamSynchronize(wk.stream));
+    return LSQR_B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// solve_ez + LSQR  (src/lsqr.f90:207-259, 432-882) -- fused engine
+// ---------------------------------------------------------------------------------------------
+enum { CLS_APROD = 0, CLS_ATPROD = 1, CLS_UPDATE = 2, CLS_OTHER = 3 };
+
+struct ProfScope {   // profile mode: one event pair around a launch
+    lsqr_b200_ez *me; bool on; size_t slot;
+    ProfScope(lsqr_b200_ez *m, int cls) : me(m), on(m->opt.profile != 0), slot(0)
+    {
+        if (!on) return;
+        if (me->prof_cls.size() >= 4096) { on = false; return; }
+        cudaEvent_t a, b;
+        cudaEventCreate(&a); cudaEventCreate(&b);
+        slot = me->prof_ev.size();
+        me->prof_ev.push_back(a); me->prof_ev.push_back(b);
+        me->prof_cls.push_back(cls);
+        cudaEventRecord(a, me->wk.stream);
+    }
+    ~ProfScope() { if (on) cudaEventRecord(me->prof_ev[slot + 1], me->wk.stream); }
+};
+
+static int allreduce_g(lsqr_b200_ez *me)
+{
+    NcclApi *api = nccl_api();
+    LSQRB_NCCL(api->AllReduce(me->g, me->g, (size_t)me->n + 1, ncclFloat64, ncclSum, me->comm, me->wk.stream));
+    return LSQR_B200_OK;
+}
+
+// one LSQR iteration, enqueued (no host synchronisation)
+static int enqueue_iteration(lsqr_b200_ez *me, bool wantse)
+{
+    Work &wk = me->wk;
+    if (me->opt.world_size > 1) {
+        { ProfScope p(me, CLS_APROD);  LSQRB_TRY(launch_spmv<EPI_FUSED_APROD>(wk, me->A, me->lanes_a, me->v, me->u, me->g + me->n)); }
+        { ProfScope p(me, CLS_ATPROD); LSQRB_TRY(launch_spmv<EPI_STORE>(wk, me->AT, me->lanes_at, me->u, me->g, nullptr)); }
+        { ProfScope p(me, CLS_OTHER);  LSQRB_TRY(allreduce_g(me)); }
+        { ProfScope p(me, CLS_OTHER);
+          vfinish_kernel<false><<<wk.grid_for(me->n, kThreads), kThreads, 0, wk.stream>>>(me->n, me->g, me->v, wk.st);
+          wk.launches++; LSQRB_CUDA(cudaGetLastError()); }
+    } else {
+        { ProfScope p(me, CLS_APROD);  LSQRB_TRY(launch_spmv<EPI_FUSED_APROD>(wk, me->A, me->lanes_a, me->v, me->u, nullptr)); }
+        { ProfScope p(me, CLS_ATPROD); LSQRB_TRY(launch_spmv<EPI_FUSED_ATPROD>(wk, me->AT, me->lanes_at, me->u, me->v, nullptr)); }
+    }
+    { ProfScope p(me, CLS_UPDATE); LSQRB_TRY(launch_update<true>(wk, me->n, me->x, me->w, me->v, me->se, wantse)); }
+    return LSQR_B200_OK;
+}
+
+static int build_graph(lsqr_b200_ez *me, bool wantse)
+{
+    if (me->graph_exec && me->graph_wantse == (int)wantse) return LSQR_B200_OK;
+    if (me->graph_exec) { cudaGraphExecDestroy(me->graph_exec); me->graph_exec = nullptr; }
+    Work &wk = me->wk;
+    cudaGraph_t graph = nullptr;
+    const int64_t saved = wk.launches;
+    LSQRB_CUDA(cudaStreamBeginCapture(wk.stream, cudaStreamCaptureModeThreadLocal));
+    int rc = LSQR_B200_OK;
+    for (int i = 0; i < me->batch && rc == LSQR_B200_OK; ++i) rc = enqueue_iteration(me, wantse);
+    cudaError_t e = cudaStreamEndCapture(wk.stream, &graph);
+    wk.launches = saved;
+    if (rc != LSQR_B200_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+    LSQRB_CUDA(e);
+    LSQRB_CUDA(cudaGraphInstantiate(&me->graph_exec, graph, 0));
+    cudaGraphDestroy(graph);
+    me->graph_wantse = (int)wantse;
+    return LSQR_B200_OK;
+}
+
+static int ez_solve_fused(lsqr_b200_ez *me, const double *b, double damp, double *x, int32_t *istop,
+                          double *se, int32_t *itn, double *anorm, double *acond,
+                          double *rnorm, double *arnorm, double *xnorm)
+{
+    Work &wk = me->wk;
+    const int64_t m = me->m, n = me->n;
+    const bool wantse = se != nullptr;
+    const bool dist = me->opt.world_size > 1;
+    LSQRB_CUDA(cudaSetDevice(wk.device));
+    if (wantse && !me->se) LSQRB_CUDA(cudaMalloc(&me->se, sizeof(double) * (size_t)std::max<int64_t>(n, 1)));
+    wk.launches = 0;
+    for (auto e : me->prof_ev) cudaEventDestroy(e);
+    me->prof_ev.clear(); me->prof_cls.clear();
+
+    LogCtx lc;
+    lc.log = me->opt.log; lc.log_user = me->opt.log_user; lc.iter = me->opt.iter; lc.iter_user = me->opt.iter_user;
+    lc.m = dist && me->opt.m_global > 0 ? me->opt.m_global : m; lc.n = n; lc.damp = damp;
+    lc.atol = me->opt.atol; lc.btol = me->opt.btol; lc.conlim = me->opt.conlim;
+    lc.ctol = me->opt.conlim > 0.0 ? 1.0 / me->opt.conlim : 0.0;
+    lc.itnlim = me->opt.itnlim; lc.wantse = wantse;
+    lc.header();
+
+    LSQRB_CUDA(cudaEventRecord(me->ev_t0, wk.stream));
+    LSQRB_TRY(wk.reset_state(damp, me->opt.atol, me->opt.btol, me->opt.conlim, me->opt.itnlim, wantse, dist));
+
+    // u = b (:242); v = 0, x = 0, se = 0 (:621-630)
+    if (m > 0) LSQRB_CUDA(cudaMemcpyAsync(me->u, b, sizeof(double) * (size_t)m, cudaMemcpyDefault, wk.stream));
+    if (n > 0) {
+        LSQRB_CUDA(cudaMemsetAsync(me->v, 0, sizeof(double) * (size_t)n, wk.stream));
+        LSQRB_CUDA(cudaMemsetAsync(me->x, 0, sizeof(double) * (size_t)n, wk.stream));
+        LSQRB_CUDA(cudaMemsetAsync(me->w, 0, sizeof(double) * (size_t)n, wk.stream));
+        if (wantse) LSQRB_CUDA(cudaMemsetAsync(me->se, 0, sizeof(double) * (size_t)n, wk.stream));
+    }
+    // beta = ||u||; v = A'(u/beta); alpha = ||v||; w = v/alpha  (:632-644), lazily normalised
+    if (dist) {
+        sumsq_kernel<POST_NONE><<<wk.grid_for(m, kThreads), kThreads, 0, wk.stream>>>(m, me->u, wk.st, me->g + n);
+        wk.launches++;
+        LSQRB_TRY(launch_spmv<EPI_STORE>(wk, me->AT, me->lanes_at, me->u, me->g, nullptr));
+        LSQRB_TRY(allreduce_g(me));
+        vfinish_kernel<true><<<wk.grid_for(n, kThreads), kThreads, 0, wk.stream>>>(n, me->g, me->v, wk.st);
+        wk.launches++;
+    } else {
+        sumsq_kernel<POST_INIT_BETA><<<wk.grid_for(m, kThreads), kThreads, 0, wk.stream>>>(m, me->u, wk.st, nullptr);
+        wk.launches++;
+        LSQRB_TRY(launch_spmv<EPI_INIT_ATPROD>(wk, me->AT, me->lanes_at, me->u, me->v, nullptr));
+    }
+    init_w_kernel<<<wk.grid_for(n, kThreads), kThreads, 0, wk.stream>>>(n, me->w, me->v, wk.st);
+    record0_kernel<<<1, 1, 0, wk.stream>>>(wk.st, wk.ring_d);
+    wk.launches += 2;
+    LSQRB_CUDA(cudaGetLastError());
+    LSQRB_CUDA(cudaEventRecord(me->ev_t1, wk.stream));
+
+    // ---- iteration loop: enqueue batch j+1, then wait for batch j and look at its records -----
+    const bool use_graph = me->opt.use_graph && !me->opt.profile && !dist;
+    if (use_graph) LSQRB_TRY(build_graph(me, wantse));
+    const int itnlim = std::max(me->opt.itnlim, 1);   // the reference always runs one iteration (:673-676,798)
+    const int B = me->batch;
+    int seen = -1, enq = 0, nb = 0, done_batches = 0;   // records consumed, iterations / batches enqueued, batches finished
+    bool stop = false;
+    auto enqueue_batch = [&]() -> int {
+        if (use_graph) {
+            LSQRB_CUDA(cudaGraphLaunch(me->graph_exec, wk.stream));
+            wk.launches += (int64_t)B * 3;
+        } else {
+            for (int i = 0; i < B; ++i) LSQRB_TRY(enqueue_iteration(me, wantse));
+        }
+        LSQRB_CUDA(cudaEventRecord(wk.ev[nb & 3], wk.stream));
+        enq += B;
+        nb += 1;
+        return LSQR_B200_OK;
+    };
+    auto check = [&](int upto) {
+        stop = drain_ring(wk, lc, seen, upto);
+        if (seen >= 0 && wk.ring_h[0].arnorm == 0.0) stop = true;   // alpha*beta = 0: no iterations (:646-648)
+    };
+    // Keep two batches in flight.  The device stops by itself (done flag; istop = 5 at itnlim), so an
+    // over-enqueued batch is a run of no-op kernels.  Launch decisions depend only on the records of
+    // fully finished batches, which makes them identical on every rank of a multi-GPU run (all ranks
+    // must enqueue the same sequence of all-reduces).
+    while (!stop) {
+        while (nb < done_batches + 2 && enq < itnlim) LSQRB_TRY(enqueue_batch());
+        if (done_batches == nb) {
+            LSQRB_CUDA(cudaStreamSynchronize(wk.stream));
+            check(itnlim);
+            break;
+        }
+        LSQRB_CUDA(cudaEventSynchronize(wk.ev[done_batches & 3]));
+        done_batches += 1;
+        check(std::min(done_batches * B, itnlim));
+    }
+    LSQRB_CUDA(cudaEventRecord(me->ev_t2, wk.stream));
+
+    // se(i) = rnorm/sqrt(t) sqrt(se(i))  (:857-865)
+    if (wantse && n > 0) {
+        const int64_t mg = dist && me->opt.m_global > 0 ? me->opt.m_global : m;
+        double t = 1.0;
+        if (mg > n) t = (double)(mg - n);
+        if (damp > 0.0) t = (double)mg;
+        se_finish_kernel<<<wk.grid_for(n, kThreads), kThreads, 0, wk.stream>>>(n, me->se, wk.st, t);
+        wk.launches++;
+        LSQRB_CUDA(cudaMemcpyAsync(se, me->se, sizeof(double) * (size_t)n, cudaMemcpyDefault, wk.stream));
+    }
+    if (n > 0) LSQRB_CUDA(cudaMemcpyAsync(x, me->x, sizeof(double) * (size_t)n, cudaMemcpyDefault, wk.stream));
+    LSQRB_TRY(wk.fetch_state());
+    // any records the loop did not print yet (e.g. the stopping iteration)
+    drain_ring(wk, lc, seen, wk.h.itn);
+
+    int is = wk.h.istop;
+    if (damp > 0.0 && is == 2) is = 3;   // :871
+    lc.footer(is, wk.h);
+    if (istop) *istop = is;
+    if (itn) *itn = wk.h.itn;
+    if (anorm) *anorm = wk.h.anorm;
+    if (acond) *acond = wk.h.acond;
+    if (rnorm) *rnorm = wk.h.rnorm;
+    if (arnorm) *arnorm = wk.h.arnorm;
+    if (xnorm) *xnorm = wk.h.xnorm;
+
+    // timings
+    float ms = 0.f;
+    me->times.total_launches = wk.launches;
+    if (cudaEventElapsedTime(&ms, me->ev_t0, me->ev_t1) == cudaSuccess) me->times.init_ms = ms;
+    if (cudaEventElapsedTime(&ms, me->ev_t1, me->ev_t2) == cudaSuccess) me->times.loop_ms = ms;
+    if (me->opt.profile) {
+        double acc[4] = {0, 0, 0, 0};
+        int64_t cnt[4] = {0, 0, 0, 0};
+        for (size_t i = 0; i < me->prof_cls.size(); ++i) {
+            if (cudaEventElapsedTime(&ms, me->prof_ev[2 * i], me->prof_ev[2 * i + 1]) == cudaSuccess) {
+                acc[me->prof_cls[i]] += ms;
+                cnt[me->prof_cls[i]] += 1;
+            }
+        }
+        me->times.aprod_ms = cnt[0] ? acc[0] / cnt[0] : 0;   me->times.aprod_launches = cnt[0];
+        me->times.atprod_ms = cnt[1] ? acc[1] / cnt[1] : 0;  me->times.atprod_launches = cnt[1];
+        me->times.update_ms = cnt[2] ? acc[2] / cnt[2] : 0;  me->times.update_launches = cnt[2];
+        me->times.other_ms = cnt[3] ? acc[3] / cnt[3] : 0;   me->times.other_launches = cnt[3];
+    }
+    return LSQR_B200_OK;
+}
+
+static int ez_solve_reference_structure(lsqr_b200_ez *me, const double *b, double damp, double *x, int32_t *istop,
+                                        double *se, int32_t *itn, double *anorm, double *acond,
+                                        double *rnorm, double *arnorm, double *xnorm);
+
+int lsqr_b200_ez_solve(lsqr_b200_ez *me, const double *b, double damp, double *x, int32_t *istop,
+                       double *se, int32_t *itn, double *anorm, double *acond,
+                       double *rnorm, double *arnorm, double *xnorm)
+{
+    if (!me) return LSQR_B200_ERR_ARG;
+    if ((me->m > 0 && !b) || (me->n > 0 && !x)) { set_last_error("NULL b or x"); return LSQR_B200_ERR_ARG; }
+    if (me->opt.engine == 1 && me->opt.world_size == 1)
+        return ez_solve_reference_structure(me, b, damp, x, istop, se, itn, anorm, acond, rnorm, arnorm, xnorm);
+    return ez_solve_fused(me, b, damp, x, istop, se, itn, anorm, acond, rnorm, arnorm, xnorm);
+}
+
+int lsqr_b200_ez_get_kernel_times(const lsqr_b200_ez *me, lsqr_b200_kernel_times *out)
+{
+    if (!me || !out) return LSQR_B200_ERR_ARG;
+    *out = me->times;
+    return LSQR_B200_OK;
+}
+
+}  // extern "C"
+
+// =============================================================================================
+// Operator-hook path: LSQR with the reference's pass structure (dscal / aprod / dnrm2 as
+// separate steps, u and v kept normalised), src/lsqr.f90:432-882
+// =============================================================================================
+namespace lsqrb {
+
+static int scal_dev(Work &wk, int64_t n, double *x, const double *coef)
+{
+    scal_kernel<<<wk.grid_for(n, kThreads), kThreads, 0, wk.stream>>>(n, x, coef, 1.0);
+    wk.launches++;
+    LSQRB_CUDA(cudaGetLastError());
+    return LSQR_B200_OK;
+}
+
+template <int POST>
+static int sumsq_dev(Work &wk, int64_t n, const double *x, double *result)
+{
+    sumsq_kernel<POST><<<wk.grid_for(n, kThreads), kThreads, 0, wk.stream>>>(n, x, wk.st, result);
+    wk.launches++;
+    LSQRB_CUDA(cudaGetLastError());
+    return LSQR_B200_OK;
+}
+
+static int lsqr_with_operator(Work &wk, lsqr_b200_aprod_fn aprod, void *aprod_user,
+                              int32_t m, int32_t n, double damp, int wantse,
+                              double *u, double *v, double *w, double *x, double *se,
+                              double atol, double btol, double conlim, int32_t itnlim,
+                              const lsqr_b200_options *opts,
+                              int32_t *istop, int32_t *itn, double *anorm, double *acond,
+                              double *rnorm, double *arnorm, double *xnorm)
+{
+    LSQRB_CUDA(cudaSetDevice(wk.device));
+    DevState *st = wk.st;
+    LogCtx lc;
+    if (opts) { lc.log = opts->log; lc.log_user = opts->log_user; lc.iter = opts->iter; lc.iter_user = opts->iter_user; }
+    lc.m = m; lc.n = n; lc.damp = damp; lc.atol = atol; lc.btol = btol; lc.conlim = conlim;
+    lc.ctol = conlim > 0.0 ? 1.0 / conlim : 0.0; lc.itnlim = itnlim; lc.wantse = wantse;
+    lc.header();
+    LSQRB_TRY(wk.reset_state(damp, atol, btol, conlim, itnlim, wantse, 0));
+
+    auto call_aprod = [&](int mode) -> int {
+        int rc = aprod(aprod_user, mode, m, n, v, u, (void *)wk.stream);
+        if (rc != 0) { set_last_error("aprod callback returned " + std::to_string(rc)); return LSQR_B200_ERR_CALLBACK; }
+        return LSQR_B200_OK;
+    };
+
+    // :621-644
+    if (n > 0) {
+        LSQRB_CUDA(cudaMemsetAsync(v, 0, sizeof(double) * (size_t)n, wk.stream));
+        LSQRB_CUDA(cudaMemsetAsync(x, 0, sizeof(double) * (size_t)n, wk.stream));
+        if (wantse) LSQRB_CUDA(cudaMemsetAsync(se, 0, sizeof(double) * (size_t)n, wk.stream));
+    }
+    LSQRB_TRY(sumsq_dev<POST_INIT_BETA>(wk, m, u, nullptr));
+    LSQRB_TRY(scal_dev(wk, m, u, &st->g_c1));            // u /= beta
+    LSQRB_TRY(call_aprod(2));                            // v += A'u
+    LSQRB_TRY(sumsq_dev<POST_INIT_ALPHA>(wk, n, v, nullptr));
+    LSQRB_TRY(scal_dev(wk, n, v, &st->g_c3));            // v /= alpha
+    LSQRB_CUDA(cudaMemcpyAsync(w, v, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, wk.stream));   // dcopy
+    record0_kernel<<<1, 1, 0, wk.stream>>>(st, wk.ring_d);
+    wk.launches++;
+    LSQRB_CUDA(cudaStreamSynchronize(wk.stream));
+
+    int seen = -1;
+    bool stop = drain_ring(wk, lc, seen, 0);
+    if (wk.ring_h[0].istop != 0.0 || wk.ring_h[0].arnorm == 0.0) stop = true;   // alpha*beta = 0 (:646)
+    int k = 0;
+    while (!stop && k < itnlim) {
+        ++k;
+        LSQRB_TRY(scal_dev(wk, m, u, &st->g_c0));        // u *= -alpha            (:681)
+        LSQRB_TRY(call_aprod(1));                        // u += A v               (:682)
+        LSQRB_TRY(sumsq_dev<POST_G_BETA>(wk, m, u, nullptr));   // beta, anorm     (:683-689)
+        LSQRB_TRY(scal_dev(wk, m, u, &st->g_c1));        // u /= beta              (:692)
+        LSQRB_TRY(scal_dev(wk, n, v, &st->g_c2));        // v *= -beta             (:693)
+        LSQRB_TRY(call_aprod(2));                        // v += A'u               (:694)
+        LSQRB_TRY(sumsq_dev<POST_G_ALPHA>(wk, n, v, nullptr));  // alpha, rotations, tests (:695-810)
+        LSQRB_TRY(scal_dev(wk, n, v, &st->g_c3));        // v /= alpha             (:697)
+        LSQRB_TRY(launch_update<false>(wk, n, x, w, v, se, wantse != 0));   // (:729-745)
+        LSQRB_CUDA(cudaStreamSynchronize(wk.stream));
+        stop = drain_ring(wk, lc, seen, k);
+    }
+    if (wantse && n > 0) {
+        double t = 1.0;
+        if (m > n) t = (double)(m - n);
+        if (damp > 0.0) t = (double)m;
+        se_finish_kernel<<<wk.grid_for(n, kThreads), kThreads, 0, wk.stream>>>(n, se, st, t);
+        wk.launches++;
+    }
+    LSQRB_TRY(wk.fetch_state());
+    int is = wk.h.istop;
+    if (damp > 0.0 && is == 2) is = 3;
+    lc.footer(is, wk.h);
+    if (istop) *istop = is;
+    if (itn) *itn = wk.h.itn;
+    if (anorm) *anorm = wk.h.anorm;
+    if (acond) *acond = wk.h.acond;
+    if (rnorm) *rnorm = wk.h.rnorm;
+    if (arnorm) *arnorm = wk.h.arnorm;
+    if (xnorm) *xnorm = wk.h.xnorm;
+    return LSQR_B200_OK;
+}
+
+// generators of acheck's "unlikely" vectors (src/lsqr.f90:946-961)
+__global__ void acheck_fill_kernel(int64_t n, double *x, int reciprocal)
+{
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
+        const double t = sqrt((double)(i + 2));
+        x[i] = reciprocal ? 1.0 / t : t;
+    }
+}
+
+__global__ void xcheck_w_kernel(int64_t n, double *w, const double *v, const double *x, double dampsq)
+{
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads)
+        w[i] = v[i] - dampsq * x[i];
+}
+
+static int reduce_to_host(Work &wk, int64_t n, const double *x, const double *y, double *out)
+{
+    double *d_res = &wk.st->partial[kMaxPartials - 1];   // last slot is never used as a block partial (grid < kMaxPartials)
+    if (y) dot_kernel<<<std::min(wk.grid_for(n, kThreads), kMaxPartials - 1), kThreads, 0, wk.stream>>>(n, x, y, wk.st, d_res);
+    else   sumsq_kernel<POST_NONE><<<std::min(wk.grid_for(n, kThreads), kMaxPartials - 1), kThreads, 0, wk.stream>>>(n, x, wk.st, d_res);
+    wk.launches++;
+    LSQRB_CUDA(cudaGetLastError());
+    LSQRB_CUDA(cudaMemcpyAsync(out, d_res, sizeof(double), cudaMemcpyDeviceToHost, wk.stream));
+    LSQRB_CUDA(cudaStreamSynchronize(wk.stream));
+    return LSQR_B200_OK;
+}
+
+static int scal_imm(Work &wk, int64_t n, double *x, double a)
+{
+    scal_kernel<<<wk.grid_for(n, kThreads), kThreads, 0, wk.stream>>>(n, x, nullptr, a);
+    wk.launches++;
+    LSQRB_CUDA(cudaGetLastError());
+    return LSQR_B200_OK;
+}
+
+struct ScopedWork {   // a Work for handle-less entry points
+    Work wk;
+    bool ok = false;
+    int rc;
+    ScopedWork(const lsqr_b200_options *o, void *stream_override = nullptr)
+    {
+        rc = wk.init(o ? o->device : -1, stream_override ? stream_override : (o ? o->stream : nullptr));
+        ok = rc == LSQR_B200_OK;
+    }
+    ~ScopedWork() { wk.destroy(); }
+};
+
+}  // namespace lsqrb
+
+static int ez_solve_reference_structure(lsqr_b200_ez *me, const double *b, double damp, double *x, int32_t *istop,
+                                        double *se, int32_t *itn, double *anorm, double *acond,
+                                        double *rnorm, double *arnorm, double *xnorm)
+{
+    Work &wk = me->wk;
+    const int64_t m = me->m, n = me->n;
+    const bool wantse = se != nullptr;
+    LSQRB_CUDA(cudaSetDevice(wk.device));
+    if (wantse && !me->se) LSQRB_CUDA(cudaMalloc(&me->se, sizeof(double) * (size_t)std::max<int64_t>(n, 1)));
+    wk.launches = 0;
+    if (m > 0) LSQRB_CUDA(cudaMemcpyAsync(me->u, b, sizeof(double) * (size_t)m, cudaMemcpyDefault, wk.stream));
+    lsqr_b200_options o = me->opt;
+    LSQRB_TRY(lsqr_with_operator(wk, lsqr_b200_ez_aprod_device, me, me->m, me->n, damp, wantse,
+                                 me->u, me->v, me->w, me->x, me->se,
+                                 me->opt.atol, me->opt.btol, me->opt.conlim, me->opt.itnlim, &o,
+                                 istop, itn, anorm, acond, rnorm, arnorm, xnorm));
+    if (n > 0) LSQRB_CUDA(cudaMemcpyAsync(x, me->x, sizeof(double) * (size_t)n, cudaMemcpyDefault, wk.stream));
+    if (wantse && n > 0) LSQRB_CUDA(cudaMemcpyAsync(se, me->se, sizeof(double) * (size_t)n, cudaMemcpyDefault, wk.stream));
+    LSQRB_CUDA(cudaStreamSynchronize(wk.stream));
+    me->times.total_launches = wk.launches;
+    return LSQR_B200_OK;
+}
+
+extern "C" {
+
+int lsqr_b200_lsqr(lsqr_b200_aprod_fn aprod, void *aprod_user,
+                   int32_t m, int32_t n, double damp, int32_t wantse,
+                   double *u, double *v, double *w, double *x, double *se,
+                   double atol, double btol, double conlim, int32_t itnlim,
+                   const lsqr_b200_options *opts,
+                   int32_t *istop, int32_t *itn, double *anorm, double *acond,
+                   double *rnorm, double *arnorm, double *xnorm)
+{
+    if (!aprod || m < 0 || n < 0) return LSQR_B200_ERR_ARG;
+    if ((m > 0 && !u) || (n > 0 && (!v || !w || !x)) || (wantse && n > 0 && !se)) {
+        set_last_error("NULL work vector");
+        return LSQR_B200_ERR_ARG;
+    }
+    ScopedWork sw(opts);
+    if (!sw.ok) return sw.rc;
+    return lsqr_with_operator(sw.wk, aprod, aprod_user, m, n, damp, wantse, u, v, w, x, se,
+                              atol, btol, conlim, itnlim, opts, istop, itn, anorm, acond, rnorm, arnorm, xnorm);
+}
+
+// acheck, src/lsqr.f90:908-994
+int lsqr_b200_acheck(lsqr_b200_aprod_fn aprod, void *aprod_user, int32_t m, int32_t n,
+                     double eps, double *v, double *w, double *x, double *y,
+                     const lsqr_b200_options *opts, int32_t *inform, double *relerr)
+{
+    if (!aprod || m < 1 || n < 1 || !v || !w || !x || !y) return LSQR_B200_ERR_ARG;
+    ScopedWork sw(opts);
+    if (!sw.ok) return sw.rc;
+    Work &wk = sw.wk;
+    const double tol = pow(eps, 0.5);   // power = 0.5 (:927)
+    if (opts && opts->log) { opts->log(opts->log_user, ""); opts->log(opts->log_user, ""); opts->log(opts->log_user, "Enter acheck. Test of aprod for LSQR and CRAIG"); }
+    acheck_fill_kernel<<<wk.grid_for(n, kThreads), kThreads, 0, wk.stream>>>(n, x, 0);
+    acheck_fill_kernel<<<wk.grid_for(m, kThreads), kThreads, 0, wk.stream>>>(m, y, 1);
+    double alfa, beta;
+    LSQRB_TRY(reduce_to_host(wk, n, x, nullptr, &alfa));
+    LSQRB_TRY(reduce_to_host(wk, m, y, nullptr, &beta));
+    alfa = sqrt(alfa); beta = sqrt(beta);
+    LSQRB_TRY(scal_imm(wk, n, x, 1.0 / alfa));
+    LSQRB_TRY(scal_imm(wk, m, y, 1.0 / beta));
+    LSQRB_CUDA(cudaMemcpyAsync(w, y, sizeof(double) * (size_t)m, cudaMemcpyDeviceToDevice, wk.stream));
+    LSQRB_CUDA(cudaMemcpyAsync(v, x, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, wk.stream));
+    if (aprod(aprod_user, 1, m, n, x, w, (void *)wk.stream) != 0) return LSQR_B200_ERR_CALLBACK;   // w = y + A x
+    if (aprod(aprod_user, 2, m, n, v, y, (void *)wk.stream) != 0) return LSQR_B200_ERR_CALLBACK;   // v = x + A'y
+    LSQRB_TRY(reduce_to_host(wk, m, y, w, &alfa));   // y'w
+    LSQRB_TRY(reduce_to_host(wk, n, x, v, &beta));   // x'v
+    const double test1 = fabs(alfa - beta);
+    const double test2 = 1.0 + fabs(alfa) + fabs(beta);
+    const double test3 = test1 / test2;
+    if (inform) *inform = test3 <= tol ? 0 : 1;
+    if (relerr) *relerr = test3;
+    if (opts && opts->log) {
+        std::string s = (test3 <= tol ? "aprod seems OK. Relative error = " : "aprod seems incorrect. Relative error = ") + fe(10, 1, test3);
+        opts->log(opts->log_user, s.c_str());
+    }
+    return LSQR_B200_OK;
+}
+
+// xcheck, src/lsqr.f90:1015-1154
+int lsqr_b200_xcheck(lsqr_b200_aprod_fn aprod, void *aprod_user, int32_t m, int32_t n,
+                     double anorm, double damp, double eps,
+                     const double *b, double *u, double *v, double *w, const double *x,
+                     const lsqr_b200_options *opts,
+                     int32_t *inform, double *test1, double *test2, double *test3, double *norms)
+{
+    if (!aprod || m < 1 || n < 1 || !b || !u || !v || !w || !x) return LSQR_B200_ERR_ARG;
+    ScopedWork sw(opts);
+    if (!sw.ok) return sw.rc;
+    Work &wk = sw.wk;
+    const double dampsq = damp * damp;
+    const double tol = pow(eps, 0.5);
+    double *xtmp = nullptr;   // the reference copies x because aprod's x is intent(inout) (:1064)
+    LSQRB_CUDA(cudaMalloc(&xtmp, sizeof(double) * (size_t)n));
+    LSQRB_CUDA(cudaMemcpyAsync(xtmp, x, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, wk.stream));
+    // u = b - A x via u = -b + A x, u = -u (:1069-1076)
+    LSQRB_CUDA(cudaMemcpyAsync(u, b, sizeof(double) * (size_t)m, cudaMemcpyDeviceToDevice, wk.stream));
+    LSQRB_TRY(scal_imm(wk, m, u, -1.0));
+    int rc = aprod(aprod_user, 1, m, n, xtmp, u, (void *)wk.stream);
+    if (rc == 0) rc = scal_imm(wk, m, u, -1.0);
+    // v = A'u (:1080-1083)
+    if (rc == 0) rc = cudaMemsetAsync(v, 0, sizeof(double) * (size_t)n, wk.stream) == cudaSuccess ? 0 : LSQR_B200_ERR_CUDA;
+    if (rc == 0) rc = aprod(aprod_user, 2, m, n, v, u, (void *)wk.stream);
+    cudaStreamSynchronize(wk.stream);
+    cudaFree(xtmp);
+    if (rc != 0) return rc == LSQR_B200_ERR_CUDA ? rc : LSQR_B200_ERR_CALLBACK;
+    // w = A'u - damp^2 x (:1089-1094)
+    xcheck_w_kernel<<<wk.grid_for(n, kThreads), kThreads, 0, wk.stream>>>(n, w, v, x, damp != 0.0 ? dampsq : 0.0);
+    double bnorm, xnorm, rho1, sigma1, rho2, sigma2;
+    LSQRB_TRY(reduce_to_host(wk, m, b, nullptr, &bnorm));
+    LSQRB_TRY(reduce_to_host(wk, n, x, nullptr, &xnorm));
+    LSQRB_TRY(reduce_to_host(wk, m, u, nullptr, &rho1));
+    LSQRB_TRY(reduce_to_host(wk, n, v, nullptr, &sigma1));
+    bnorm = sqrt(bnorm); xnorm = sqrt(xnorm); rho1 = sqrt(rho1); sigma1 = sqrt(sigma1);
+    if (damp == 0.0) {
+        rho2 = rho1;
+        sigma2 = sigma1;
+    } else {
+        rho2 = sqrt(rho1 * rho1 + dampsq * (xnorm * xnorm));
+        LSQRB_TRY(reduce_to_host(wk, n, w, nullptr, &sigma2));
+        sigma2 = sqrt(sigma2);
+    }
+    int inf;
+    double t1 = 0, t2 = 0, t3 = 0;
+    if (bnorm == 0.0 && xnorm == 0.0) {
+        inf = 0;
+    } else {
+        inf = 4;
+        t1 = rho1 / (bnorm + anorm * xnorm);
+        t2 = 0.0;
+        if (rho1 > 0.0) t2 = sigma1 / (anorm * rho1);
+        t3 = t2;
+        if (rho2 > 0.0) t3 = sigma2 / (anorm * rho2);
+        if (t3 <= tol) inf = 3;
+        if (t2 <= tol) inf = 2;
+        if (t1 <= tol) inf = 1;
+    }
+    if (inform) *inform = inf;
+    if (test1) *test1 = t1;
+    if (test2) *test2 = t2;
+    if (test3) *test3 = t3;
+    if (norms) { norms[0] = bnorm; norms[1] = xnorm; norms[2] = rho1; norms[3] = sigma1; norms[4] = rho2; norms[5] = sigma2; }
+    if (opts && opts->log) {
+        auto L = [&](const std::string &s) { opts->log(opts->log_user, s.c_str()); };
+        L(""); L("");
+        L("Enter xcheck. Does x solve Ax = b, etc?");
+        L(" damp            =" + fe(10, 3, damp));
+        L(" norm(x)         =" + fe(10, 3, xnorm));
+        L(" norm(r)         =" + fe(15, 8, rho1) + " = rho1");
+        L(" norm(A'r)       =" + fe(10, 3, sigma1) + "      = sigma1");
+        if (damp != 0.0) {
+            L("");
+            L(" norm(s)         =" + fe(10, 3, rho1 / damp));
+            L(" norm(x,s)       =" + fe(10, 3, rho2 / damp));
+            L(" norm(rbar)      =" + fe(15, 8, rho2) + " = rho2");
+            L(" norm(Abar'rbar) =" + fe(10, 3, sigma2) + "      = sigma2");
+        }
+        L("");
+        char buf[64];
+        snprintf(buf, sizeof buf, " inform          =%2d", inf);
+        L(buf);
+        L(" tol             =" + fe(10, 3, tol));
+        L(" test1           =" + fe(10, 3, t1) + " (Ax = b)");
+        L(" test2           =" + fe(10, 3, t2) + " (least-squares)");
+        L(" test3           =" + fe(10, 3, t3) + " (damped least-squares)");
+    }
+    return LSQR_B200_OK;
+}
+
+// ---- device BLAS-1 (src/lsqrblas.f90), stride 1 ------------------------------------------------
+int lsqr_b200_dnrm2(int64_t n, const double *x, double *result, void *stream)
+{
+    if (!result || n < 0 || (n > 0 && !x)) return LSQR_B200_ERR_ARG;
+    if (n < 1) { *result = 0.0; return LSQR_B200_OK; }   // :131
+    ScopedWork sw(nullptr, stream);
+    if (!sw.ok) return sw.rc;
+    double s;
+    LSQRB_TRY(reduce_to_host(sw.wk, n, x, nullptr, &s));
+    *result = sqrt(s);
+    return LSQR_B200_OK;
+}
+
+int lsqr_b200_ddot(int64_t n, const double *x, const double *y, double *result, void *stream)
+{
+    if (!result || n < 0 || (n > 0 && (!x || !y))) return LSQR_B200_ERR_ARG;
+    if (n < 1) { *result = 0.0; return LSQR_B200_OK; }
+    ScopedWork sw(nullptr, stream);
+    if (!sw.ok) return sw.rc;
+    return reduce_to_host(sw.wk, n, x, y, result);
+}
+
+int lsqr_b200_dscal(int64_t n, double da, double *x, void *stream)
+{
+    if (n < 0 || (n > 0 && !x)) return LSQR_B200_ERR_ARG;
+    if (n == 0) return LSQR_B200_OK;
+    ScopedWork sw(nullptr, stream);
+    if (!sw.ok) return sw.rc;
+    LSQRB_TRY(scal_imm(sw.wk, n, x, da));
+    LSQRB_CUDA(cudaStreamSynchronize(sw.wk.stream));
+    return LSQR_B200_OK;
+}
+
+int lsqr_b200_dcopy(int64_t n, const double *x, double *y, void *stream)
+{
+    if (n < 0 || (n > 0 && (!x || !y))) return LSQR_B200_ERR_ARG;
+    if (n == 0) return LSQR_B200_OK;
+    int count = lsqr_b200_device_count();
+    if (count == 0) return LSQR_B200_ERR_NO_DEVICE;
+    LSQRB_CUDA(cudaMemcpyAsync(y, x, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    LSQRB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return LSQR_B200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,401 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on identical inputs.
+
+Contract (BASELINE.json north_star): CSR / CSR' / permutation arrays bit-exact; istop identical;
+iteration count within +-2; relative difference in x, ||r|| and ||A'r|| <= 1e-10 on
+well-conditioned problems (reduction order differs, so floating point is not bit-exact).
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import oracle as O   # the checker (test infrastructure)
+
+RTOL = 1e-10   # north_star tolerance for x, rnorm, ||A'r||
+
+
+@pytest.fixture(scope="module")
+def lb():
+    import lsqr_b200
+    assert lsqr_b200.device_count() > 0, "no CUDA device"
+    return lsqr_b200
+
+
+def relerr(a, b):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+def true_residuals(irow, icol, a, m, n, x, b, damp=0.0):
+    """||b - A x|| and ||A'r - damp^2 x|| recomputed from x the way xcheck does (src/lsqr.f90:1073-1101)."""
+    r = b.copy()
+    np.subtract.at(r, irow - 1, a * x[icol - 1])
+    atr = np.zeros(n)
+    np.add.at(atr, icol - 1, a * r[irow - 1])
+    return np.linalg.norm(r), np.linalg.norm(atr - damp * damp * x)
+
+
+def ez1():
+    a = np.array([1, 4, 7, 2, 5, 88, 3, 66, 9], float)
+    icol = np.array([1, 1, 1, 2, 2, 2, 3, 3, 3], np.int32)
+    irow = np.array([1, 2, 3] * 3, np.int32)
+    return 3, 3, a, irow, icol, np.array([1.0, 2.0, 3.0])
+
+
+def ez2():
+    a = np.array([4.1, 1.1, 11.1, 5.1, -3.1, 3.1, 66.1, 8.1, -87.1, 0.1, -9.1, 2.1])
+    icol = np.array([1, 1, 1, 2, 2, 2, 3, 3, 3, 4, 4, 4], np.int32)
+    irow = np.array([1, 2, 3] * 4, np.int32)
+    return 3, 4, a, irow, icol, np.array([1.0, 2.0, 3.0])
+
+
+# ------------------------------------------------------------------ the reference's own ez tests
+@pytest.mark.parametrize("case", [ez1, ez2], ids=["test_1", "test_2"])
+@pytest.mark.parametrize("engine", [0, 1], ids=["fused", "refstruct"])
+def test_ez_kats(lb, case, engine):
+    m, n, a, irow, icol, b = case()
+    s = lb.LsqrSolverEz().initialize(m, n, a, irow, icol, itnlim=100, engine=engine)
+    r = s.solve(b, 0.0)
+    ref = O.SolverEz(m, n, a, irow, icol, itnlim=100).solve(b, 0.0)
+    A = a.reshape(m, n, order="F")
+    assert np.max(np.abs(A @ r.x - b)) <= 1e-12          # test/lsqrtest_ez.f90:50,102
+    assert r.istop == ref.istop == 1                      # README.md:56
+    assert abs(r.itn - ref.itn) <= 2
+    assert relerr(r.x, ref.x) <= RTOL
+    assert abs(r.anorm - ref.anorm) <= 1e-9 * ref.anorm
+    assert abs(r.xnorm - ref.xnorm) <= 1e-9 * ref.xnorm
+
+
+def test_readme_example(lb):
+    m, n, a, irow, icol, b = ez1()
+    r = lb.LsqrSolverEz().initialize(m, n, a, irow, icol).solve(b, 0.0)     # README.md:44-45, defaults
+    assert r.istop == 1
+    np.testing.assert_allclose(r.x, [1.242424e0, -6.060606e-2, -4.040404e-2], rtol=5e-7)   # README.md:57
+
+
+# ------------------------------------------------------------------ K0: validation / error stops
+def test_error_stops(lb):
+    S = lb.LsqrSolverEz
+    with pytest.raises(lb.LsqrError, match="invalid a,icol,irow sizes in initialize_ez") as e:
+        S().initialize(2, 2, [1.0, 2.0], [1], [1, 2])
+    assert e.value.code == 1
+    with pytest.raises(lb.LsqrError, match="invalid irow or m in initialize_ez") as e:
+        S().initialize(2, 2, [1.0, 2.0], [1, 3], [1, 2])
+    assert e.value.code == 2
+    with pytest.raises(lb.LsqrError, match="invalid icol or n in initialize_ez") as e:
+        S().initialize(2, 2, [1.0, 2.0], [1, 2], [1, 3])
+    assert e.value.code == 3
+    with pytest.raises(lb.LsqrError) as e:                      # lower bound: UB in the reference, rejected here
+        S().initialize(2, 2, [1.0, 2.0], [0, 2], [1, 2])
+    assert e.value.code == 6
+    s = S().initialize(2, 2, [1.0, 2.0], [1, 2], [1, 2])
+    x, y = np.zeros(2), np.zeros(2)
+    with pytest.raises(lb.LsqrError, match="lsqr_solver_ez class not properly initialized"):
+        s.aprod(1, 3, 2, x, y)
+    with pytest.raises(lb.LsqrError, match="invalid mode in aprod_ez"):
+        s.aprod(3, 2, 2, x, y)
+    with pytest.raises(lb.LsqrError, match="not properly initialized"):
+        S().solve(np.zeros(2))
+
+
+# ------------------------------------------------------------------ K1/K2: CSR build, bit-exact
+def _random_coo(rng, m, n, nnz, sorted_rows=False):
+    irow = rng.integers(1, m + 1, nnz).astype(np.int32)
+    icol = rng.integers(1, n + 1, nnz).astype(np.int32)
+    if sorted_rows:
+        irow = np.sort(irow)
+    a = rng.standard_normal(nnz)
+    return irow, icol, a
+
+
+@pytest.mark.parametrize("m,n,nnz,sorted_rows", [
+    (50, 30, 2000, False),          # many duplicates
+    (1000, 1700, 5000, False),      # empty rows and columns
+    (4096, 4096, 100_000, True),    # row-sorted COO: identity permutation for A
+    (300_000, 70_000, 1_000_000, False),
+    (7, 5, 0, False),               # empty matrix
+    (1, 1, 1, False),
+])
+def test_csr_build_bit_exact(lb, m, n, nnz, sorted_rows):
+    rng = np.random.default_rng(nnz + m)
+    irow, icol, a = _random_coo(rng, m, n, nnz, sorted_rows)
+    s = lb.LsqrSolverEz().initialize(m, n, a, irow, icol)
+    for transpose, nkeys in ((False, m), (True, n)):
+        ptr, idx, val, perm = s.get_csr(transpose)
+        rptr, ridx, rval, rperm = O.coo_to_csr(nkeys, irow, icol, a, by_col=transpose)
+        np.testing.assert_array_equal(ptr, rptr)
+        np.testing.assert_array_equal(perm, rperm)
+        np.testing.assert_array_equal(idx, ridx)
+        assert val.tobytes() == rval.tobytes()          # bit-exact, including signed zeros / NaN payloads
+
+
+def test_csr_build_from_device_pointers(lb):
+    import torch
+    rng = np.random.default_rng(5)
+    m, n, nnz = 3000, 2000, 50_000
+    irow, icol, a = _random_coo(rng, m, n, nnz)
+    s = lb.LsqrSolverEz().initialize(m, n, torch.from_numpy(a).cuda(), torch.from_numpy(irow).cuda(),
+                                     torch.from_numpy(icol).cuda())
+    ptr, idx, val, perm = s.get_csr(True)
+    rptr, ridx, rval, rperm = O.coo_to_csr(n, irow, icol, a, by_col=True)
+    np.testing.assert_array_equal(perm, rperm)
+    assert val.tobytes() == rval.tobytes()
+
+
+# ------------------------------------------------------------------ K3/K4 plain products (aprod_ez)
+@pytest.mark.parametrize("m,n,per_row", [(2000, 300, 3), (5000, 5000, 12), (400, 9000, 40), (1000, 64, 200)])
+def test_aprod_modes_match_oracle(lb, m, n, per_row):
+    rng = np.random.default_rng(m * 7 + n)
+    nnz = m * per_row
+    irow, icol, a = _random_coo(rng, m, n, nnz)
+    s = lb.LsqrSolverEz().initialize(m, n, a, irow, icol)
+    ref = O.SolverEz(m, n, a, irow, icol)
+    x, y = rng.standard_normal(n), rng.standard_normal(m)
+    y1, yr = y.copy(), y.copy()
+    s.aprod(1, m, n, x, y1)
+    ref.aprod(1, x.copy(), yr)
+    assert relerr(y1, yr) <= 1e-14
+    x2, xr = x.copy(), x.copy()
+    s.aprod(2, m, n, x2, y)
+    ref.aprod(2, xr, y.copy())
+    assert relerr(x2, xr) <= 1e-14
+
+
+# ------------------------------------------------------------------ full solves on the BASELINE workload families
+def _solve_both(lb, cfg, atol, btol, conlim, itnlim, damp=None, shuffle=False, want_se=False, engine=0, **kw):
+    from lsqr_b200 import synth
+    damp = cfg["damp"] if damp is None else damp
+    irow, icol, a = synth.coo_block(cfg["kind"], cfg["seed"], cfg["m"], cfg["n"], cfg["k"])
+    m, n = cfg["m"], cfg["n"]
+    b = synth.rhs_block(irow, icol, a, m, synth.x_true(cfg["seed"], n), cfg["seed"])
+    if shuffle:
+        irow, icol, a = synth.shuffle_coo(irow, icol, a, cfg["seed"])
+    s = lb.LsqrSolverEz().initialize(m, n, a, irow, icol, atol=atol, btol=btol, conlim=conlim, itnlim=itnlim,
+                                     engine=engine, **kw)
+    r = s.solve(b, damp, want_se=want_se, trace=True)
+    ref = O.SolverEz(m, n, a, irow, icol, atol=atol, btol=btol, conlim=conlim, itnlim=itnlim).solve(
+        b, damp, wantse=want_se, trace=True)
+    return (irow, icol, a, b, m, n, damp), r, ref
+
+
+def _assert_parity(data, r, ref, itn_tol=2, rtol=RTOL):
+    irow, icol, a, b, m, n, damp = data
+    assert r.istop == ref.istop
+    assert abs(r.itn - ref.itn) <= itn_tol
+    assert relerr(r.x, ref.x) <= rtol
+    assert abs(r.rnorm - ref.rnorm) <= rtol * ref.rnorm
+    rn, arn = true_residuals(irow, icol, a, m, n, np.asarray(r.x), b, damp)
+    rn_ref, arn_ref = true_residuals(irow, icol, a, m, n, ref.x, b, damp)
+    assert abs(rn - rn_ref) <= rtol * rn_ref
+    # ||A'r|| at convergence is a difference of nearly equal vectors; compare relative to ||A|| ||r||
+    assert abs(arn - arn_ref) <= rtol * ref.anorm * rn_ref
+    assert abs(r.anorm - ref.anorm) <= 1e-9 * ref.anorm
+    assert abs(r.acond - ref.acond) <= 1e-8 * ref.acond
+    assert abs(r.xnorm - ref.xnorm) <= 1e-9 * ref.xnorm
+
+
+@pytest.mark.parametrize("name,scale,shuffle", [
+    ("C2", 10, False), ("C2", 10, True), ("C3", 100, False), ("C4", 100, False), ("C5", 500, False)])
+@pytest.mark.parametrize("tol", [1e-8, 1e-12])
+def test_solve_parity_scaled_configs(lb, name, scale, shuffle, tol):
+    from lsqr_b200 import synth
+    cfg = synth.scaled(name, scale)
+    data, r, ref = _solve_both(lb, cfg, tol, tol, 1e8, 4000, shuffle=shuffle)
+    assert ref.istop in (1, 2, 3)
+    _assert_parity(data, r, ref)
+
+
+def test_solve_parity_c2_full_size(lb):
+    from lsqr_b200 import synth
+    data, r, ref = _solve_both(lb, synth.CONFIGS["C2"], 1e-10, 1e-10, 1e8, 1000)
+    _assert_parity(data, r, ref)
+
+
+@pytest.mark.parametrize("engine", [0, 1], ids=["fused", "refstruct"])
+def test_iteration_trace_matches_oracle(lb, engine):
+    """Every per-iteration scalar of the device recurrence against the oracle's (first 20 iterations)."""
+    from lsqr_b200 import synth
+    cfg = synth.scaled("C3", 200)
+    data, r, ref = _solve_both(lb, cfg, 1e-12, 1e-12, 1e8, 20, engine=engine)
+    assert r.itn == ref.itn == 20 and r.istop == ref.istop == 5
+    got = [t for t in r.trace if t["itn"] >= 1]
+    assert len(got) == 20
+    for g, w in zip(got, ref.trace):
+        assert int(g["itn"]) == w["itn"]
+        for key in ("x1", "rnorm", "test1", "test2", "anorm", "acond", "phi", "dknorm", "dxk", "alfopt",
+                    "alpha", "beta", "xnorm", "arnorm"):
+            assert abs(g[key] - w[key]) <= 1e-9 * max(abs(w[key]), 1e-300), (key, g["itn"], g[key], w[key])
+
+
+def test_fused_equals_reference_structure_engine(lb):
+    from lsqr_b200 import synth
+    cfg = synth.scaled("C2", 20)
+    _, r0, _ = _solve_both(lb, cfg, 1e-10, 1e-10, 1e8, 500, engine=0)
+    _, r1, _ = _solve_both(lb, cfg, 1e-10, 1e-10, 1e8, 500, engine=1)
+    assert r0.istop == r1.istop and abs(r0.itn - r1.itn) <= 1
+    assert relerr(r0.x, r1.x) <= RTOL
+
+
+def test_graph_and_plain_launch_paths_agree_bitwise(lb):
+    from lsqr_b200 import synth
+    cfg = synth.scaled("C2", 20)
+    _, r0, _ = _solve_both(lb, cfg, 1e-10, 1e-10, 1e8, 500, use_graph=True)
+    _, r1, _ = _solve_both(lb, cfg, 1e-10, 1e-10, 1e8, 500, use_graph=False)
+    assert r0.itn == r1.itn and r0.istop == r1.istop
+    assert np.asarray(r0.x).tobytes() == np.asarray(r1.x).tobytes()      # deterministic reductions
+
+
+def test_repeated_solves_are_deterministic_and_reusable(lb):
+    from lsqr_b200 import synth
+    cfg = synth.scaled("C2", 20)
+    irow, icol, a = synth.coo_block(cfg["kind"], cfg["seed"], cfg["m"], cfg["n"], cfg["k"])
+    b = synth.rhs_block(irow, icol, a, cfg["m"], synth.x_true(1, cfg["n"]), 1)
+    s = lb.LsqrSolverEz().initialize(cfg["m"], cfg["n"], a, irow, icol, atol=1e-10, btol=1e-10, itnlim=500)
+    r1 = s.solve(b, 0.0)
+    x1 = np.array(r1.x)
+    r2 = s.solve(2.0 * b, 0.0)                      # new rhs on the same handle (src/lsqr.f90:239-240)
+    r3 = s.solve(b, 0.0)
+    assert np.array(r3.x).tobytes() == x1.tobytes() and r3.itn == r1.itn
+    assert relerr(r2.x, 2.0 * x1) <= 1e-9
+
+
+# ------------------------------------------------------------------ damping, standard errors, stop codes
+def test_damped_solve_and_standard_errors(lb):
+    from lsqr_b200 import synth
+    cfg = synth.scaled("C3", 100)
+    data, r, ref = _solve_both(lb, cfg, 1e-10, 1e-10, 1e8, 2000, damp=1e-2, want_se=True)
+    assert ref.istop == 3                               # damped least squares (src/lsqr.f90:871)
+    _assert_parity(data, r, ref)
+    assert relerr(r.se, ref.se) <= 1e-8                 # unpinned in the reference: oracle-only parity
+
+
+def test_standard_errors_undamped_refstruct(lb):
+    from lsqr_b200 import synth
+    cfg = synth.scaled("C2", 50)
+    data, r, ref = _solve_both(lb, cfg, 1e-10, 1e-10, 1e8, 2000, want_se=True, engine=1)
+    _assert_parity(data, r, ref)
+    assert relerr(r.se, ref.se) <= 1e-8
+
+
+def test_istop_0_zero_rhs(lb):
+    m, n, a, irow, icol, b = ez1()
+    r = lb.LsqrSolverEz().initialize(m, n, a, irow, icol).solve(np.zeros(3), 0.0)
+    ref = O.SolverEz(m, n, a, irow, icol).solve(np.zeros(3), 0.0)
+    assert r.istop == ref.istop == 0 and r.itn == ref.itn == 0
+    assert np.all(np.asarray(r.x) == 0.0)
+    assert r.anorm == 0.0 and r.acond == 0.0 and r.xnorm == 0.0 and r.arnorm == 0.0
+
+
+def test_istop_0_rhs_orthogonal_to_range(lb):
+    # A'b = 0 with b != 0: alpha = 0 -> istop 0, x = 0; rnorm = ||b|| (documented deviation: the reference
+    # leaves rnorm unassigned on this path, src/lsqr.f90:646-653)
+    a = np.array([1.0, 1.0]); irow = np.array([1, 2], np.int32); icol = np.array([1, 1], np.int32)
+    b = np.array([1.0, -1.0])
+    r = lb.LsqrSolverEz().initialize(2, 1, a, irow, icol).solve(b, 0.0)
+    assert r.istop == 0 and r.itn == 0 and r.x[0] == 0.0
+    assert abs(r.rnorm - np.sqrt(2.0)) < 1e-15
+
+
+def test_istop_5_iteration_limit(lb):
+    from lsqr_b200 import synth
+    cfg = synth.scaled("C2", 50)
+    for lim in (1, 3, 8, 9, 17):                        # around the enqueue batch size
+        data, r, ref = _solve_both(lb, cfg, 0.0, 0.0, 0.0, lim)
+        assert r.istop == ref.istop == 5 and r.itn == ref.itn == lim
+        assert relerr(r.x, ref.x) <= RTOL
+
+
+def test_istop_4_condition_limit(lb):
+    from lsqr_b200 import synth
+    cfg = synth.scaled("C2", 50)
+    data, r, ref = _solve_both(lb, cfg, 0.0, 0.0, 5.0, 500)
+    assert r.istop == ref.istop == 4 and abs(r.itn - ref.itn) <= 1
+
+
+def test_istop_2_incompatible_least_squares(lb):
+    from lsqr_b200 import synth
+    cfg = synth.scaled("C2", 50)
+    data, r, ref = _solve_both(lb, cfg, 1e-9, 1e-14, 1e8, 2000)
+    assert ref.istop == 2
+    _assert_parity(data, r, ref)
+
+
+def test_zero_tolerances_stop_at_machine_precision(lb):
+    # defaults atol = btol = conlim = 0 (src/lsqr.f90:46-51): the 1+t <= 1 tests end the run (:792-804)
+    from lsqr_b200 import synth
+    cfg = synth.scaled("C2", 100)
+    data, r, ref = _solve_both(lb, cfg, 0.0, 0.0, 0.0, 5000)
+    assert r.istop == ref.istop and r.istop in (1, 2)
+    assert abs(r.itn - ref.itn) <= 6                    # stops inside rounding noise: looser than +-2
+    assert relerr(r.x, ref.x) <= 1e-9
+
+
+# ------------------------------------------------------------------ ragged / degenerate shapes
+def test_underdetermined_and_empty_rows(lb):
+    rng = np.random.default_rng(11)
+    m, n, nnz = 300, 1000, 4000
+    irow, icol, a = _random_coo(rng, m, n, nnz)
+    irow[irow == 7] = 8                                  # row 7 is empty
+    icol[icol == 13] = 14                                # column 13 is empty
+    b = rng.standard_normal(m)
+    r = lb.LsqrSolverEz().initialize(m, n, a, irow, icol, atol=1e-12, btol=1e-12, itnlim=3000).solve(b)
+    ref = O.SolverEz(m, n, a, irow, icol, atol=1e-12, btol=1e-12, itnlim=3000).solve(b)
+    assert r.istop == ref.istop and abs(r.itn - ref.itn) <= 3
+    assert relerr(r.x, ref.x) <= 1e-8                    # random 300x1000: acond ~ 1e2..1e3
+    assert r.x[12] == 0.0                                # the empty column never moves
+
+
+def test_matrix_without_entries(lb):
+    r = lb.LsqrSolverEz().initialize(4, 3, np.zeros(0), np.zeros(0, np.int32), np.zeros(0, np.int32)).solve(np.ones(4))
+    assert r.istop == 0 and r.itn == 0 and np.all(np.asarray(r.x) == 0.0)
+
+
+def test_one_by_one(lb):
+    r = lb.LsqrSolverEz().initialize(1, 1, [4.0], [1], [1]).solve([2.0])
+    ref = O.SolverEz(1, 1, [4.0], [1], [1]).solve([2.0])
+    assert r.istop == ref.istop and r.itn == ref.itn
+    assert abs(r.x[0] - 0.5) < 1e-15
+
+
+def test_device_resident_vectors(lb):
+    import torch
+    from lsqr_b200 import synth
+    cfg = synth.scaled("C2", 50)
+    irow, icol, a = synth.coo_block(cfg["kind"], cfg["seed"], cfg["m"], cfg["n"], cfg["k"])
+    b = synth.rhs_block(irow, icol, a, cfg["m"], synth.x_true(1, cfg["n"]), 1)
+    s = lb.LsqrSolverEz().initialize(cfg["m"], cfg["n"], a, irow, icol, atol=1e-10, btol=1e-10, itnlim=500)
+    rh = s.solve(b, 0.0)
+    rd = s.solve(torch.from_numpy(b).cuda(), 0.0)
+    assert rd.x.is_cuda and rd.itn == rh.itn
+    assert rd.x.cpu().numpy().tobytes() == np.asarray(rh.x).tobytes()
+
+
+# ------------------------------------------------------------------ nout log
+def test_log_lines_follow_reference_format(lb):
+    m, n, a, irow, icol, b = ez1()
+    lines = []
+    r = lb.LsqrSolverEz().initialize(m, n, a, irow, icol, itnlim=100, nout=lines.append).solve(b, 0.0)
+    ref = O.SolverEz(m, n, a, irow, icol, itnlim=100).solve(b, 0.0, log=True)
+    assert r.log == lines
+    # header and column titles are character-identical; numeric rows agree to the printed digits
+    for got, want in zip(lines[:12], ref.log[:12]):
+        assert got == want
+    assert len(lines) == len(ref.log)
+    assert lines[-1] == ref.log[-1]
+    assert any(l.startswith(" Exit  LSQR.       istop  = 1") for l in lines)
+
+
+# ------------------------------------------------------------------ device BLAS-1
+def test_device_blas1(lb):
+    import torch
+    rng = np.random.default_rng(2)
+    for n in (1, 5, 1000, 1_000_003):
+        x = rng.standard_normal(n); y = rng.standard_normal(n)
+        xd, yd = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+        assert abs(lb.dnrm2(n, xd) - O.dnrm2(x)) <= 1e-13 * O.dnrm2(x)
+        assert abs(lb.ddot(n, xd, yd) - O.ddot(x, y)) <= 1e-12 * np.linalg.norm(x) * np.linalg.norm(y)
+        lb.dscal(n, -2.5, xd)
+        np.testing.assert_array_equal(xd.cpu().numpy(), -2.5 * x)
+        lb.dcopy(n, xd, yd)
+        assert torch.equal(xd, yd)
+    assert lb.dnrm2(0, torch.zeros(1, dtype=torch.float64, device="cuda")) == 0.0

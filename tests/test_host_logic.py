@@ -1,0 +1,175 @@
+"""CPU tests of the host logic: the C-ABI library loads and exports every declared symbol, it fails
+loudly without a GPU, the synthetic generators are block-consistent, and the multi-process (gloo,
+world_size 2) launcher logic works."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    import lsqr_b200
+    lib = C.CDLL(lsqr_b200.LIB_PATH)
+    declared = set()
+    for hdr in os.listdir(os.path.join(ROOT, "include")):
+        text = open(os.path.join(ROOT, "include", hdr)).read()
+        declared |= set(re.findall(r"LSQR_B200_API[^;{]*?\b(lsqr_b200_\w+)\s*\(", text))
+    assert len(declared) >= 20
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} is declared in include/ but not exported"
+    nm = subprocess.run(["nm", "-D", "--defined-only", lsqr_b200.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (lsqr_b200_\w+)", nm))
+    assert exported == declared, exported ^ declared
+
+
+def test_error_messages_are_the_reference_error_stops():
+    import lsqr_b200
+    L = lsqr_b200._lib.load()
+    assert L.lsqr_b200_error_message(1) == b"invalid a,icol,irow sizes in initialize_ez"     # src/lsqr.f90:109
+    assert L.lsqr_b200_error_message(2) == b"invalid irow or m in initialize_ez"             # :110
+    assert L.lsqr_b200_error_message(3) == b"invalid icol or n in initialize_ez"             # :111
+    assert L.lsqr_b200_error_message(4) == b"lsqr_solver_ez class not properly initialized"  # :152
+    assert L.lsqr_b200_error_message(5) == b"invalid mode in aprod_ez"                       # :197
+    assert L.lsqr_b200_version() >= 100
+
+
+def test_default_options_match_reference_defaults():
+    import lsqr_b200
+    o = lsqr_b200._lib.default_options()
+    assert (o.atol, o.btol, o.conlim, o.itnlim) == (0.0, 0.0, 0.0, 100)      # src/lsqr.f90:46-51
+    assert o.world_size == 1 and o.use_graph == 1 and o.engine == 0
+
+
+@pytest.mark.skipif(os.path.exists("/dev/nvidia0"), reason="a GPU is present")
+def test_no_cpu_fallback_without_gpu():
+    """On a box without a GPU the product path must fail loudly, never compute on the CPU."""
+    import lsqr_b200
+    assert lsqr_b200.device_count() == 0
+    with pytest.raises(lsqr_b200.LsqrError) as e:
+        lsqr_b200.LsqrSolverEz().initialize(3, 3, [1.0, 2.0, 3.0], [1, 2, 3], [1, 2, 3])
+    assert e.value.code == 10 and "no CPU" in str(e.value)
+    # the size check of initialize_ez precedes everything else, exactly like the reference (:109)
+    with pytest.raises(lsqr_b200.LsqrError) as e:
+        lsqr_b200.LsqrSolverEz().initialize(3, 3, [1.0, 2.0, 3.0], [1, 2], [1, 2, 3])
+    assert e.value.code == 1
+
+
+def test_product_package_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "lsqr_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.replace("oracle/csr_oracle.c", ""), f"{f} mentions the oracle"
+
+
+# ------------------------------------------------------------------ synthetic generators
+@pytest.mark.parametrize("kind,k", [("uniform", 10), ("banded", 50), ("powerlaw", 0)])
+def test_generator_blocks_concatenate_to_the_whole(kind, k):
+    from lsqr_b200 import synth
+    m, n = 5000, 1200
+    irow, icol, a = synth.coo_block(kind, 3, m, n, k)
+    assert irow.dtype == np.int32 and icol.dtype == np.int32
+    assert icol.min() >= 1 and icol.max() <= n and irow.min() == 1 and irow.max() == m
+    assert np.all(np.diff(irow) >= 0)                       # row-sorted
+    parts = [synth.coo_block(kind, 3, m, n, k, r0, r1 - r0) for r0, r1 in ((0, 1700), (1700, 1701), (1701, m))]
+    off = [0, 1700, 1701]
+    np.testing.assert_array_equal(np.concatenate([p[0] + o for p, o in zip(parts, off)]), irow)
+    np.testing.assert_array_equal(np.concatenate([p[1] for p in parts]), icol)
+    np.testing.assert_array_equal(np.concatenate([p[2] for p in parts]), a)
+    if kind == "powerlaw":
+        lens = np.bincount(irow - 1, minlength=m)
+        assert lens.min() >= 1 and lens.max() <= synth.POWERLAW_MAX
+        row_norm2 = np.bincount(irow - 1, weights=a * a)
+        assert row_norm2.max() <= 1.0                       # values are scaled by 1/sqrt(L)
+    if kind == "banded":
+        center = (np.arange(m) * n) // m
+        d = (icol - 1 - center[irow - 1]) % n
+        assert np.all((d <= 100) | (d >= n - 100))
+        assert a.min() >= 0.0
+
+
+def test_b_iter_formula():
+    from lsqr_b200 import synth
+    c = synth.CONFIGS["C2"]
+    assert synth.b_iter_bytes(10_000_000, c["m"], c["n"]) == 274_800_008          # 0.2748 GB
+    c = synth.CONFIGS["C5"]
+    assert synth.b_iter_bytes(2_000_000_000, c["m"], c["n"]) == 51_480_000_008    # 51.48 GB
+
+
+def test_row_partition():
+    from lsqr_b200 import dist
+    for m, world in ((10, 3), (100_000_000, 8), (5, 8), (7, 1)):
+        blocks = [dist.row_block(m, world, r) for r in range(world)]
+        assert blocks[0][0] == 0 and blocks[-1][1] == m
+        assert all(blocks[i][1] == blocks[i + 1][0] for i in range(world - 1))
+        sizes = [b - a for a, b in blocks]
+        assert max(sizes) - min(sizes) <= 1
+    ptr = np.concatenate([[0], np.cumsum([1, 1, 1, 100, 1, 1, 1, 1])])
+    blocks = dist.row_blocks_by_nnz(ptr, 2)
+    assert blocks[0][0] == 0 and blocks[-1][1] == 8 and blocks[0][1] == blocks[1][0]
+
+
+# ------------------------------------------------------------------ world_size-2 gloo tests
+_WORKER = r"""
+import os, sys, numpy as np
+sys.path.insert(0, os.environ["LSQR_ROOT"])
+import torch, torch.distributed as td
+td.init_process_group("gloo")
+rank, world = td.get_rank(), td.get_world_size()
+from lsqr_b200 import dist, synth
+from oracle import oracle as O      # checker: models the engine's multi-GPU data flow on the CPU
+
+# 1. the 128-byte communicator id reaches every rank unchanged
+uid = dist.exchange_unique_id(world, rank, make_id=lambda: bytes(range(128)))
+assert uid == bytes(range(128)), uid
+
+# 2. row-partitioned LSQR (local Aprod, all-reduce of [A_p'u_p | sum u_p^2]) == the serial oracle
+cfg = synth.scaled("C2", 200)
+m, n = cfg["m"], cfg["n"]
+row0, row1 = dist.row_block(m, world, rank)
+irow, icol, a = synth.coo_block(cfg["kind"], cfg["seed"], m, n, cfg["k"], row0, row1 - row0)
+xt = synth.x_true(cfg["seed"], n)
+b_loc = synth.rhs_block(irow, icol, a, row1 - row0, xt, cfg["seed"], row0)
+loc = O.SolverEz(row1 - row0, n, a, irow, icol)
+
+def aprod(mode, m_, n_, x, y):
+    # y is the GLOBAL m-vector here (the model keeps it replicated for simplicity); rows outside the block stay 0
+    if mode == 1:
+        yl = np.zeros(row1 - row0); loc.aprod(1, x, yl)
+        full = np.zeros(m); full[row0:row1] = yl
+        t = torch.from_numpy(full); td.all_reduce(t); y += t.numpy()
+    else:
+        g = np.zeros(n); loc.aprod(2, g, np.ascontiguousarray(y[row0:row1]))
+        t = torch.from_numpy(g); td.all_reduce(t); x += t.numpy()
+
+b_full = np.zeros(m); b_full[row0:row1] = b_loc
+t = torch.from_numpy(b_full); td.all_reduce(t); b_full = t.numpy()
+r = O.lsqr(aprod, m, n, b_full, atol=1e-10, btol=1e-10, conlim=1e8, itnlim=500)
+
+I, J, A = synth.coo_block(cfg["kind"], cfg["seed"], m, n, cfg["k"])
+ref = O.SolverEz(m, n, A, I, J, atol=1e-10, btol=1e-10, conlim=1e8, itnlim=500).solve(b_full)
+assert r.istop == ref.istop and abs(r.itn - ref.itn) <= 2, (r.istop, ref.istop, r.itn, ref.itn)
+assert np.linalg.norm(r.x - ref.x) <= 1e-10 * np.linalg.norm(ref.x)
+xs = [torch.zeros(n, dtype=torch.float64) for _ in range(world)]
+td.all_gather(xs, torch.from_numpy(r.x))
+assert all(torch.equal(xs[0], t) for t in xs)           # every rank holds the identical solution
+td.destroy_process_group()
+print("RANK_OK", rank)
+"""
+
+
+def test_two_process_gloo_row_partition(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    env = dict(os.environ, LSQR_ROOT=ROOT, OMP_NUM_THREADS="1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29611", str(script)],
+                       capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert r.stdout.count("RANK_OK") == 2
