@@ -189,9 +189,16 @@ def _assert_parity(data, r, ref, itn_tol=2, rtol=RTOL):
     assert abs(rn - rn_ref) <= rtol * rn_ref
     # ||A'r|| at convergence is a difference of nearly equal vectors; compare relative to ||A|| ||r||
     assert abs(arn - arn_ref) <= rtol * ref.anorm * rn_ref
-    assert abs(r.anorm - ref.anorm) <= 1e-9 * ref.anorm
-    assert abs(r.acond - ref.acond) <= 1e-8 * ref.acond
-    assert abs(r.xnorm - ref.xnorm) <= 1e-9 * ref.xnorm
+    # anorm / acond / xnorm grow with every iteration: compare them at the last COMMON iteration
+    k = min(r.itn, ref.itn)
+    if k >= 1 and r.trace and ref.trace:
+        g = next(t for t in r.trace if int(t["itn"]) == k)
+        w = next(t for t in ref.trace if t["itn"] == k)
+        for key, tol in (("anorm", 1e-9), ("acond", 1e-8), ("xnorm", 1e-9), ("rnorm", 1e-9)):
+            assert abs(g[key] - w[key]) <= tol * abs(w[key]), (key, k, g[key], w[key])
+    if r.itn == ref.itn:
+        assert abs(r.anorm - ref.anorm) <= 1e-9 * ref.anorm
+        assert abs(r.xnorm - ref.xnorm) <= 1e-9 * ref.xnorm
 
 
 @pytest.mark.parametrize("name,scale,shuffle", [
