@@ -65,13 +65,18 @@ struct DevState {
 
     int itn, istop, nstop, maxdx;
     int done;                // set after the x/w update of the stopping iteration
-    int pad0;
+    int upd_pending;         // the x/w update of iteration rec.itn has not been applied yet (deferred-update engine)
+
+    // scalars of the iteration whose x/w update is still outstanding; published to the host ring
+    // (with x(1)) by step_after_update
+    lsqr_b200_iter_record rec;
 
     // completion counters of the "last block finishes the reduction" pattern
     unsigned int counter[4];
 
     // partial sums of the reducing kernels (fixed slot per block => deterministic final sum)
     double partial[kMaxPartials];
+    double partial2[kMaxPartials];   // second simultaneous reduction (fused Atprod + deferred update)
 };
 
 // ---------------------------------------------------------------------------------------------

@@ -17,6 +17,7 @@
 
 #include "build_csr.h"
 #include "kernels.cuh"
+#include "spmv_stream.cuh"
 
 namespace lsqrb {
 
@@ -112,6 +113,7 @@ struct Work {
     lsqr_b200_iter_record *ring_h = nullptr;      // pinned, mapped
     lsqr_b200_iter_record *ring_d = nullptr;      // device alias of ring_h
     int max_grid = kNumSMs * 8;
+    int stream_grid = kNumSMs * 3;   // persistent CTAs of the tile-streamed kernels (3 x 74 KB of smem per SM)
     int64_t launches = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 
@@ -141,6 +143,7 @@ struct Work {
         int sms = 0;
         LSQRB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
         max_grid = std::min(kMaxPartials, std::max(1, sms) * env_int("LSQR_B200_BLOCKS_PER_SM", 8));
+        stream_grid = std::min(kMaxPartials, std::max(1, sms) * env_int("LSQR_B200_STREAM_CTAS_PER_SM", 3));
         return LSQR_B200_OK;
     }
 
@@ -209,6 +212,55 @@ static int launch_spmv(Work &wk, const Csr &M, int lanes, const double *x, doubl
     case 16: spmv_rowgroup_kernel<16, EPI><<<grid, kThreads, 0, wk.stream>>>(V, x, out, wk.st, aux); break;
     default: spmv_rowgroup_kernel<32, EPI><<<grid, kThreads, 0, wk.stream>>>(V, x, out, wk.st, aux); break;
     }
+    wk.launches++;
+    LSQRB_CUDA(cudaGetLastError());
+    return LSQR_B200_OK;
+}
+
+// ---- variant 2: tile-streamed kernels (spmv_stream.cuh) -----------------------------------------
+struct TileMapOwner {
+    uint2 *tiles = nullptr;
+    int ntiles = 0;
+};
+
+static int build_tile_map(Work &wk, const Csr &M, TileMapOwner *out)
+{
+    const int64_t nt = std::max<int64_t>(1, (M.nnz + kTile - 1) / kTile);
+    out->ntiles = (int)nt;
+    LSQRB_CUDA(cudaMalloc(&out->tiles, sizeof(uint2) * (size_t)(nt + 1)));
+    build_tiles_kernel<<<(int)((nt + 1 + 255) / 256), 256, 0, wk.stream>>>(M.ptr, M.nrows, M.nnz, (int)nt, out->tiles);
+    LSQRB_CUDA(cudaGetLastError());
+    return LSQR_B200_OK;
+}
+
+template <int EPI>
+static int stream_kernel_prepare()
+{
+    static bool done = false;
+    if (!done) {
+        LSQRB_CUDA(cudaFuncSetAttribute(spmv_stream_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStreamSmem));
+        done = true;
+    }
+    return LSQR_B200_OK;
+}
+
+struct StreamExtra {   // operands of the fused deferred update
+    double *ux = nullptr, *uw = nullptr, *use = nullptr;
+};
+
+template <int EPI>
+static int launch_stream(Work &wk, const Csr &M, const TileMapOwner &map, const double *x, double *out, double *aux,
+                         const StreamExtra &ex = StreamExtra())
+{
+    LSQRB_TRY(stream_kernel_prepare<EPI>());
+    StreamArgs a;
+    a.A = CsrView{M.ptr, M.idx, M.val, M.nrows};
+    a.map = TileMap{map.tiles, map.ntiles};
+    a.x = x; a.out = out; a.st = wk.st; a.aux = aux;
+    a.ux = ex.ux; a.uw = ex.uw; a.use = ex.use;
+    a.ring = wk.ring_d;
+    const int grid = std::max(1, std::min(map.ntiles, wk.stream_grid));
+    spmv_stream_kernel<EPI><<<grid, kStreamThreads, kStreamSmem, wk.stream>>>(a);
     wk.launches++;
     LSQRB_CUDA(cudaGetLastError());
     return LSQR_B200_OK;
@@ -364,6 +416,9 @@ struct lsqr_b200_ez {
     int64_t nnz = 0;
     Csr A, AT;
     int lanes_a = 4, lanes_at = 32;
+    TileMapOwner mapA, mapAT;
+    bool stream = true;           // tile-streamed kernels (variant 2) vs sub-warp-per-row (variant 1)
+    bool deferred = true;         // single GPU, variant 2: x/w update fused into the next Atprod (2 kernels / iteration)
     lsqr_b200_options opt;
     double *u = nullptr, *v = nullptr, *w = nullptr, *x = nullptr, *se = nullptr;
     double *g = nullptr;          // multi-GPU: [ A_p'u_p (n) | sum(u_p^2) ]
@@ -387,6 +442,8 @@ static void ez_free(lsqr_b200_ez *me)
     if (me->comm) { NcclApi *a = nccl_api(); if (a) a->CommDestroy(me->comm); }
     csr_free(&me->A);
     csr_free(&me->AT);
+    if (me->mapA.tiles) cudaFree(me->mapA.tiles);
+    if (me->mapAT.tiles) cudaFree(me->mapAT.tiles);
     for (double *p : {me->u, me->v, me->w, me->x, me->se, me->g, me->tmp_m, me->tmp_n}) if (p) cudaFree(p);
     for (auto e : {me->ev_t0, me->ev_t1, me->ev_t2}) if (e) cudaEventDestroy(e);
     for (auto e : me->prof_ev) cudaEventDestroy(e);
@@ -488,6 +545,14 @@ static int ez_initialize_impl(lsqr_b200_ez *me, int64_t nnz, const double *a, co
 
     me->lanes_a = pick_lanes(me->A, "LSQR_B200_LANES_A");
     me->lanes_at = pick_lanes(me->AT, "LSQR_B200_LANES_AT");
+    const int variant = me->opt.spmv_variant ? me->opt.spmv_variant : env_int("LSQR_B200_SPMV_VARIANT", 2);
+    me->stream = variant != 1;
+    me->deferred = me->stream && me->opt.world_size == 1 && env_int("LSQR_B200_DEFERRED_UPDATE", 1) != 0;
+    if (me->stream) {
+        LSQRB_TRY(build_tile_map(wk, me->A, &me->mapA));
+        LSQRB_TRY(build_tile_map(wk, me->AT, &me->mapAT));
+        LSQRB_CUDA(cudaStreamSynchronize(wk.stream));
+    }
 
     const size_t mm = (size_t)std::max<int32_t>(me->m, 1), nn = (size_t)std::max<int32_t>(me->n, 1);
     LSQRB_CUDA(cudaMalloc(&me->u, sizeof(double) * mm));
@@ -589,8 +654,10 @@ int lsqr_b200_ez_aprod_device(void *handle, int32_t mode, int32_t m, int32_t n,
     cudaStream_t saved = wk.stream;
     if (stream) wk.stream = (cudaStream_t)stream;
     int rc;
-    if (mode == 1)      rc = launch_spmv<EPI_ACC>(wk, me->A, me->lanes_a, x_dev, y_dev, nullptr);    // y += A x
-    else if (mode == 2) rc = launch_spmv<EPI_ACC>(wk, me->AT, me->lanes_at, y_dev, x_dev, nullptr);  // x += A'y
+    if (mode == 1)      rc = me->stream ? launch_stream<SEPI_ACC>(wk, me->A, me->mapA, x_dev, y_dev, nullptr)
+                                        : launch_spmv<EPI_ACC>(wk, me->A, me->lanes_a, x_dev, y_dev, nullptr);    // y += A x
+    else if (mode == 2) rc = me->stream ? launch_stream<SEPI_ACC>(wk, me->AT, me->mapAT, y_dev, x_dev, nullptr)
+                                        : launch_spmv<EPI_ACC>(wk, me->AT, me->lanes_at, y_dev, x_dev, nullptr);  // x += A'y
     else                rc = LSQR_B200_ERR_MODE;                                                     // :197
     wk.stream = saved;
     return rc;
@@ -651,20 +718,52 @@ static int allreduce_g(lsqr_b200_ez *me)
     return LSQR_B200_OK;
 }
 
+// the SpMV flavours of one handle
+static int do_aprod_fused(lsqr_b200_ez *me, double *aux)
+{
+    return me->stream ? launch_stream<SEPI_APROD>(me->wk, me->A, me->mapA, me->v, me->u, aux)
+                      : launch_spmv<EPI_FUSED_APROD>(me->wk, me->A, me->lanes_a, me->v, me->u, aux);
+}
+static int do_atprod_store(lsqr_b200_ez *me)
+{
+    return me->stream ? launch_stream<SEPI_STORE>(me->wk, me->AT, me->mapAT, me->u, me->g, nullptr)
+                      : launch_spmv<EPI_STORE>(me->wk, me->AT, me->lanes_at, me->u, me->g, nullptr);
+}
+static int do_atprod_fused(lsqr_b200_ez *me)
+{
+    return me->stream ? launch_stream<SEPI_ATPROD>(me->wk, me->AT, me->mapAT, me->u, me->v, nullptr)
+                      : launch_spmv<EPI_FUSED_ATPROD>(me->wk, me->AT, me->lanes_at, me->u, me->v, nullptr);
+}
+static int do_atprod_init(lsqr_b200_ez *me)
+{
+    return me->stream ? launch_stream<SEPI_INIT_ATPROD>(me->wk, me->AT, me->mapAT, me->u, me->v, nullptr)
+                      : launch_spmv<EPI_INIT_ATPROD>(me->wk, me->AT, me->lanes_at, me->u, me->v, nullptr);
+}
+static int do_atprod_upd(lsqr_b200_ez *me)   // Atprod of this iteration + deferred x/w update of the previous one
+{
+    StreamExtra ex;
+    ex.ux = me->x; ex.uw = me->w; ex.use = me->se;
+    return launch_stream<SEPI_ATPROD_UPD>(me->wk, me->AT, me->mapAT, me->u, me->v, nullptr, ex);
+}
+
 // one LSQR iteration, enqueued (no host synchronisation)
 static int enqueue_iteration(lsqr_b200_ez *me, bool wantse)
 {
     Work &wk = me->wk;
     if (me->opt.world_size > 1) {
-        { ProfScope p(me, CLS_APROD);  LSQRB_TRY(launch_spmv<EPI_FUSED_APROD>(wk, me->A, me->lanes_a, me->v, me->u, me->g + me->n)); }
-        { ProfScope p(me, CLS_ATPROD); LSQRB_TRY(launch_spmv<EPI_STORE>(wk, me->AT, me->lanes_at, me->u, me->g, nullptr)); }
+        { ProfScope p(me, CLS_APROD);  LSQRB_TRY(do_aprod_fused(me, me->g + me->n)); }
+        { ProfScope p(me, CLS_ATPROD); LSQRB_TRY(do_atprod_store(me)); }
         { ProfScope p(me, CLS_OTHER);  LSQRB_TRY(allreduce_g(me)); }
         { ProfScope p(me, CLS_OTHER);
           vfinish_kernel<false><<<wk.grid_for(me->n, kThreads), kThreads, 0, wk.stream>>>(me->n, me->g, me->v, wk.st);
           wk.launches++; LSQRB_CUDA(cudaGetLastError()); }
+    } else if (me->deferred) {
+        { ProfScope p(me, CLS_APROD);  LSQRB_TRY(do_aprod_fused(me, nullptr)); }
+        { ProfScope p(me, CLS_ATPROD); LSQRB_TRY(do_atprod_upd(me)); }
+        return LSQR_B200_OK;
     } else {
-        { ProfScope p(me, CLS_APROD);  LSQRB_TRY(launch_spmv<EPI_FUSED_APROD>(wk, me->A, me->lanes_a, me->v, me->u, nullptr)); }
-        { ProfScope p(me, CLS_ATPROD); LSQRB_TRY(launch_spmv<EPI_FUSED_ATPROD>(wk, me->AT, me->lanes_at, me->u, me->v, nullptr)); }
+        { ProfScope p(me, CLS_APROD);  LSQRB_TRY(do_aprod_fused(me, nullptr)); }
+        { ProfScope p(me, CLS_ATPROD); LSQRB_TRY(do_atprod_fused(me)); }
     }
     { ProfScope p(me, CLS_UPDATE); LSQRB_TRY(launch_update<true>(wk, me->n, me->x, me->w, me->v, me->se, wantse)); }
     return LSQR_B200_OK;
@@ -727,14 +826,14 @@ static int ez_solve_fused(lsqr_b200_ez *me, const double *b, double damp, double
     if (dist) {
         sumsq_kernel<POST_NONE><<<wk.grid_for(m, kThreads), kThreads, 0, wk.stream>>>(m, me->u, wk.st, me->g + n);
         wk.launches++;
-        LSQRB_TRY(launch_spmv<EPI_STORE>(wk, me->AT, me->lanes_at, me->u, me->g, nullptr));
+        LSQRB_TRY(do_atprod_store(me));
         LSQRB_TRY(allreduce_g(me));
         vfinish_kernel<true><<<wk.grid_for(n, kThreads), kThreads, 0, wk.stream>>>(n, me->g, me->v, wk.st);
         wk.launches++;
     } else {
         sumsq_kernel<POST_INIT_BETA><<<wk.grid_for(m, kThreads), kThreads, 0, wk.stream>>>(m, me->u, wk.st, nullptr);
         wk.launches++;
-        LSQRB_TRY(launch_spmv<EPI_INIT_ATPROD>(wk, me->AT, me->lanes_at, me->u, me->v, nullptr));
+        LSQRB_TRY(do_atprod_init(me));
     }
     init_w_kernel<<<wk.grid_for(n, kThreads), kThreads, 0, wk.stream>>>(n, me->w, me->v, wk.st);
     record0_kernel<<<1, 1, 0, wk.stream>>>(wk.st, wk.ring_d);
@@ -752,7 +851,7 @@ static int ez_solve_fused(lsqr_b200_ez *me, const double *b, double damp, double
     auto enqueue_batch = [&]() -> int {
         if (use_graph) {
             LSQRB_CUDA(cudaGraphLaunch(me->graph_exec, wk.stream));
-            wk.launches += (int64_t)B * 3;
+            wk.launches += (int64_t)B * (me->deferred ? 2 : 3);
         } else {
             for (int i = 0; i < B; ++i) LSQRB_TRY(enqueue_iteration(me, wantse));
         }
@@ -780,6 +879,8 @@ static int ez_solve_fused(lsqr_b200_ez *me, const double *b, double damp, double
         done_batches += 1;
         check(std::min(done_batches * B, itnlim));
     }
+    // deferred-update engine: the x/w update of the stopping iteration may still be outstanding
+    if (me->deferred) LSQRB_TRY(do_atprod_upd(me));
     LSQRB_CUDA(cudaEventRecord(me->ev_t2, wk.stream));
 
     // se(i) = rnorm/sqrt(t) sqrt(se(i))  (:857-865)

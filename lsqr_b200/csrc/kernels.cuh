@@ -181,36 +181,54 @@ __device__ __forceinline__ void step_after_atprod(DevState &s, double sumsq, boo
     s.test1 = test1;
     s.test2 = test2;
 
+    // snapshot of this iteration's scalars; x(1) is added when the x/w update has been applied
+    s.rec.itn = (double)s.itn;
+    s.rec.istop = (double)istop;
+    s.rec.rnorm = s.rnorm;
+    s.rec.test1 = test1;
+    s.rec.test2 = test2;
+    s.rec.anorm = s.anorm;
+    s.rec.acond = s.acond;
+    s.rec.phi = phi;
+    s.rec.dknorm = dknorm;
+    s.rec.dxk = dxk;
+    s.rec.alfopt = s.alfopt;
+    s.rec.alpha = alpha;
+    s.rec.beta = beta;
+    s.rec.xnorm = s.xnorm;
+    s.rec.arnorm = s.arnorm;
+
     // coefficients of the next Aprod:  u'' = A (v'/alpha) - alpha (u'/beta)
     s.ca_mat = s.inv_alpha;
     s.ca_vec = -alpha * s.inv_beta;
 }
 
-// after the x/w update: publish the iteration record, close the iteration
+// after the x/w update of iteration rec.itn: publish its record, close the iteration
 __device__ __forceinline__ void step_after_update(DevState &s, double sum_w2, double x1,
                                                   volatile lsqr_b200_iter_record *ring)
 {
     s.wnorm2 = sum_w2;
     s.x1 = x1;
-    volatile lsqr_b200_iter_record *r = ring + (s.itn % kRingSize);
-    r->istop = (double)s.istop;
+    const int itn = (int)s.rec.itn;
+    volatile lsqr_b200_iter_record *r = ring + (itn % kRingSize);
+    r->istop = s.rec.istop;
     r->x1 = x1;
-    r->rnorm = s.rnorm;
-    r->test1 = s.test1;
-    r->test2 = s.test2;
-    r->anorm = s.anorm;
-    r->acond = s.acond;
-    r->phi = s.phi;
-    r->dknorm = s.dknorm;
-    r->dxk = s.dxk;
-    r->alfopt = s.alfopt;
-    r->alpha = s.alpha;
-    r->beta = s.beta;
-    r->xnorm = s.xnorm;
-    r->arnorm = s.arnorm;
+    r->rnorm = s.rec.rnorm;
+    r->test1 = s.rec.test1;
+    r->test2 = s.rec.test2;
+    r->anorm = s.rec.anorm;
+    r->acond = s.rec.acond;
+    r->phi = s.rec.phi;
+    r->dknorm = s.rec.dknorm;
+    r->dxk = s.rec.dxk;
+    r->alfopt = s.rec.alfopt;
+    r->alpha = s.rec.alpha;
+    r->beta = s.rec.beta;
+    r->xnorm = s.rec.xnorm;
+    r->arnorm = s.rec.arnorm;
     __threadfence_system();
-    r->itn = (double)s.itn;   // written last: the host treats the record as complete when itn matches
-    if (s.istop != 0) s.done = 1;
+    r->itn = s.rec.itn;   // written last: the host treats the record as complete when itn matches
+    if (s.rec.istop != 0.0) s.done = 1;
 }
 
 // =============================================================================================
@@ -239,6 +257,40 @@ __device__ __forceinline__ bool finish_reduction(DevState *st, int cslot, double
     if (threadIdx.x == 0) {
         st->counter[cslot] = 0;
         *total = tot;
+        return true;
+    }
+    return false;
+}
+
+// Two simultaneous reductions behind one ticket (sum v'^2 and sum w'^2 of the fused kernel).
+template <int THREADS>
+__device__ __forceinline__ bool finish_reduction2(DevState *st, int cslot, double v1, double v2,
+                                                  double *smem, double *total1, double *total2)
+{
+    __shared__ int s_is_last2;
+    const double b1 = block_sum<THREADS>(v1, smem);
+    const double b2 = block_sum<THREADS>(v2, smem);
+    if (threadIdx.x == 0) {
+        __stcg(&st->partial[blockIdx.x], b1);
+        __stcg(&st->partial2[blockIdx.x], b2);
+        __threadfence();
+        const unsigned int ticket = atomicAdd(&st->counter[cslot], 1u);
+        s_is_last2 = (ticket == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_is_last2) return false;
+    __threadfence();
+    double a1 = 0.0, a2 = 0.0;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += THREADS) {
+        a1 += __ldcg(&st->partial[i]);
+        a2 += __ldcg(&st->partial2[i]);
+    }
+    const double t1 = block_sum<THREADS>(a1, smem);
+    const double t2 = block_sum<THREADS>(a2, smem);
+    if (threadIdx.x == 0) {
+        st->counter[cslot] = 0;
+        *total1 = t1;
+        *total2 = t2;
         return true;
     }
     return false;

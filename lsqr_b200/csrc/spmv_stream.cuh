@@ -1,0 +1,360 @@
+// spmv_stream.cuh -- K3/K4, variant 2: tile-streamed CSR SpMV for sm_100a.
+//
+// The matrix is cut into row-aligned tiles of ~kTile stored entries.  A persistent CTA walks its
+// tiles; for each tile ONE elected thread issues two 1-D TMA bulk copies (cp.async.bulk, SASS
+// UBLKCP) that stream the tile's val[] and idx[] segments from HBM into a 3-stage shared-memory
+// ring guarded by mbarriers, so the HBM stream never waits on the row structure and needs no
+// registers.  All threads then (1) gather x[idx] from L2 and overwrite val with the products,
+// (2) reduce the products row by row out of shared memory with G lanes per row (G chosen per tile
+// from its mean row length) and apply the fused epilogue.  Tiles holding a row longer than the
+// ring slot are processed straight from global memory by the whole CTA.
+//
+// Everything about the summation order is fixed by the tile map, never by scheduling, so results
+// are run-to-run reproducible.  HBM traffic = val + idx once, ptr once, out once (+old once).
+#pragma once
+
+#include "kernels.cuh"
+
+namespace lsqrb {
+
+constexpr int kTile = 1536;      // nominal stored entries per tile
+constexpr int kCap = 2048;       // ring-slot capacity (entries); a tile fits iff its rows are <= kCap - kTile + 1 long
+constexpr int kSlot = kCap + 8;  // + alignment slack on both sides
+constexpr int kStages = 3;
+constexpr int kStreamThreads = 256;
+constexpr size_t kStreamSmem = (size_t)kStages * kSlot * (sizeof(double) + sizeof(int32_t)) + 64;
+
+struct TileMap {
+    const uint2 *tiles;   // [ntiles+1]  {first row, first stored entry}; tiles[ntiles] = {nrows, nnz}
+    int ntiles;
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers: mbarrier + 1-D bulk TMA
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        " .reg .pred p;\n"
+        " mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        " selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    // try_wait suspends the thread in hardware for a bounded time; a copy that never lands would
+    // otherwise hang the GPU, so give up loudly after ~2 s instead.
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000ll) __trap();
+    }
+}
+// global -> shared bulk copy, completion counted in bytes on the mbarrier; matrix data is read once,
+// so it carries an L2 evict-first policy.
+__device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar, uint64_t policy)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+        ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// Tile map construction: tile t starts at the first row whose first entry is at or after t*kTile.
+// ---------------------------------------------------------------------------------------------
+__global__ void build_tiles_kernel(const uint32_t *__restrict__ ptr, int64_t nrows, int64_t nnz, int ntiles, uint2 *tiles)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > ntiles) return;
+    if (t == ntiles) { tiles[t] = make_uint2((uint32_t)nrows, (uint32_t)nnz); return; }
+    const uint64_t target = (uint64_t)t * kTile;
+    int64_t lo = 0, hi = nrows;   // first r in [0, nrows] with ptr[r] >= target
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if ((uint64_t)ptr[mid] >= target) hi = mid; else lo = mid + 1;
+    }
+    tiles[t] = make_uint2((uint32_t)lo, ptr[lo]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// epilogues
+// ---------------------------------------------------------------------------------------------
+enum StreamEpilogue {
+    SEPI_APROD = 0,        // u' = ca_mat*s + ca_vec*u ; sum u'^2 ; step_after_aprod (or partial to aux)
+    SEPI_ATPROD = 1,       // v' = ct_mat*s + ct_vec*v ; sum v'^2 ; step_after_atprod
+    SEPI_INIT_ATPROD = 2,  // v  = ct_mat*s            ; sum v^2  ; step_init_alpha
+    SEPI_ACC = 3,          // out += s
+    SEPI_STORE = 4,        // out  = s
+    SEPI_ATPROD_UPD = 5    // SEPI_ATPROD fused with the DEFERRED x/w update of the previous iteration:
+                           //   x += t1 w ; w' = v/alpha + t2 w ; sum w'^2   (v = old v, read anyway)
+};
+
+struct StreamArgs {
+    CsrView A;
+    TileMap map;
+    const double *x;       // gathered dense vector
+    double *out;           // result vector (rows of A)
+    DevState *st;
+    double *aux;           // multi-GPU: where SEPI_APROD puts its partial sum(u'^2)
+    double *ux, *uw, *use; // SEPI_ATPROD_UPD: solution, search direction, standard errors
+    volatile lsqr_b200_iter_record *ring;
+};
+
+template <int EPI>
+struct RowEpilogue {
+    double cm = 1.0, cv = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0, ia = 1.0;
+    bool upd = false, wantse = false;
+    double sq = 0.0, sq2 = 0.0;
+
+    __device__ __forceinline__ void load(const DevState *st)
+    {
+        if (EPI == SEPI_APROD) { cm = st->ca_mat; cv = st->ca_vec; }
+        if (EPI == SEPI_ATPROD || EPI == SEPI_INIT_ATPROD || EPI == SEPI_ATPROD_UPD) { cm = st->ct_mat; cv = st->ct_vec; }
+        if (EPI == SEPI_ATPROD_UPD) {
+            upd = st->upd_pending != 0; wantse = st->wantse != 0;
+            t1 = st->t1; t2 = st->t2; t3 = st->t3; ia = st->inv_alpha;
+        }
+    }
+    // `old` = out[row] fetched before the row sum (hides the DRAM latency behind the reduction)
+    __device__ __forceinline__ bool needs_old() const { return EPI == SEPI_APROD || EPI == SEPI_ATPROD || EPI == SEPI_ACC || EPI == SEPI_ATPROD_UPD; }
+    __device__ __forceinline__ void apply(const StreamArgs &a, int64_t row, double s, double old)
+    {
+        if (EPI == SEPI_ACC) { a.out[row] = old + s; return; }
+        if (EPI == SEPI_STORE) { a.out[row] = s; return; }
+        if (EPI == SEPI_INIT_ATPROD) { const double r = cm * s; a.out[row] = r; sq += r * r; return; }
+        const double r = cm * s + cv * old;
+        a.out[row] = r;
+        sq += r * r;
+        if (EPI == SEPI_ATPROD_UPD && upd) {
+            const double wo = a.uw[row];
+            a.ux[row] = t1 * wo + a.ux[row];
+            const double wn = t2 * wo + ia * old;
+            a.uw[row] = wn;
+            sq2 += wn * wn;
+            if (wantse) a.use[row] += (t3 * wo) * (t3 * wo);
+        }
+    }
+};
+
+// reduce rows [r0, r1) of a staged tile; products sit in sval[], entry e of the matrix at sval[e - a0]
+template <int G, int EPI>
+__device__ __forceinline__ void reduce_rows(const StreamArgs &a, RowEpilogue<EPI> &epi, const double *sval,
+                                            uint32_t r0, uint32_t r1, uint32_t a0)
+{
+    constexpr int kGroups = kStreamThreads / G;
+    const int lane = threadIdx.x % G;
+    const int grp = threadIdx.x / G;
+    const uint32_t nrows = r1 - r0;
+    const uint32_t rounds = (nrows + kGroups - 1) / kGroups;
+    for (uint32_t it = 0; it < rounds; ++it) {
+        const uint32_t r = r0 + it * kGroups + grp;
+        const bool valid = r < r1;
+        double s = 0.0, old = 0.0;
+        if (valid) {
+            const uint32_t p0 = a.A.ptr[r] - a0, p1 = a.A.ptr[r + 1] - a0;
+            if (lane == 0 && epi.needs_old()) old = a.out[r];
+            for (uint32_t k = p0 + lane; k < p1; k += G) s += sval[k];
+        }
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (valid && lane == 0) epi.apply(a, r, s, old);
+    }
+}
+
+// What a fused launch has to do, decided from the device state (uniform over the grid)
+enum StreamMode {
+    MODE_FULL = 0,         // stream the matrix, reduce rows, epilogue
+    MODE_UPDATE_ONLY = 1,  // beta = 0: no A' product (src/lsqr.f90:691), but the deferred x/w update is due
+    MODE_FLUSH = 2         // the stopping iteration is known: only x += t1 w of that iteration is left
+};
+
+template <int EPI>
+__global__ void __launch_bounds__(kStreamThreads)
+spmv_stream_kernel(StreamArgs a)
+{
+    constexpr bool kFused = (EPI == SEPI_APROD || EPI == SEPI_ATPROD || EPI == SEPI_INIT_ATPROD || EPI == SEPI_ATPROD_UPD);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *sval = reinterpret_cast<double *>(smem_raw);                              // [kStages][kSlot]
+    int32_t *sidx = reinterpret_cast<int32_t *>(smem_raw + (size_t)kStages * kSlot * sizeof(double));   // [kStages][kSlot]
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)kStages * kSlot * (sizeof(double) + sizeof(int32_t)));
+    __shared__ double s_red[kStreamThreads / 32];
+
+    DevState *st = a.st;
+    RowEpilogue<EPI> epi;
+    int mode = MODE_FULL;
+    if (kFused) {
+        if (st->done) return;
+        if (EPI == SEPI_APROD && st->istop != 0) return;   // stop already decided: only the deferred update is left
+        if (EPI == SEPI_ATPROD && st->beta == 0.0) {
+            // beta = 0: the reference skips the A' half and keeps alpha (src/lsqr.f90:691-699)
+            if (blockIdx.x == 0 && threadIdx.x == 0) step_after_atprod(*st, 0.0, false);
+            return;
+        }
+        if (EPI == SEPI_ATPROD_UPD) {
+            if (st->istop != 0) mode = MODE_FLUSH;
+            else if (st->beta == 0.0) mode = MODE_UPDATE_ONLY;
+        }
+        epi.load(st);
+    }
+
+    const uint64_t pol_stream = l2_policy_evict_first();
+    const uint64_t pol_keep = l2_policy_evict_last();
+    const int tid = threadIdx.x;
+
+    if (mode != MODE_FULL) {
+        // elementwise part only (n-vectors): x += t1 w [; w' = v/alpha + t2 w]
+        if (epi.upd) {
+            const int64_t n = a.A.nrows;
+            for (int64_t i = (int64_t)blockIdx.x * kStreamThreads + tid; i < n; i += (int64_t)gridDim.x * kStreamThreads) {
+                const double wo = a.uw[i];
+                a.ux[i] = epi.t1 * wo + a.ux[i];
+                if (epi.wantse) a.use[i] += (epi.t3 * wo) * (epi.t3 * wo);
+                if (mode == MODE_UPDATE_ONLY) {
+                    const double wn = epi.t2 * wo + epi.ia * a.out[i];
+                    a.uw[i] = wn;
+                    epi.sq2 += wn * wn;
+                }
+            }
+        }
+    } else {
+        if (tid == 0) {
+            for (int s = 0; s < kStages; ++s) mbar_init(full + s, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+
+        // producer (thread 0): stage tile t into ring slot `slot`; false if the tile needs no staging
+        auto stage_tile = [&](int t, int slot) {
+            const uint2 t0 = a.map.tiles[t], t1 = a.map.tiles[t + 1];
+            const uint32_t len = t1.y - t0.y;
+            if (t0.x == t1.x || len == 0 || len > (uint32_t)kCap) return false;   // rowless, empty or long tile
+            const uint32_t a0 = t0.y & ~3u;
+            const uint32_t a1 = (t1.y + 3u) & ~3u;
+            const uint32_t cnt = a1 - a0;
+            mbar_expect_tx(full + slot, cnt * 12u);
+            tma_load_1d(sval + (size_t)slot * kSlot, a.A.val + a0, cnt * 8u, full + slot, pol_stream);
+            tma_load_1d(sidx + (size_t)slot * kSlot, a.A.idx + a0, cnt * 4u, full + slot, pol_stream);
+            return true;
+        };
+
+        int prod_t = blockIdx.x;          // producer's next tile
+        int prod_n = 0;                   // tiles staged so far
+        int cons_n = 0;                   // staged tiles consumed so far
+        if (tid == 0) {
+            while (prod_n < kStages && prod_t < a.map.ntiles) {
+                if (stage_tile(prod_t, prod_n % kStages)) ++prod_n;
+                prod_t += gridDim.x;
+            }
+        }
+
+        for (int t = blockIdx.x; t < a.map.ntiles; t += gridDim.x) {
+            const uint2 t0 = a.map.tiles[t], t1 = a.map.tiles[t + 1];
+            const uint32_t r0 = t0.x, r1 = t1.x, e0 = t0.y, e1 = t1.y;
+            const uint32_t len = e1 - e0;
+            if (r0 == r1) continue;                       // no row starts in this tile (inside a long row)
+            if (len > (uint32_t)kCap) {
+                // ---- long tile: every row straight from global memory, whole CTA per row
+                for (uint32_t r = r0; r < r1; ++r) {
+                    const uint32_t p0 = a.A.ptr[r], p1 = a.A.ptr[r + 1];
+                    double old = 0.0;
+                    if (tid == 0 && epi.needs_old()) old = a.out[r];
+                    double s = 0.0;
+#pragma unroll 4
+                    for (uint32_t k = p0 + tid; k < p1; k += kStreamThreads) {
+                        const double v = ldg_stream_f64(a.A.val + k, pol_stream);
+                        const int32_t c = ldg_stream_s32(a.A.idx + k, pol_stream);
+                        s += v * ldg_keep_f64(a.x + c, pol_keep);
+                    }
+                    s = block_sum<kStreamThreads>(s, s_red);
+                    if (tid == 0) epi.apply(a, r, s, old);
+                }
+                continue;
+            }
+            const uint32_t a0 = e0 & ~3u;
+            double *sv = sval;
+            if (len > 0) {
+                const int slot = cons_n % kStages;
+                sv = sval + (size_t)slot * kSlot;
+                const int32_t *si = sidx + (size_t)slot * kSlot;
+                mbar_wait(full + slot, (uint32_t)(cons_n / kStages) & 1u);
+                // ---- gather + multiply in place
+                const uint32_t off = e0 - a0;
+#pragma unroll 4
+                for (uint32_t i = tid; i < len; i += kStreamThreads) {
+                    const uint32_t k = off + i;
+                    sv[k] = sv[k] * ldg_keep_f64(a.x + si[k], pol_keep);
+                }
+                __syncthreads();
+            }
+            // ---- row reduction out of shared memory, lanes per row from the tile's mean row length
+            const uint32_t nrows = r1 - r0;
+            const uint32_t avg = len / nrows;
+            if (avg <= 4)       reduce_rows<1, EPI>(a, epi, sv, r0, r1, a0);
+            else if (avg <= 8)  reduce_rows<2, EPI>(a, epi, sv, r0, r1, a0);
+            else if (avg <= 16) reduce_rows<4, EPI>(a, epi, sv, r0, r1, a0);
+            else if (avg <= 32) reduce_rows<8, EPI>(a, epi, sv, r0, r1, a0);
+            else if (avg <= 64) reduce_rows<16, EPI>(a, epi, sv, r0, r1, a0);
+            else                reduce_rows<32, EPI>(a, epi, sv, r0, r1, a0);
+            if (len > 0) {
+                fence_proxy_async_smem();                 // order this thread's generic-proxy writes (products) before the async refill
+                __syncthreads();                          // everyone is done with this slot
+                ++cons_n;
+                if (tid == 0) {
+                    while (prod_t < a.map.ntiles) {
+                        const bool staged = stage_tile(prod_t, prod_n % kStages);
+                        prod_t += gridDim.x;
+                        if (staged) { ++prod_n; break; }
+                    }
+                }
+            }
+        }
+    }
+
+    if (kFused) {
+        double total, total_w;
+        if (EPI == SEPI_ATPROD_UPD) {
+            // sum(w'^2) of the deferred update closes iteration k; sum(v'^2) drives the step of iteration k+1
+            if (finish_reduction2<kStreamThreads>(st, 0, epi.sq, epi.sq2, s_red, &total, &total_w)) {
+                if (st->upd_pending) {
+                    __threadfence();
+                    step_after_update(*st, total_w, __ldcg(a.ux), a.ring);
+                    st->upd_pending = 0;
+                }
+                if (!st->done) {
+                    step_after_atprod(*st, total, mode == MODE_FULL);
+                    st->upd_pending = 1;
+                }
+            }
+        } else if (finish_reduction<kStreamThreads>(st, 0, epi.sq, s_red, &total)) {
+            if (EPI == SEPI_APROD) {
+                if (a.aux) *a.aux = total; else step_after_aprod(*st, total);
+            }
+            else if (EPI == SEPI_ATPROD) step_after_atprod(*st, total, true);
+            else step_init_alpha(*st, total);
+        }
+    }
+}
+
+}  // namespace lsqrb

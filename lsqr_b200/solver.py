@@ -132,7 +132,7 @@ class LsqrSolverEz:
     def initialize(self, m: int, n: int, a, irow, icol, atol: float = 0.0, btol: float = 0.0,
                    conlim: float = 0.0, itnlim: int = 100, nout=None, *,
                    device: int = -1, stream: int = 0, engine: int = 0, use_graph: bool = True,
-                   profile: bool = False, world_size: int = 1, rank: int = 0,
+                   profile: bool = False, spmv_variant: int = 0, world_size: int = 1, rank: int = 0,
                    nccl_unique_id: Optional[bytes] = None, m_global: int = 0) -> "LsqrSolverEz":
         L = _lib.load()
         self.destroy()                       # `me` is intent(out): re-initialising resets the object (:95)
@@ -143,6 +143,7 @@ class LsqrSolverEz:
         o.atol, o.btol, o.conlim, o.itnlim = float(atol), float(btol), float(conlim), int(itnlim)
         o.device, o.stream = int(device), int(stream) or None
         o.engine, o.use_graph, o.profile = int(engine), int(bool(use_graph)), int(bool(profile))
+        o.spmv_variant = int(spmv_variant)
         o.world_size, o.rank, o.m_global = int(world_size), int(rank), int(m_global)
         idbuf = None
         if nccl_unique_id is not None:

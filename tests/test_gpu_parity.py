@@ -212,6 +212,37 @@ def test_solve_parity_scaled_configs(lb, name, scale, shuffle, tol):
     _assert_parity(data, r, ref)
 
 
+@pytest.mark.parametrize("name,scale", [("C2", 10), ("C3", 100), ("C4", 100)])
+def test_solve_parity_subwarp_variant(lb, name, scale):
+    """Variant 1 (sub-warp per row, separate update kernel) against the oracle and against variant 2."""
+    from lsqr_b200 import synth
+    cfg = synth.scaled(name, scale)
+    data, r1, ref = _solve_both(lb, cfg, 1e-10, 1e-10, 1e8, 4000, spmv_variant=1)
+    _assert_parity(data, r1, ref)
+    _, r2, _ = _solve_both(lb, cfg, 1e-10, 1e-10, 1e8, 4000, spmv_variant=2)
+    assert r1.istop == r2.istop and abs(r1.itn - r2.itn) <= 1
+    assert relerr(r1.x, r2.x) <= RTOL
+
+
+def test_long_rows_take_the_whole_cta_path(lb):
+    """Rows longer than a ring slot (and a 1-entry-per-row tail) through the tile-streamed kernels."""
+    rng = np.random.default_rng(8)
+    m, n = 600, 9000
+    lens = np.where(np.arange(m) % 97 == 0, 5000, 1)          # a few 5000-entry rows among 1-entry rows
+    irow = np.repeat(np.arange(1, m + 1), lens).astype(np.int32)
+    icol = rng.integers(1, n + 1, irow.size).astype(np.int32)
+    a = rng.standard_normal(irow.size)
+    s = lb.LsqrSolverEz().initialize(m, n, a, irow, icol)
+    ref = O.SolverEz(m, n, a, irow, icol)
+    x, y = rng.standard_normal(n), rng.standard_normal(m)
+    y1, yr = y.copy(), y.copy()
+    s.aprod(1, m, n, x, y1); ref.aprod(1, x.copy(), yr)
+    assert relerr(y1, yr) <= 1e-13
+    x2, xr = x.copy(), x.copy()
+    s.aprod(2, m, n, x2, y); ref.aprod(2, xr, y.copy())
+    assert relerr(x2, xr) <= 1e-13
+
+
 def test_solve_parity_c2_full_size(lb):
     from lsqr_b200 import synth
     data, r, ref = _solve_both(lb, synth.CONFIGS["C2"], 1e-10, 1e-10, 1e8, 1000)
