@@ -128,7 +128,7 @@ int coo_to_csr_device(cudaStream_t stream, int64_t nkeys, int64_t nnz,
     out->nrows = nkeys;
     out->nnz = nnz;
     out->was_sorted = 1;
-    LSQRB_CUDA(cudaMalloc(&out->ptr, sizeof(uint32_t) * (size_t)(nkeys + 1)));
+    LSQRB_CUDA(cudaMalloc(&out->ptr, sizeof(uint32_t) * (size_t)(nkeys + 1 + 8)));   // + slack for aligned bulk reads
     const size_t nz = (size_t)(nnz > 0 ? nnz : 1);
     const size_t nzp = nz + 8;   // the tile-streamed SpMV reads 16-byte aligned supersets of a tile (spmv_stream.cuh)
     LSQRB_CUDA(cudaMalloc(&out->idx, sizeof(int32_t) * nzp));
@@ -136,7 +136,7 @@ int coo_to_csr_device(cudaStream_t stream, int64_t nkeys, int64_t nnz,
     LSQRB_CUDA(cudaMemsetAsync(out->idx + nz - 1, 0, sizeof(int32_t) * 9, stream));
     LSQRB_CUDA(cudaMemsetAsync(out->val + nz - 1, 0, sizeof(double) * 9, stream));
     LSQRB_CUDA(cudaMalloc(&out->perm, sizeof(uint32_t) * nz));
-    LSQRB_CUDA(cudaMemsetAsync(out->ptr, 0, sizeof(uint32_t) * (size_t)(nkeys + 1), stream));
+    LSQRB_CUDA(cudaMemsetAsync(out->ptr, 0, sizeof(uint32_t) * (size_t)(nkeys + 1 + 8), stream));
     if (nnz == 0) return LSQR_B200_OK;
 
     // ptr: histogram of the keys, then an exclusive prefix sum

@@ -113,7 +113,8 @@ struct Work {
     lsqr_b200_iter_record *ring_h = nullptr;      // pinned, mapped
     lsqr_b200_iter_record *ring_d = nullptr;      // device alias of ring_h
     int max_grid = kNumSMs * 8;
-    int stream_grid = kNumSMs * 3;   // persistent CTAs of the tile-streamed kernels (3 x 74 KB of smem per SM)
+    int stream_grid = kNumSMs * 3;   // cap on the persistent CTAs of the tile-streamed kernels
+    int sms = kNumSMs;
     int64_t launches = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 
@@ -140,8 +141,8 @@ struct Work {
         LSQRB_CUDA(cudaHostAlloc(&ring_h, sizeof(lsqr_b200_iter_record) * kRingSize, cudaHostAllocMapped));
         LSQRB_CUDA(cudaHostGetDevicePointer(&ring_d, ring_h, 0));
         for (auto &e : ev) LSQRB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDefault));
-        int sms = 0;
         LSQRB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+        sms = std::max(1, sms);
         max_grid = std::min(kMaxPartials, std::max(1, sms) * env_int("LSQR_B200_BLOCKS_PER_SM", 8));
         stream_grid = std::min(kMaxPartials, std::max(1, sms) * env_int("LSQR_B200_STREAM_CTAS_PER_SM", 3));
         return LSQR_B200_OK;
@@ -233,14 +234,22 @@ static int build_tile_map(Work &wk, const Csr &M, TileMapOwner *out)
     return LSQR_B200_OK;
 }
 
+// Opt in to the large dynamic shared memory window and the maximum carve-out, and measure how many
+// CTAs of this instantiation are co-resident per SM: the persistent grid is sized to exactly that.
 template <int EPI>
-static int stream_kernel_prepare()
+static int stream_kernel_prepare(int *ctas_per_sm)
 {
-    static bool done = false;
-    if (!done) {
+    static int occ = 0;
+    if (occ == 0) {
         LSQRB_CUDA(cudaFuncSetAttribute(spmv_stream_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStreamSmem));
-        done = true;
+        LSQRB_CUDA(cudaFuncSetAttribute(spmv_stream_kernel<EPI>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        int n = 0;
+        LSQRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, spmv_stream_kernel<EPI>, kStreamThreads, kStreamSmem));
+        occ = std::max(1, n);
+        if (env_int("LSQR_B200_VERBOSE", 0))
+            fprintf(stderr, "[lsqr_b200] spmv_stream_kernel<%d>: %d CTAs/SM, %zu B dynamic smem\n", EPI, occ, kStreamSmem);
     }
+    *ctas_per_sm = occ;
     return LSQR_B200_OK;
 }
 
@@ -252,14 +261,16 @@ template <int EPI>
 static int launch_stream(Work &wk, const Csr &M, const TileMapOwner &map, const double *x, double *out, double *aux,
                          const StreamExtra &ex = StreamExtra())
 {
-    LSQRB_TRY(stream_kernel_prepare<EPI>());
+    int occ = 1;
+    LSQRB_TRY(stream_kernel_prepare<EPI>(&occ));
     StreamArgs a;
     a.A = CsrView{M.ptr, M.idx, M.val, M.nrows};
     a.map = TileMap{map.tiles, map.ntiles};
     a.x = x; a.out = out; a.st = wk.st; a.aux = aux;
     a.ux = ex.ux; a.uw = ex.uw; a.use = ex.use;
     a.ring = wk.ring_d;
-    const int grid = std::max(1, std::min(map.ntiles, wk.stream_grid));
+    a.out_aligned16 = ((uintptr_t)out & 15u) == 0;
+    const int grid = std::max(1, std::min(map.ntiles, std::min(wk.stream_grid, wk.sms * occ)));
     spmv_stream_kernel<EPI><<<grid, kStreamThreads, kStreamSmem, wk.stream>>>(a);
     wk.launches++;
     LSQRB_CUDA(cudaGetLastError());

@@ -17,12 +17,18 @@
 
 namespace lsqrb {
 
-constexpr int kTile = 1536;      // nominal stored entries per tile
-constexpr int kCap = 2048;       // ring-slot capacity (entries); a tile fits iff its rows are <= kCap - kTile + 1 long
-constexpr int kSlot = kCap + 8;  // + alignment slack on both sides
+constexpr int kTile = 1024;      // nominal stored entries per tile
+constexpr int kCap = 1536;       // ring-slot capacity (entries); a tile fits iff its rows are <= kCap - kTile + 1 long
+constexpr int kCapS = kCap + 8;  // + alignment slack on both sides
+constexpr int kRowCap = 512;     // rows per tile whose ptr[] / out[] segments are staged too
+constexpr int kOldS = kRowCap + 4;
+constexpr int kPtrS = kRowCap + 8;
 constexpr int kStages = 3;
 constexpr int kStreamThreads = 256;
-constexpr size_t kStreamSmem = (size_t)kStages * kSlot * (sizeof(double) + sizeof(int32_t)) + 64;
+// one ring slot: val[kCapS] f64 | old[kOldS] f64 | idx[kCapS] i32 | ptr[kPtrS] u32   (every part a multiple of 16 bytes)
+constexpr size_t kSlotBytes = (size_t)kCapS * 8 + (size_t)kOldS * 8 + (size_t)kCapS * 4 + (size_t)kPtrS * 4;
+constexpr size_t kStreamSmem = (size_t)kStages * kSlotBytes + 64;
+static_assert(kSlotBytes % 16 == 0 && (kCapS * 8) % 16 == 0 && (kOldS * 8) % 16 == 0 && (kCapS * 4) % 16 == 0, "TMA alignment");
 
 struct TileMap {
     const uint2 *tiles;   // [ntiles+1]  {first row, first stored entry}; tiles[ntiles] = {nrows, nnz}
@@ -119,6 +125,7 @@ struct StreamArgs {
     DevState *st;
     double *aux;           // multi-GPU: where SEPI_APROD puts its partial sum(u'^2)
     double *ux, *uw, *use; // SEPI_ATPROD_UPD: solution, search direction, standard errors
+    int out_aligned16;     // out[] may be the source of 16-byte aligned bulk copies
     volatile lsqr_b200_iter_record *ring;
 };
 
@@ -158,10 +165,13 @@ struct RowEpilogue {
     }
 };
 
-// reduce rows [r0, r1) of a staged tile; products sit in sval[], entry e of the matrix at sval[e - a0]
-template <int G, int EPI>
+// reduce rows [r0, r1) of a staged tile; products sit in sval[], entry e of the matrix at sval[e - a0].
+// SROWS: the tile's ptr[] and out[] segments were staged too (sptr[r - r0a], sold[r - r0a], the
+// latter for the first n_old rows), so the reduction touches global memory only to store.
+template <int G, int EPI, bool SROWS>
 __device__ __forceinline__ void reduce_rows(const StreamArgs &a, RowEpilogue<EPI> &epi, const double *sval,
-                                            uint32_t r0, uint32_t r1, uint32_t a0)
+                                            const uint32_t *sptr, const double *sold, uint32_t n_old,
+                                            uint32_t r0, uint32_t r1, uint32_t a0, uint32_t r0a)
 {
     constexpr int kGroups = kStreamThreads / G;
     const int lane = threadIdx.x % G;
@@ -173,14 +183,31 @@ __device__ __forceinline__ void reduce_rows(const StreamArgs &a, RowEpilogue<EPI
         const bool valid = r < r1;
         double s = 0.0, old = 0.0;
         if (valid) {
-            const uint32_t p0 = a.A.ptr[r] - a0, p1 = a.A.ptr[r + 1] - a0;
-            if (lane == 0 && epi.needs_old()) old = a.out[r];
+            uint32_t p0, p1;
+            if (SROWS) { p0 = sptr[r - r0a] - a0; p1 = sptr[r - r0a + 1] - a0; }
+            else       { p0 = a.A.ptr[r] - a0;    p1 = a.A.ptr[r + 1] - a0; }
+            if (lane == 0 && epi.needs_old()) old = (SROWS && r - r0a < n_old) ? sold[r - r0a] : a.out[r];
             for (uint32_t k = p0 + lane; k < p1; k += G) s += sval[k];
         }
 #pragma unroll
         for (int o = G / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         if (valid && lane == 0) epi.apply(a, r, s, old);
     }
+}
+
+template <int EPI, bool SROWS>
+__device__ __forceinline__ void reduce_tile(const StreamArgs &a, RowEpilogue<EPI> &epi, const double *sval,
+                                            const uint32_t *sptr, const double *sold, uint32_t n_old,
+                                            uint32_t r0, uint32_t r1, uint32_t a0, uint32_t r0a, uint32_t len)
+{
+    // lanes per row from the tile's mean row length
+    const uint32_t avg = len / (r1 - r0);
+    if (avg <= 4)       reduce_rows<1, EPI, SROWS>(a, epi, sval, sptr, sold, n_old, r0, r1, a0, r0a);
+    else if (avg <= 8)  reduce_rows<2, EPI, SROWS>(a, epi, sval, sptr, sold, n_old, r0, r1, a0, r0a);
+    else if (avg <= 16) reduce_rows<4, EPI, SROWS>(a, epi, sval, sptr, sold, n_old, r0, r1, a0, r0a);
+    else if (avg <= 32) reduce_rows<8, EPI, SROWS>(a, epi, sval, sptr, sold, n_old, r0, r1, a0, r0a);
+    else if (avg <= 64) reduce_rows<16, EPI, SROWS>(a, epi, sval, sptr, sold, n_old, r0, r1, a0, r0a);
+    else                reduce_rows<32, EPI, SROWS>(a, epi, sval, sptr, sold, n_old, r0, r1, a0, r0a);
 }
 
 // What a fused launch has to do, decided from the device state (uniform over the grid)
@@ -196,9 +223,11 @@ spmv_stream_kernel(StreamArgs a)
 {
     constexpr bool kFused = (EPI == SEPI_APROD || EPI == SEPI_ATPROD || EPI == SEPI_INIT_ATPROD || EPI == SEPI_ATPROD_UPD);
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    double *sval = reinterpret_cast<double *>(smem_raw);                              // [kStages][kSlot]
-    int32_t *sidx = reinterpret_cast<int32_t *>(smem_raw + (size_t)kStages * kSlot * sizeof(double));   // [kStages][kSlot]
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)kStages * kSlot * (sizeof(double) + sizeof(int32_t)));
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)kStages * kSlotBytes);
+    auto slot_val = [&](int s) { return reinterpret_cast<double *>(smem_raw + (size_t)s * kSlotBytes); };
+    auto slot_old = [&](int s) { return slot_val(s) + kCapS; };
+    auto slot_idx = [&](int s) { return reinterpret_cast<int32_t *>(slot_old(s) + kOldS); };
+    auto slot_ptr = [&](int s) { return reinterpret_cast<uint32_t *>(slot_idx(s) + kCapS); };
     __shared__ double s_red[kStreamThreads / 32];
 
     DevState *st = a.st;
@@ -246,16 +275,31 @@ spmv_stream_kernel(StreamArgs a)
         __syncthreads();
 
         // producer (thread 0): stage tile t into ring slot `slot`; false if the tile needs no staging
+        const uint32_t out_rows = (uint32_t)a.A.nrows;
+        const bool stage_old = epi.needs_old() && a.out_aligned16;
         auto stage_tile = [&](int t, int slot) {
             const uint2 t0 = a.map.tiles[t], t1 = a.map.tiles[t + 1];
             const uint32_t len = t1.y - t0.y;
             if (t0.x == t1.x || len == 0 || len > (uint32_t)kCap) return false;   // rowless, empty or long tile
             const uint32_t a0 = t0.y & ~3u;
-            const uint32_t a1 = (t1.y + 3u) & ~3u;
-            const uint32_t cnt = a1 - a0;
-            mbar_expect_tx(full + slot, cnt * 12u);
-            tma_load_1d(sval + (size_t)slot * kSlot, a.A.val + a0, cnt * 8u, full + slot, pol_stream);
-            tma_load_1d(sidx + (size_t)slot * kSlot, a.A.idx + a0, cnt * 4u, full + slot, pol_stream);
+            const uint32_t cnt = ((t1.y + 3u) & ~3u) - a0;
+            uint32_t bytes = cnt * 12u;
+            const uint32_t nrows = t1.x - t0.x;
+            const uint32_t r0a = t0.x & ~3u;
+            uint32_t cnt_ptr = 0, cnt_old = 0;
+            if (nrows <= (uint32_t)kRowCap) {
+                cnt_ptr = ((t1.x + 1u + 3u) & ~3u) - r0a;                       // ptr[r0a .. r1], padded (array has slack)
+                bytes += cnt_ptr * 4u;
+                if (stage_old) {
+                    cnt_old = (min(t1.x, out_rows) - r0a) & ~1u;                // never read past the end of out[]
+                    bytes += cnt_old * 8u;
+                }
+            }
+            mbar_expect_tx(full + slot, bytes);
+            tma_load_1d(slot_val(slot), a.A.val + a0, cnt * 8u, full + slot, pol_stream);
+            tma_load_1d(slot_idx(slot), a.A.idx + a0, cnt * 4u, full + slot, pol_stream);
+            if (cnt_ptr) tma_load_1d(slot_ptr(slot), a.A.ptr + r0a, cnt_ptr * 4u, full + slot, pol_stream);
+            if (cnt_old) tma_load_1d(slot_old(slot), a.out + r0a, cnt_old * 8u, full + slot, pol_stream);
             return true;
         };
 
@@ -293,11 +337,14 @@ spmv_stream_kernel(StreamArgs a)
                 continue;
             }
             const uint32_t a0 = e0 & ~3u;
-            double *sv = sval;
+            const uint32_t r0a = r0 & ~3u;
+            const uint32_t nrows = r1 - r0;
+            const bool srows = len > 0 && nrows <= (uint32_t)kRowCap;
+            const uint32_t n_old = (srows && stage_old) ? ((min(r1, out_rows) - r0a) & ~1u) : 0u;
+            const int slot = cons_n % kStages;
+            double *sv = slot_val(slot);
             if (len > 0) {
-                const int slot = cons_n % kStages;
-                sv = sval + (size_t)slot * kSlot;
-                const int32_t *si = sidx + (size_t)slot * kSlot;
+                const int32_t *si = slot_idx(slot);
                 mbar_wait(full + slot, (uint32_t)(cons_n / kStages) & 1u);
                 // ---- gather + multiply in place
                 const uint32_t off = e0 - a0;
@@ -308,15 +355,9 @@ spmv_stream_kernel(StreamArgs a)
                 }
                 __syncthreads();
             }
-            // ---- row reduction out of shared memory, lanes per row from the tile's mean row length
-            const uint32_t nrows = r1 - r0;
-            const uint32_t avg = len / nrows;
-            if (avg <= 4)       reduce_rows<1, EPI>(a, epi, sv, r0, r1, a0);
-            else if (avg <= 8)  reduce_rows<2, EPI>(a, epi, sv, r0, r1, a0);
-            else if (avg <= 16) reduce_rows<4, EPI>(a, epi, sv, r0, r1, a0);
-            else if (avg <= 32) reduce_rows<8, EPI>(a, epi, sv, r0, r1, a0);
-            else if (avg <= 64) reduce_rows<16, EPI>(a, epi, sv, r0, r1, a0);
-            else                reduce_rows<32, EPI>(a, epi, sv, r0, r1, a0);
+            // ---- row reduction out of shared memory
+            if (srows) reduce_tile<EPI, true>(a, epi, sv, slot_ptr(slot), slot_old(slot), n_old, r0, r1, a0, r0a, len);
+            else       reduce_tile<EPI, false>(a, epi, sv, nullptr, nullptr, 0u, r0, r1, a0, r0a, len);
             if (len > 0) {
                 fence_proxy_async_smem();                 // order this thread's generic-proxy writes (products) before the async refill
                 __syncthreads();                          // everyone is done with this slot
