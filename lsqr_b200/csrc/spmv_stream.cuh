@@ -17,18 +17,16 @@
 
 namespace lsqrb {
 
-constexpr int kTile = 1024;      // nominal stored entries per tile
-constexpr int kCap = 1536;       // ring-slot capacity (entries); a tile fits iff its rows are <= kCap - kTile + 1 long
+constexpr int kTile = 3072;      // nominal stored entries per tile
+constexpr int kCap = 4096;       // ring-slot capacity (entries); a tile fits iff its rows are <= kCap - kTile + 1 long
 constexpr int kCapS = kCap + 8;  // + alignment slack on both sides
-constexpr int kRowCap = 512;     // rows per tile whose ptr[] / out[] segments are staged too
-constexpr int kOldS = kRowCap + 4;
-constexpr int kPtrS = kRowCap + 8;
-constexpr int kStages = 3;
-constexpr int kStreamThreads = 256;
-// one ring slot: val[kCapS] f64 | old[kOldS] f64 | idx[kCapS] i32 | ptr[kPtrS] u32   (every part a multiple of 16 bytes)
-constexpr size_t kSlotBytes = (size_t)kCapS * 8 + (size_t)kOldS * 8 + (size_t)kCapS * 4 + (size_t)kPtrS * 4;
+constexpr int kStages = 2;
+constexpr int kStreamThreads = 512;
+constexpr int kPrefRounds = 2;   // thread-per-row mode: rounds whose ptr[] / out[] loads are issued before the gather phase
+// one ring slot: val[kCapS] f64 | idx[kCapS] i32   (both multiples of 16 bytes)
+constexpr size_t kSlotBytes = (size_t)kCapS * 8 + (size_t)kCapS * 4;
 constexpr size_t kStreamSmem = (size_t)kStages * kSlotBytes + 64;
-static_assert(kSlotBytes % 16 == 0 && (kCapS * 8) % 16 == 0 && (kOldS * 8) % 16 == 0 && (kCapS * 4) % 16 == 0, "TMA alignment");
+static_assert(kSlotBytes % 16 == 0 && (kCapS * 8) % 16 == 0, "TMA alignment");
 
 struct TileMap {
     const uint2 *tiles;   // [ntiles+1]  {first row, first stored entry}; tiles[ntiles] = {nrows, nnz}
@@ -165,49 +163,28 @@ struct RowEpilogue {
     }
 };
 
-// reduce rows [r0, r1) of a staged tile; products sit in sval[], entry e of the matrix at sval[e - a0].
-// SROWS: the tile's ptr[] and out[] segments were staged too (sptr[r - r0a], sold[r - r0a], the
-// latter for the first n_old rows), so the reduction touches global memory only to store.
-template <int G, int EPI, bool SROWS>
-__device__ __forceinline__ void reduce_rows(const StreamArgs &a, RowEpilogue<EPI> &epi, const double *sval,
-                                            const uint32_t *sptr, const double *sold, uint32_t n_old,
-                                            uint32_t r0, uint32_t r1, uint32_t a0, uint32_t r0a)
+// Row reduction with G lanes per row (G = 8 or 32) out of the products in sval[]; entry e of the matrix
+// sits at sval[e - a0].
+template <int G, int EPI>
+__device__ __forceinline__ void reduce_rows_group(const StreamArgs &a, RowEpilogue<EPI> &epi, const double *sval,
+                                                  uint32_t r0, uint32_t r1, uint32_t a0)
 {
     constexpr int kGroups = kStreamThreads / G;
     const int lane = threadIdx.x % G;
     const int grp = threadIdx.x / G;
-    const uint32_t nrows = r1 - r0;
-    const uint32_t rounds = (nrows + kGroups - 1) / kGroups;
-    for (uint32_t it = 0; it < rounds; ++it) {
-        const uint32_t r = r0 + it * kGroups + grp;
+    for (uint32_t rb = r0; rb < r1; rb += kGroups) {
+        const uint32_t r = rb + grp;
         const bool valid = r < r1;
         double s = 0.0, old = 0.0;
         if (valid) {
-            uint32_t p0, p1;
-            if (SROWS) { p0 = sptr[r - r0a] - a0; p1 = sptr[r - r0a + 1] - a0; }
-            else       { p0 = a.A.ptr[r] - a0;    p1 = a.A.ptr[r + 1] - a0; }
-            if (lane == 0 && epi.needs_old()) old = (SROWS && r - r0a < n_old) ? sold[r - r0a] : a.out[r];
+            const uint32_t p0 = a.A.ptr[r] - a0, p1 = a.A.ptr[r + 1] - a0;
+            if (lane == 0 && epi.needs_old()) old = a.out[r];
             for (uint32_t k = p0 + lane; k < p1; k += G) s += sval[k];
         }
 #pragma unroll
         for (int o = G / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         if (valid && lane == 0) epi.apply(a, r, s, old);
     }
-}
-
-template <int EPI, bool SROWS>
-__device__ __forceinline__ void reduce_tile(const StreamArgs &a, RowEpilogue<EPI> &epi, const double *sval,
-                                            const uint32_t *sptr, const double *sold, uint32_t n_old,
-                                            uint32_t r0, uint32_t r1, uint32_t a0, uint32_t r0a, uint32_t len)
-{
-    // lanes per row from the tile's mean row length
-    const uint32_t avg = len / (r1 - r0);
-    if (avg <= 4)       reduce_rows<1, EPI, SROWS>(a, epi, sval, sptr, sold, n_old, r0, r1, a0, r0a);
-    else if (avg <= 8)  reduce_rows<2, EPI, SROWS>(a, epi, sval, sptr, sold, n_old, r0, r1, a0, r0a);
-    else if (avg <= 16) reduce_rows<4, EPI, SROWS>(a, epi, sval, sptr, sold, n_old, r0, r1, a0, r0a);
-    else if (avg <= 32) reduce_rows<8, EPI, SROWS>(a, epi, sval, sptr, sold, n_old, r0, r1, a0, r0a);
-    else if (avg <= 64) reduce_rows<16, EPI, SROWS>(a, epi, sval, sptr, sold, n_old, r0, r1, a0, r0a);
-    else                reduce_rows<32, EPI, SROWS>(a, epi, sval, sptr, sold, n_old, r0, r1, a0, r0a);
 }
 
 // What a fused launch has to do, decided from the device state (uniform over the grid)
@@ -225,9 +202,7 @@ spmv_stream_kernel(StreamArgs a)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)kStages * kSlotBytes);
     auto slot_val = [&](int s) { return reinterpret_cast<double *>(smem_raw + (size_t)s * kSlotBytes); };
-    auto slot_old = [&](int s) { return slot_val(s) + kCapS; };
-    auto slot_idx = [&](int s) { return reinterpret_cast<int32_t *>(slot_old(s) + kOldS); };
-    auto slot_ptr = [&](int s) { return reinterpret_cast<uint32_t *>(slot_idx(s) + kCapS); };
+    auto slot_idx = [&](int s) { return reinterpret_cast<int32_t *>(slot_val(s) + kCapS); };
     __shared__ double s_red[kStreamThreads / 32];
 
     DevState *st = a.st;
@@ -274,32 +249,20 @@ spmv_stream_kernel(StreamArgs a)
         }
         __syncthreads();
 
+        const uint2 *tiles = a.map.tiles;
+        const int ntiles = a.map.ntiles;
+        const uint32_t *ptr = a.A.ptr;
+
         // producer (thread 0): stage tile t into ring slot `slot`; false if the tile needs no staging
-        const uint32_t out_rows = (uint32_t)a.A.nrows;
-        const bool stage_old = epi.needs_old() && a.out_aligned16;
         auto stage_tile = [&](int t, int slot) {
-            const uint2 t0 = a.map.tiles[t], t1 = a.map.tiles[t + 1];
+            const uint2 t0 = tiles[t], t1 = tiles[t + 1];
             const uint32_t len = t1.y - t0.y;
             if (t0.x == t1.x || len == 0 || len > (uint32_t)kCap) return false;   // rowless, empty or long tile
             const uint32_t a0 = t0.y & ~3u;
             const uint32_t cnt = ((t1.y + 3u) & ~3u) - a0;
-            uint32_t bytes = cnt * 12u;
-            const uint32_t nrows = t1.x - t0.x;
-            const uint32_t r0a = t0.x & ~3u;
-            uint32_t cnt_ptr = 0, cnt_old = 0;
-            if (nrows <= (uint32_t)kRowCap) {
-                cnt_ptr = ((t1.x + 1u + 3u) & ~3u) - r0a;                       // ptr[r0a .. r1], padded (array has slack)
-                bytes += cnt_ptr * 4u;
-                if (stage_old) {
-                    cnt_old = (min(t1.x, out_rows) - r0a) & ~1u;                // never read past the end of out[]
-                    bytes += cnt_old * 8u;
-                }
-            }
-            mbar_expect_tx(full + slot, bytes);
+            mbar_expect_tx(full + slot, cnt * 12u);
             tma_load_1d(slot_val(slot), a.A.val + a0, cnt * 8u, full + slot, pol_stream);
             tma_load_1d(slot_idx(slot), a.A.idx + a0, cnt * 4u, full + slot, pol_stream);
-            if (cnt_ptr) tma_load_1d(slot_ptr(slot), a.A.ptr + r0a, cnt_ptr * 4u, full + slot, pol_stream);
-            if (cnt_old) tma_load_1d(slot_old(slot), a.out + r0a, cnt_old * 8u, full + slot, pol_stream);
             return true;
         };
 
@@ -307,21 +270,26 @@ spmv_stream_kernel(StreamArgs a)
         int prod_n = 0;                   // tiles staged so far
         int cons_n = 0;                   // staged tiles consumed so far
         if (tid == 0) {
-            while (prod_n < kStages && prod_t < a.map.ntiles) {
+            while (prod_n < kStages && prod_t < ntiles) {
                 if (stage_tile(prod_t, prod_n % kStages)) ++prod_n;
                 prod_t += gridDim.x;
             }
         }
 
-        for (int t = blockIdx.x; t < a.map.ntiles; t += gridDim.x) {
-            const uint2 t0 = a.map.tiles[t], t1 = a.map.tiles[t + 1];
-            const uint32_t r0 = t0.x, r1 = t1.x, e0 = t0.y, e1 = t1.y;
+        uint2 d0 = make_uint2(0, 0), d1 = make_uint2(0, 0);
+        if ((int)blockIdx.x < ntiles) { d0 = tiles[blockIdx.x]; d1 = tiles[blockIdx.x + 1]; }
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+            const uint32_t r0 = d0.x, r1 = d1.x, e0 = d0.y, e1 = d1.y;
+            {   // descriptor of the next tile: in flight while this one is processed
+                const int tn = t + gridDim.x;
+                if (tn < ntiles) { d0 = tiles[tn]; d1 = tiles[tn + 1]; }
+            }
             const uint32_t len = e1 - e0;
             if (r0 == r1) continue;                       // no row starts in this tile (inside a long row)
             if (len > (uint32_t)kCap) {
                 // ---- long tile: every row straight from global memory, whole CTA per row
                 for (uint32_t r = r0; r < r1; ++r) {
-                    const uint32_t p0 = a.A.ptr[r], p1 = a.A.ptr[r + 1];
+                    const uint32_t p0 = ptr[r], p1 = ptr[r + 1];
                     double old = 0.0;
                     if (tid == 0 && epi.needs_old()) old = a.out[r];
                     double s = 0.0;
@@ -337,33 +305,75 @@ spmv_stream_kernel(StreamArgs a)
                 continue;
             }
             const uint32_t a0 = e0 & ~3u;
-            const uint32_t r0a = r0 & ~3u;
             const uint32_t nrows = r1 - r0;
-            const bool srows = len > 0 && nrows <= (uint32_t)kRowCap;
-            const uint32_t n_old = (srows && stage_old) ? ((min(r1, out_rows) - r0a) & ~1u) : 0u;
+            const bool thread_per_row = len <= 24u * nrows;          // mean row length <= 24
+            // thread-per-row mode: issue the row-pointer / old-value loads of the first rounds now, so their
+            // DRAM latency hides behind the gather phase
+            uint32_t pp0[kPrefRounds], pp1[kPrefRounds];
+            double pold[kPrefRounds];
+            if (thread_per_row) {
+#pragma unroll
+                for (int j = 0; j < kPrefRounds; ++j) {
+                    const uint32_t r = r0 + tid + j * kStreamThreads;
+                    pp0[j] = pp1[j] = 0u; pold[j] = 0.0;
+                    if (r < r1) {
+                        pp0[j] = ptr[r]; pp1[j] = ptr[r + 1];
+                        if (epi.needs_old()) pold[j] = a.out[r];
+                    }
+                }
+            }
             const int slot = cons_n % kStages;
             double *sv = slot_val(slot);
             if (len > 0) {
                 const int32_t *si = slot_idx(slot);
                 mbar_wait(full + slot, (uint32_t)(cons_n / kStages) & 1u);
-                // ---- gather + multiply in place
-                const uint32_t off = e0 - a0;
-#pragma unroll 4
-                for (uint32_t i = tid; i < len; i += kStreamThreads) {
-                    const uint32_t k = off + i;
-                    sv[k] = sv[k] * ldg_keep_f64(a.x + si[k], pol_keep);
+                // ---- gather + multiply in place, four consecutive entries per thread and step.  The aligned
+                // superset [a0, a1) may hold a few entries of the neighbouring tiles: harmless extra products.
+                const uint32_t ngroups = (((e1 + 3u) & ~3u) - a0) >> 2;
+#pragma unroll 2
+                for (uint32_t gq = tid; gq < ngroups; gq += kStreamThreads) {
+                    const int4 c = *reinterpret_cast<const int4 *>(si + 4 * gq);
+                    double2 v01 = *reinterpret_cast<const double2 *>(sv + 4 * gq);
+                    double2 v23 = *reinterpret_cast<const double2 *>(sv + 4 * gq + 2);
+                    const double x0 = ldg_keep_f64(a.x + c.x, pol_keep);
+                    const double x1 = ldg_keep_f64(a.x + c.y, pol_keep);
+                    const double x2 = ldg_keep_f64(a.x + c.z, pol_keep);
+                    const double x3 = ldg_keep_f64(a.x + c.w, pol_keep);
+                    v01.x *= x0; v01.y *= x1; v23.x *= x2; v23.y *= x3;
+                    *reinterpret_cast<double2 *>(sv + 4 * gq) = v01;
+                    *reinterpret_cast<double2 *>(sv + 4 * gq + 2) = v23;
                 }
                 __syncthreads();
             }
             // ---- row reduction out of shared memory
-            if (srows) reduce_tile<EPI, true>(a, epi, sv, slot_ptr(slot), slot_old(slot), n_old, r0, r1, a0, r0a, len);
-            else       reduce_tile<EPI, false>(a, epi, sv, nullptr, nullptr, 0u, r0, r1, a0, r0a, len);
+            if (thread_per_row) {
+#pragma unroll
+                for (int j = 0; j < kPrefRounds; ++j) {
+                    const uint32_t r = r0 + tid + j * kStreamThreads;
+                    if (r < r1) {
+                        double s = 0.0;
+                        for (uint32_t k = pp0[j] - a0; k < pp1[j] - a0; ++k) s += sv[k];
+                        epi.apply(a, r, s, pold[j]);
+                    }
+                }
+                for (uint32_t r = r0 + tid + kPrefRounds * kStreamThreads; r < r1; r += kStreamThreads) {
+                    const uint32_t p0 = ptr[r] - a0, p1 = ptr[r + 1] - a0;
+                    const double old = epi.needs_old() ? a.out[r] : 0.0;
+                    double s = 0.0;
+                    for (uint32_t k = p0; k < p1; ++k) s += sv[k];
+                    epi.apply(a, r, s, old);
+                }
+            } else if (len <= 96u * nrows) {
+                reduce_rows_group<8, EPI>(a, epi, sv, r0, r1, a0);
+            } else {
+                reduce_rows_group<32, EPI>(a, epi, sv, r0, r1, a0);
+            }
             if (len > 0) {
                 fence_proxy_async_smem();                 // order this thread's generic-proxy writes (products) before the async refill
                 __syncthreads();                          // everyone is done with this slot
                 ++cons_n;
                 if (tid == 0) {
-                    while (prod_t < a.map.ntiles) {
+                    while (prod_t < ntiles) {
                         const bool staged = stage_tile(prod_t, prod_n % kStages);
                         prod_t += gridDim.x;
                         if (staged) { ++prod_n; break; }
