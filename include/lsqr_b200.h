@@ -99,7 +99,8 @@ typedef struct lsqr_b200_options {
                                 (dscal / aprod / dnrm2 as separate kernels; for A/B parity) */
     int32_t use_graph;       /* 1 (default) = CUDA-graph the iteration, 0 = plain launches */
     int32_t profile;         /* 1 = time every kernel class with CUDA events (slower)  */
-    int32_t spmv_variant;    /* 0 = auto, 1 = sub-warp-per-row only, 2 = tile-streamed only */
+    int32_t spmv_variant;    /* 0 = default (3), 1 = sub-warp per row, 2 = CTA tiles streamed by TMA,
+                                3 = warp-autonomous segmented kernel */
     /* --- multi-GPU: A is row-partitioned, one process per GPU ----------- */
     int32_t world_size;      /* 1 (default) = single GPU                         */
     int32_t rank;

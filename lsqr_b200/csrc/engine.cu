@@ -18,6 +18,7 @@
 #include "build_csr.h"
 #include "kernels.cuh"
 #include "spmv_stream.cuh"
+#include "spmv_warp.cuh"
 
 namespace lsqrb {
 
@@ -222,14 +223,30 @@ static int launch_spmv(Work &wk, const Csr &M, int lanes, const double *x, doubl
 struct TileMapOwner {
     uint2 *tiles = nullptr;
     int ntiles = 0;
+    uint32_t tile = kTile;   // nominal stored entries per tile
+    int kind = 2;            // 2 = CTA tiles of the TMA-streamed kernel, 3 = warp tiles of the segmented kernel
 };
 
-static int build_tile_map(Work &wk, const Csr &M, TileMapOwner *out)
+// Variant 3 sizes its tiles so that every warp of the persistent grid gets the same number of them
+// (k tiles of ~8K entries or less each): a small matrix is cut into exactly one tile per warp.
+static uint32_t warp_tile_size(const Work &wk, int64_t nnz)
 {
-    const int64_t nt = std::max<int64_t>(1, (M.nnz + kTile - 1) / kTile);
+    const int forced = env_int("LSQR_B200_WARP_TILE", 0);
+    if (forced >= 128) return (uint32_t)forced;
+    const int64_t nwarps = (int64_t)wk.sms * kWMinBlocks * kWWarps;
+    const int64_t k = std::max<int64_t>(1, (nnz + nwarps * 8192 - 1) / (nwarps * 8192));
+    const int64_t t = (nnz + nwarps * k - 1) / (nwarps * k);
+    return (uint32_t)std::max<int64_t>(512, (t + 3) & ~(int64_t)3);
+}
+
+static int build_tile_map(Work &wk, const Csr &M, int kind, TileMapOwner *out)
+{
+    out->kind = kind;
+    out->tile = kind == 3 ? warp_tile_size(wk, M.nnz) : (uint32_t)kTile;
+    const int64_t nt = std::max<int64_t>(1, (M.nnz + out->tile - 1) / out->tile);
     out->ntiles = (int)nt;
     LSQRB_CUDA(cudaMalloc(&out->tiles, sizeof(uint2) * (size_t)(nt + 1)));
-    build_tiles_kernel<<<(int)((nt + 1 + 255) / 256), 256, 0, wk.stream>>>(M.ptr, M.nrows, M.nnz, (int)nt, out->tiles);
+    build_tiles_kernel<<<(int)((nt + 1 + 255) / 256), 256, 0, wk.stream>>>(M.ptr, M.nrows, M.nnz, (int)nt, out->tile, out->tiles);
     LSQRB_CUDA(cudaGetLastError());
     return LSQR_B200_OK;
 }
@@ -261,8 +278,6 @@ template <int EPI>
 static int launch_stream(Work &wk, const Csr &M, const TileMapOwner &map, const double *x, double *out, double *aux,
                          const StreamExtra &ex = StreamExtra())
 {
-    int occ = 1;
-    LSQRB_TRY(stream_kernel_prepare<EPI>(&occ));
     StreamArgs a;
     a.A = CsrView{M.ptr, M.idx, M.val, M.nrows};
     a.map = TileMap{map.tiles, map.ntiles};
@@ -270,8 +285,15 @@ static int launch_stream(Work &wk, const Csr &M, const TileMapOwner &map, const 
     a.ux = ex.ux; a.uw = ex.uw; a.use = ex.use;
     a.ring = wk.ring_d;
     a.out_aligned16 = ((uintptr_t)out & 15u) == 0;
-    const int grid = std::max(1, std::min(map.ntiles, std::min(wk.stream_grid, wk.sms * occ)));
-    spmv_stream_kernel<EPI><<<grid, kStreamThreads, kStreamSmem, wk.stream>>>(a);
+    if (map.kind == 3) {
+        const int grid = std::max(1, std::min((map.ntiles + kWWarps - 1) / kWWarps, wk.sms * kWMinBlocks));
+        spmv_warp_kernel<EPI><<<grid, kWThreads, 0, wk.stream>>>(a);
+    } else {
+        int occ = 1;
+        LSQRB_TRY(stream_kernel_prepare<EPI>(&occ));
+        const int grid = std::max(1, std::min(map.ntiles, std::min(wk.stream_grid, wk.sms * occ)));
+        spmv_stream_kernel<EPI><<<grid, kStreamThreads, kStreamSmem, wk.stream>>>(a);
+    }
     wk.launches++;
     LSQRB_CUDA(cudaGetLastError());
     return LSQR_B200_OK;
@@ -556,12 +578,12 @@ static int ez_initialize_impl(lsqr_b200_ez *me, int64_t nnz, const double *a, co
 
     me->lanes_a = pick_lanes(me->A, "LSQR_B200_LANES_A");
     me->lanes_at = pick_lanes(me->AT, "LSQR_B200_LANES_AT");
-    const int variant = me->opt.spmv_variant ? me->opt.spmv_variant : env_int("LSQR_B200_SPMV_VARIANT", 2);
+    const int variant = me->opt.spmv_variant ? me->opt.spmv_variant : env_int("LSQR_B200_SPMV_VARIANT", 3);
     me->stream = variant != 1;
     me->deferred = me->stream && me->opt.world_size == 1 && env_int("LSQR_B200_DEFERRED_UPDATE", 1) != 0;
     if (me->stream) {
-        LSQRB_TRY(build_tile_map(wk, me->A, &me->mapA));
-        LSQRB_TRY(build_tile_map(wk, me->AT, &me->mapAT));
+        LSQRB_TRY(build_tile_map(wk, me->A, variant == 2 ? 2 : 3, &me->mapA));
+        LSQRB_TRY(build_tile_map(wk, me->AT, variant == 2 ? 2 : 3, &me->mapAT));
         LSQRB_CUDA(cudaStreamSynchronize(wk.stream));
     }
 

@@ -218,6 +218,13 @@ class LsqrSolverEz:
             raise LsqrError(4, "lsqr_solver_ez class not properly initialized")
         _lib.check(_lib.load().lsqr_b200_ez_aprod(self._h, int(mode), int(m), int(n), _ptr(x), _ptr(y)))
 
+    def aprod_device(self, mode: int, m: int, n: int, x, y, stream: int = 0) -> None:
+        """aprod on DEVICE vectors, enqueued on `stream` without synchronising (lsqr_b200_ez_aprod_device)."""
+        if not self._h:
+            raise LsqrError(4, "lsqr_solver_ez class not properly initialized")
+        _lib.check(_lib.load().lsqr_b200_ez_aprod_device(self._h, int(mode), int(m), int(n), _ptr(x), _ptr(y),
+                                                        int(stream) or None))
+
     # parity inspection
     @property
     def nnz(self) -> int:

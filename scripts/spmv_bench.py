@@ -1,0 +1,104 @@
+#!/usr/bin/env python
+"""Kernel-level A/B bench of the SpMV variants on the BASELINE workload families (GPU box only).
+
+    python scripts/spmv_bench.py [--variants 2,3] [--workloads C2:1,C3:5,C5:20,C4:10] [--reps 20]
+
+For every workload (name:scale) and variant it times y += A x (mode 1) and x += A'y (mode 2) through the
+C ABI (lsqr_b200_ez_aprod on device vectors) with CUDA events on the stream the kernels run on, reports
+algorithmic GB/s against MEASURED_PEAKS.json, cross-checks the variants against each other, and times a
+full solve.  One JSON line per (workload, variant).
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+import lsqr_b200
+from lsqr_b200 import synth, synth_device
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--variants", default="2,3")
+    ap.add_argument("--workloads", default="C2:1,C3:5,C5:20,C4:10")
+    ap.add_argument("--reps", type=int, default=20)
+    ap.add_argument("--solve", type=int, default=1)
+    args = ap.parse_args()
+    peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    dev = torch.device("cuda", 0)
+    ts = torch.cuda.Stream()
+    torch.cuda.set_stream(ts)
+    stream = ts.cuda_stream
+    for wl in args.workloads.split(","):
+        name, scale = wl.split(":")
+        cfg = synth.scaled(name, float(scale))
+        m, n = cfg["m"], cfg["n"]
+        irow, icol, a = synth_device.coo_block(cfg["kind"], cfg["seed"], m, n, cfg["k"], 0, m, dev)
+        nnz = a.numel()
+        xt = synth_device.x_true(cfg["seed"], n, dev)
+        yt = synth_device.noise(cfg["seed"], 0, m, dev, scale=1.0)
+        ref = {}
+        for variant in [int(v) for v in args.variants.split(",")]:
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            s = lsqr_b200.LsqrSolverEz().initialize(m, n, a, irow, icol, stream=stream, spmv_variant=variant,
+                                                    atol=1e-10, btol=1e-10, conlim=1e8, itnlim=100000)
+            torch.cuda.synchronize()
+            t_init = time.perf_counter() - t0
+            out = {"workload": f"{name}/{scale}", "m": m, "n": n, "nnz": nnz, "variant": variant, "init_s": round(t_init, 3)}
+            for mode in (1, 2):
+                x = xt.clone()
+                y = yt.clone()
+                s.aprod(mode, m, n, x, y)
+                res = (y if mode == 1 else x).clone()
+                key = f"mode{mode}"
+                if key in ref:
+                    out[f"{key}_maxrel_vs_first"] = float((res - ref[key]).abs().max() / ref[key].abs().max())
+                else:
+                    ref[key] = res
+                for _ in range(3):
+                    s.aprod_device(mode, m, n, x, y, stream)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(args.reps):
+                    s.aprod_device(mode, m, n, x, y, stream)
+                e1.record()
+                torch.cuda.synchronize()
+                us = e0.elapsed_time(e1) * 1e3 / args.reps
+                rows, cols = (m, n) if mode == 1 else (n, m)
+                byts = 12 * nnz + 4 * (rows + 1) + 8 * cols + 16 * rows
+                out[f"{key}_us"] = round(us, 2)
+                out[f"{key}_GBps"] = round(byts / us / 1e3, 1)
+                out[f"{key}_frac"] = round(byts / us / 1e3 / peak, 4)
+            if args.solve:
+                b = yt.clone()
+                s.aprod(1, m, n, xt.clone(), b)
+                xo = torch.empty(n, dtype=torch.float64, device=dev)
+                s.solve(b, cfg["damp"], x=xo)
+                r = s.solve(b, cfg["damp"], x=xo)
+                kt = s.kernel_times()
+                biter = synth.b_iter_bytes(nnz, m, n)
+                out.update(itn=r.itn, istop=r.istop, loop_ms=round(kt["loop_ms"], 3),
+                           us_per_iter=round(1e3 * kt["loop_ms"] / max(r.itn, 1), 2),
+                           loop_frac=round(biter * r.itn / (kt["loop_ms"] * 1e-3) / 1e9 / peak, 4))
+                key = "x"
+                xs = xo.clone()
+                if key in ref:
+                    out["x_rel_vs_first"] = float((xs - ref[key]).norm() / ref[key].norm())
+                else:
+                    ref[key] = xs
+            print(json.dumps(out), flush=True)
+            del s
+        del irow, icol, a
+        torch.cuda.empty_cache()
+
+
+if __name__ == "__main__":
+    main()

@@ -189,17 +189,18 @@ def _assert_parity(data, r, ref, itn_tol=2, rtol=RTOL):
     assert abs(rn - rn_ref) <= rtol * rn_ref
     # ||A'r|| at convergence is a difference of nearly equal vectors; compare relative to ||A|| ||r||
     assert abs(arn - arn_ref) <= rtol * ref.anorm * rn_ref
-    # anorm / acond / xnorm grow with every iteration: compare them at the last COMMON iteration
+    # anorm / acond / xnorm grow with every iteration: compare them at common iterations.  Up to iteration 40
+    # they must agree tightly.  Later Lanczos scalars (alpha_k, beta_k) drift between summation orders once
+    # orthogonality is lost, although x converges identically; the running estimates inherit that drift,
+    # so at the last common iteration of a long run only their magnitude is pinned (2 %).
     k = min(r.itn, ref.itn)
     if k >= 1 and r.trace and ref.trace:
-        g = next(t for t in r.trace if int(t["itn"]) == k)
-        w = next(t for t in ref.trace if t["itn"] == k)
-        # Late Lanczos scalars (alpha_k, beta_k) drift between summation orders once orthogonality is lost,
-        # although x converges identically; the running estimates inherit that drift on long runs.
-        loose = k > 40
-        for key, tol in (("anorm", 1e-3 if loose else 1e-9), ("acond", 1e-3 if loose else 1e-8),
-                         ("xnorm", 1e-8 if loose else 1e-9), ("rnorm", 1e-9)):
-            assert abs(g[key] - w[key]) <= tol * abs(w[key]), (key, k, g[key], w[key])
+        for kk, loose in ((min(k, 40), False), (k, k > 40)):
+            g = next(t for t in r.trace if int(t["itn"]) == kk)
+            w = next(t for t in ref.trace if t["itn"] == kk)
+            for key, tol in (("anorm", 2e-2 if loose else 1e-9), ("acond", 2e-2 if loose else 1e-8),
+                             ("xnorm", 1e-8 if loose else 1e-9), ("rnorm", 1e-9)):
+                assert abs(g[key] - w[key]) <= tol * abs(w[key]), (key, kk, g[key], w[key])
     if r.itn == ref.itn and r.itn <= 40:
         assert abs(r.anorm - ref.anorm) <= 1e-9 * ref.anorm
         assert abs(r.xnorm - ref.xnorm) <= 1e-9 * ref.xnorm
@@ -217,26 +218,29 @@ def test_solve_parity_scaled_configs(lb, name, scale, shuffle, tol):
 
 
 @pytest.mark.parametrize("name,scale", [("C2", 10), ("C3", 100), ("C4", 100)])
-def test_solve_parity_subwarp_variant(lb, name, scale):
-    """Variant 1 (sub-warp per row, separate update kernel) against the oracle and against variant 2."""
+@pytest.mark.parametrize("variant", [1, 2])
+def test_solve_parity_other_variants(lb, name, scale, variant):
+    """Variant 1 (sub-warp per row, separate update kernel) and variant 2 (CTA tiles streamed by TMA) against
+    the oracle and against the default variant 3 (warp-autonomous segmented kernel)."""
     from lsqr_b200 import synth
     cfg = synth.scaled(name, scale)
-    data, r1, ref = _solve_both(lb, cfg, 1e-10, 1e-10, 1e8, 4000, spmv_variant=1)
+    data, r1, ref = _solve_both(lb, cfg, 1e-10, 1e-10, 1e8, 4000, spmv_variant=variant)
     _assert_parity(data, r1, ref)
-    _, r2, _ = _solve_both(lb, cfg, 1e-10, 1e-10, 1e8, 4000, spmv_variant=2)
-    assert r1.istop == r2.istop and abs(r1.itn - r2.itn) <= 1
-    assert relerr(r1.x, r2.x) <= RTOL
+    _, r3, _ = _solve_both(lb, cfg, 1e-10, 1e-10, 1e8, 4000, spmv_variant=3)
+    assert r1.istop == r3.istop and abs(r1.itn - r3.itn) <= 1
+    assert relerr(r1.x, r3.x) <= RTOL
 
 
-def test_long_rows_take_the_whole_cta_path(lb):
-    """Rows longer than a ring slot (and a 1-entry-per-row tail) through the tile-streamed kernels."""
+@pytest.mark.parametrize("variant", [2, 3])
+def test_long_rows_among_single_entry_rows(lb, variant):
+    """Rows far longer than a tile / chunk (and a 1-entry-per-row tail) through the tiled kernels."""
     rng = np.random.default_rng(8)
     m, n = 600, 9000
     lens = np.where(np.arange(m) % 97 == 0, 5000, 1)          # a few 5000-entry rows among 1-entry rows
     irow = np.repeat(np.arange(1, m + 1), lens).astype(np.int32)
     icol = rng.integers(1, n + 1, irow.size).astype(np.int32)
     a = rng.standard_normal(irow.size)
-    s = lb.LsqrSolverEz().initialize(m, n, a, irow, icol)
+    s = lb.LsqrSolverEz().initialize(m, n, a, irow, icol, spmv_variant=variant)
     ref = O.SolverEz(m, n, a, irow, icol)
     x, y = rng.standard_normal(n), rng.standard_normal(m)
     y1, yr = y.copy(), y.copy()
@@ -245,6 +249,36 @@ def test_long_rows_take_the_whole_cta_path(lb):
     x2, xr = x.copy(), x.copy()
     s.aprod(2, m, n, x2, y); ref.aprod(2, xr, y.copy())
     assert relerr(x2, xr) <= 1e-13
+
+
+@pytest.mark.parametrize("variant", [1, 2, 3])
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_ragged_rows_with_gaps(lb, variant, seed):
+    """Row lengths 0..300 drawn at random (many empty rows, runs of 1-entry rows, rows crossing chunk and tile
+    boundaries), forced small warp tiles: products and fused epilogues against the oracle."""
+    rng = np.random.default_rng(100 + seed)
+    m, n = 20_000, 3000
+    lens = rng.choice([0, 0, 1, 1, 2, 3, 5, 8, 31, 32, 33, 127, 128, 129, 300], size=m)
+    lens[rng.integers(0, m, 50)] = 0
+    if seed == 1:
+        lens[:200] = 0                                         # leading empty rows
+        lens[-300:] = 0                                        # trailing empty rows
+    irow = np.repeat(np.arange(1, m + 1), lens).astype(np.int32)
+    icol = rng.integers(1, n + 1, irow.size).astype(np.int32)
+    a = rng.standard_normal(irow.size)
+    s = lb.LsqrSolverEz().initialize(m, n, a, irow, icol, atol=1e-12, btol=1e-12, itnlim=60, spmv_variant=variant)
+    ref = O.SolverEz(m, n, a, irow, icol, atol=1e-12, btol=1e-12, itnlim=60)
+    x, y = rng.standard_normal(n), rng.standard_normal(m)
+    y1, yr = y.copy(), y.copy()
+    s.aprod(1, m, n, x, y1); ref.aprod(1, x.copy(), yr)
+    assert relerr(y1, yr) <= 1e-14
+    x2, xr = x.copy(), x.copy()
+    s.aprod(2, m, n, x2, y); ref.aprod(2, xr, y.copy())
+    assert relerr(x2, xr) <= 1e-14
+    b = rng.standard_normal(m)
+    r, rr = s.solve(b, 0.1), ref.solve(b, 0.1)
+    assert r.istop == rr.istop and abs(r.itn - rr.itn) <= 2
+    assert relerr(r.x, rr.x) <= 1e-9
 
 
 def test_solve_parity_c2_full_size(lb):
@@ -441,3 +475,20 @@ def test_device_blas1(lb):
         lb.dcopy(n, xd, yd)
         assert torch.equal(xd, yd)
     assert lb.dnrm2(0, torch.zeros(1, dtype=torch.float64, device="cuda")) == 0.0
+
+
+# ------------------------------------------------------------------ K9: device generators == host generators
+@pytest.mark.parametrize("kind,k", [("uniform", 10), ("banded", 50), ("powerlaw", 0)])
+def test_device_generator_is_bit_identical_to_host(lb, kind, k):
+    import torch
+    from lsqr_b200 import synth, synth_device
+    m, n, seed = 40_000, 9_000, 5
+    dev = torch.device("cuda", 0)
+    for row0, nrows in ((0, m), (12_345, 7_000)):
+        irow, icol, a = synth.coo_block(kind, seed, m, n, k, row0, nrows)
+        dirow, dicol, da = synth_device.coo_block(kind, seed, m, n, k, row0, nrows, dev)
+        np.testing.assert_array_equal(dirow.cpu().numpy(), irow)
+        np.testing.assert_array_equal(dicol.cpu().numpy(), icol)
+        assert da.cpu().numpy().tobytes() == a.tobytes()
+    assert synth_device.x_true(seed, n, dev).cpu().numpy().tobytes() == synth.x_true(seed, n).tobytes()
+    assert synth_device.noise(seed, 77, 1000, dev).cpu().numpy().tobytes() == synth.noise(seed, 77, 1000).tobytes()
