@@ -129,18 +129,22 @@ struct StreamArgs {
 
 template <int EPI>
 struct RowEpilogue {
-    double cm = 1.0, cv = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0, ia = 1.0;
+    double cm = 1.0, cv = 0.0;
     bool upd = false, wantse = false;
     double sq = 0.0, sq2 = 0.0;
+    // coefficients of the deferred x/w update; elementwise fallback modes read them once, the row epilogue
+    // re-reads them from the (L1-resident, kernel-invariant) device state to keep registers free
+    double t1 = 0.0, t2 = 0.0, t3 = 0.0, ia = 1.0;
 
     __device__ __forceinline__ void load(const DevState *st)
     {
         if (EPI == SEPI_APROD) { cm = st->ca_mat; cv = st->ca_vec; }
         if (EPI == SEPI_ATPROD || EPI == SEPI_INIT_ATPROD || EPI == SEPI_ATPROD_UPD) { cm = st->ct_mat; cv = st->ct_vec; }
-        if (EPI == SEPI_ATPROD_UPD) {
-            upd = st->upd_pending != 0; wantse = st->wantse != 0;
-            t1 = st->t1; t2 = st->t2; t3 = st->t3; ia = st->inv_alpha;
-        }
+        if (EPI == SEPI_ATPROD_UPD) { upd = st->upd_pending != 0; wantse = st->wantse != 0; }
+    }
+    __device__ __forceinline__ void load_update_coefficients(const DevState *st)
+    {
+        t1 = st->t1; t2 = st->t2; t3 = st->t3; ia = st->inv_alpha;
     }
     // `old` = out[row] fetched before the row sum (hides the DRAM latency behind the reduction)
     __device__ __forceinline__ bool needs_old() const { return EPI == SEPI_APROD || EPI == SEPI_ATPROD || EPI == SEPI_ACC || EPI == SEPI_ATPROD_UPD; }
@@ -153,12 +157,14 @@ struct RowEpilogue {
         a.out[row] = r;
         sq += r * r;
         if (EPI == SEPI_ATPROD_UPD && upd) {
+            const DevState *st = a.st;
+            const double c1 = __ldg(&st->t1), c2 = __ldg(&st->t2), cia = __ldg(&st->inv_alpha);
             const double wo = a.uw[row];
-            a.ux[row] = t1 * wo + a.ux[row];
-            const double wn = t2 * wo + ia * old;
+            a.ux[row] = c1 * wo + a.ux[row];
+            const double wn = c2 * wo + cia * old;
             a.uw[row] = wn;
             sq2 += wn * wn;
-            if (wantse) a.use[row] += (t3 * wo) * (t3 * wo);
+            if (wantse) { const double c3 = __ldg(&st->t3); a.use[row] += (c3 * wo) * (c3 * wo); }
         }
     }
 };
@@ -230,6 +236,7 @@ spmv_stream_kernel(StreamArgs a)
     if (mode != MODE_FULL) {
         // elementwise part only (n-vectors): x += t1 w [; w' = v/alpha + t2 w]
         if (epi.upd) {
+            epi.load_update_coefficients(st);
             const int64_t n = a.A.nrows;
             for (int64_t i = (int64_t)blockIdx.x * kStreamThreads + tid; i < n; i += (int64_t)gridDim.x * kStreamThreads) {
                 const double wo = a.uw[i];

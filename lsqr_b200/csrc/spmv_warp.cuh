@@ -54,133 +54,155 @@ struct RowWindow {
     }
 };
 
+// One lane's share of a chunk: 4 consecutive stored entries.
+struct ChunkRegs {
+    double v[4];
+    int32_t c[4];
+};
+
+// Loads entries [q, q+4) of the tile [e0, e1).  Entries outside the tile (they belong to the neighbouring
+// tiles or to the allocation slack) get the value 0 and so add nothing to any row; their column index
+// stays a valid one.  Lanes entirely past the tile read nothing (index 0: a harmless in-bounds gather).
+__device__ __forceinline__ void load_chunk(const CsrView &A, uint32_t q, uint32_t e0, uint32_t e1, uint64_t pol_stream, ChunkRegs &r)
+{
+    if (q < e1) {
+        ldg_stream_f64x4(A.val + q, r.v);
+        ldg_stream_s32x4(A.idx + q, r.c, pol_stream);
+        if (q < e0 || q + 4u > e1) {   // only the first and the last chunk of a tile
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (q + k < e0 || q + k >= e1) r.v[k] = 0.0;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { r.v[k] = 0.0; r.c[k] = 0; }
+    }
+}
+
+template <int EPI>
+struct WarpTileState {
+    uint32_t wb, woff;     // window base row, lanes below woff are finished rows
+    RowWindow<EPI> win;
+    double carry;          // running sum of the row that is open at the chunk boundary
+};
+
+// Processes the chunk [base, base+128) held in `cur`; `nxt` receives the following chunk, whose loads
+// stay in flight while this one is reduced.
+template <int EPI>
+__device__ __forceinline__ void warp_chunk(const StreamArgs &a, RowEpilogue<EPI> &epi, double *su, WarpTileState<EPI> &ts,
+                                           const ChunkRegs &cur, ChunkRegs &nxt, uint32_t base, uint32_t r1, uint32_t e0, uint32_t e1,
+                                           int lane, uint64_t pol_stream, uint64_t pol_keep)
+{
+    const uint32_t endp = base + kChunk;
+    // ---- gathers of this chunk, then the stream of the next one
+    const double x0 = ldg_keep_f64(a.x + cur.c[0], pol_keep);
+    const double x1 = ldg_keep_f64(a.x + cur.c[1], pol_keep);
+    const double x2 = ldg_keep_f64(a.x + cur.c[2], pol_keep);
+    const double x3 = ldg_keep_f64(a.x + cur.c[3], pol_keep);
+    load_chunk(a.A, endp + 4u * (uint32_t)lane, e0, e1, pol_stream, nxt);
+
+    // ---- head mask of the chunk: bit i set <=> a row starts at entry base+i
+    uint32_t m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+    {
+        uint32_t p = ts.win.P;
+        uint32_t wb2 = ts.wb;
+        for (;;) {
+            const uint32_t rel = p - base;
+            const uint32_t bit = rel < kChunk ? (1u << (rel & 31u)) : 0u;
+            const uint32_t w = rel >> 5;
+            m0 |= __reduce_or_sync(0xffffffffu, w == 0u ? bit : 0u);
+            m1 |= __reduce_or_sync(0xffffffffu, w == 1u ? bit : 0u);
+            m2 |= __reduce_or_sync(0xffffffffu, w == 2u ? bit : 0u);
+            m3 |= __reduce_or_sync(0xffffffffu, w == 3u ? bit : 0u);
+            const uint32_t p31 = __shfl_sync(0xffffffffu, p, 31);
+            if (p31 >= endp || wb2 + 32u >= r1) break;     // (the sentinel ends the walk too)
+            wb2 += 32u;                                    // more than a window of rows starts in this chunk
+            const uint32_t r = wb2 + (uint32_t)lane;
+            p = r < r1 ? a.A.ptr[r] : kPtrSentinel;
+        }
+    }
+    const uint32_t mw = (lane < 8) ? m0 : (lane < 16) ? m1 : (lane < 24) ? m2 : m3;
+    const uint32_t f = (mw >> ((lane & 7) * 4)) & 0xFu;
+
+    // ---- products; segmented running sums inside the lane (t_k = sum of the lane's entries of the segment
+    // that entry k belongs to, up to and including k)
+    double t0 = cur.v[0] * x0;
+    if (lane == 0 && !(f & 1u)) t0 = ts.carry + t0;        // row that began in an earlier chunk
+    double t1 = cur.v[1] * x1;
+    if (!(f & 2u)) t1 += t0;
+    double t2 = cur.v[2] * x2;
+    if (!(f & 4u)) t2 += t1;
+    double t3 = cur.v[3] * x3;
+    if (!(f & 8u)) t3 += t2;
+    // ---- ... and across lanes (Kogge-Stone; lane l takes lane l-d iff no head lies in lanes (l-d, l])
+    const uint32_t hb = __ballot_sync(0xffffffffu, f != 0u);
+    const uint32_t below = hb & (0xffffffffu >> (31 - lane));
+    const int reach = lane - (below ? 31 - __clz(below) : 0);   // how far down this lane's open segment extends
+    double vs = t3;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const double y = __shfl_up_sync(0xffffffffu, vs, d);
+        if (d <= reach) vs += y;
+    }
+    double cin = __shfl_up_sync(0xffffffffu, vs, 1);
+    if (lane == 0) cin = 0.0;
+    // entries that precede the lane's first head continue the segment of the lanes below
+    if (!(f & 1u)) t0 += cin;
+    if (!(f & 3u)) t1 += cin;
+    if (!(f & 7u)) t2 += cin;
+    if (!(f & 15u)) t3 += cin;
+    ts.carry = __shfl_sync(0xffffffffu, t3, 31);
+    *reinterpret_cast<double2 *>(su + 4 * lane) = make_double2(t0, t1);
+    *reinterpret_cast<double2 *>(su + 4 * lane + 2) = make_double2(t2, t3);
+    __syncwarp();
+
+    // ---- rows that end in this chunk: lane j finishes row wb+j (the sentinel of absent rows never ends)
+    for (;;) {
+        const bool ends = (uint32_t)lane >= ts.woff && ts.win.PE <= endp;
+        if (ends) {
+            const double s = (ts.win.PE != ts.win.P) ? su[ts.win.PE - 1u - base] : 0.0;
+            epi.apply(a, (int64_t)ts.wb + lane, s, ts.win.O);
+        }
+        ts.woff += (uint32_t)__popc(__ballot_sync(0xffffffffu, ends));
+        if (ts.woff >= 32u && ts.wb + 32u < r1) {          // window exhausted: more rows may end here
+            ts.wb += 32u;
+            ts.woff = 0;
+            ts.win.load(a, epi, ts.wb, r1, lane);
+            continue;
+        }
+        break;
+    }
+    __syncwarp();
+    // keep the window ahead of the stream: the reload is in flight during the next chunk
+    if (endp < e1 && ts.woff >= 16u && ts.wb + ts.woff < r1) {
+        ts.wb += ts.woff;
+        ts.woff = 0;
+        ts.win.load(a, epi, ts.wb, r1, lane);
+    }
+}
+
 template <int EPI>
 __device__ __forceinline__ void warp_tile(const StreamArgs &a, RowEpilogue<EPI> &epi, double *su /* 128 doubles, this warp's */,
                                           uint32_t r0, uint32_t r1, uint32_t e0, uint32_t e1, int lane,
                                           uint64_t pol_stream, uint64_t pol_keep)
 {
     const uint32_t a0 = e0 & ~3u;
-    const uint32_t *__restrict__ ptr = a.A.ptr;
-    uint32_t wb = r0, woff = 0;
-    RowWindow<EPI> win;
-    win.load(a, epi, wb, r1, lane);
-
-    double v[4] = {0.0, 0.0, 0.0, 0.0};
-    int32_t c[4] = {0, 0, 0, 0};
-    {
-        const uint32_t q = a0 + 4u * (uint32_t)lane;
-        if (q < e1) {
-            ldg_stream_f64x4(a.A.val + q, v);
-            ldg_stream_s32x4(a.A.idx + q, c, pol_stream);
-        }
-    }
-    double carry = 0.0;
-
-    // (at least one pass, so that a tile of empty rows still gets its epilogue)
-    for (uint32_t base = a0;; base += kChunk) {
-        const uint32_t endp = base + kChunk;
-        const uint32_t q = base + 4u * (uint32_t)lane;
-
-        // ---- gathers of this chunk (invalid lanes hold index 0: a harmless in-bounds read)
-        const double x0 = ldg_keep_f64(a.x + c[0], pol_keep);
-        const double x1 = ldg_keep_f64(a.x + c[1], pol_keep);
-        const double x2 = ldg_keep_f64(a.x + c[2], pol_keep);
-        const double x3 = ldg_keep_f64(a.x + c[3], pol_keep);
-        const double cv0 = v[0], cv1 = v[1], cv2 = v[2], cv3 = v[3];
-
-        // ---- stream of the next chunk, in flight while this one is reduced
-        {
-            const uint32_t qn = q + kChunk;
-            v[0] = v[1] = v[2] = v[3] = 0.0;
-            c[0] = c[1] = c[2] = c[3] = 0;
-            if (qn < e1) {
-                ldg_stream_f64x4(a.A.val + qn, v);
-                ldg_stream_s32x4(a.A.idx + qn, c, pol_stream);
-            }
-        }
-
-        // ---- head mask of the chunk: bit i set <=> a row starts at entry base+i
-        uint32_t m0 = 0, m1 = 0, m2 = 0, m3 = 0;
-        {
-            uint32_t p = win.P;
-            uint32_t wb2 = wb;
-            for (;;) {
-                const uint32_t rel = p - base;
-                const bool hv = rel < kChunk;
-                const uint32_t bit = hv ? (1u << (rel & 31u)) : 0u;
-                const uint32_t w = rel >> 5;
-                m0 |= __reduce_or_sync(0xffffffffu, w == 0u ? bit : 0u);
-                m1 |= __reduce_or_sync(0xffffffffu, w == 1u ? bit : 0u);
-                m2 |= __reduce_or_sync(0xffffffffu, w == 2u ? bit : 0u);
-                m3 |= __reduce_or_sync(0xffffffffu, w == 3u ? bit : 0u);
-                const uint32_t p31 = __shfl_sync(0xffffffffu, p, 31);
-                if (p31 >= endp || wb2 + 32u >= r1) break;     // (the sentinel ends the walk too)
-                wb2 += 32u;                                    // more than a window of rows starts in this chunk
-                const uint32_t r = wb2 + (uint32_t)lane;
-                p = r < r1 ? ptr[r] : kPtrSentinel;
-            }
-        }
-        const uint32_t mw = (lane < 8) ? m0 : (lane < 16) ? m1 : (lane < 24) ? m2 : m3;
-        const uint32_t f = (mw >> ((lane & 7) * 4)) & 0xFu;
-
-        // ---- products (entries outside [e0, e1) belong to other tiles), carry of a row that began earlier
-        double p0 = (q + 0u >= e0 && q + 0u < e1) ? cv0 * x0 : 0.0;
-        const double p1 = (q + 1u >= e0 && q + 1u < e1) ? cv1 * x1 : 0.0;
-        const double p2 = (q + 2u >= e0 && q + 2u < e1) ? cv2 * x2 : 0.0;
-        const double p3 = (q + 3u >= e0 && q + 3u < e1) ? cv3 * x3 : 0.0;
-        if (lane == 0 && !(f & 1u)) p0 = carry + p0;
-
-        // ---- segmented running sums inside the lane ...
-        const double t0 = p0;
-        const double t1 = (f & 2u) ? p1 : t0 + p1;
-        const double t2 = (f & 4u) ? p2 : t1 + p2;
-        const double t3 = (f & 8u) ? p3 : t2 + p3;
-        // ---- ... and across lanes (Kogge-Stone; lane l takes lane l-d iff no head lies in lanes (l-d, l])
-        const uint32_t hb = __ballot_sync(0xffffffffu, f != 0u);
-        const uint32_t below = hb & (0xffffffffu >> (31 - lane));
-        const int ss = below ? 31 - __clz(below) : -1;          // last lane <= this one that holds a head
-        double vs = t3;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const double y = __shfl_up_sync(0xffffffffu, vs, d);
-            if (lane - d >= ss && lane >= d) vs += y;
-        }
-        double cin = __shfl_up_sync(0xffffffffu, vs, 1);
-        if (lane == 0) cin = 0.0;
-        double2 u01, u23;
-        u01.x = (f & 1u) ? t0 : t0 + cin;
-        u01.y = (f & 3u) ? t1 : t1 + cin;
-        u23.x = (f & 7u) ? t2 : t2 + cin;
-        u23.y = (f & 15u) ? t3 : t3 + cin;
-        carry = __shfl_sync(0xffffffffu, u23.y, 31);
-        *reinterpret_cast<double2 *>(su + 4 * lane) = u01;
-        *reinterpret_cast<double2 *>(su + 4 * lane + 2) = u23;
-        __syncwarp();
-
-        // ---- rows that end in this chunk: lane j finishes row wb+j
-        for (;;) {
-            const bool ends = (uint32_t)lane >= woff && win.PE != kPtrSentinel && win.PE <= endp;
-            if (ends) {
-                const double s = (win.PE != win.P) ? su[win.PE - 1u - base] : 0.0;
-                epi.apply(a, (int64_t)wb + lane, s, win.O);
-            }
-            woff += (uint32_t)__popc(__ballot_sync(0xffffffffu, ends));
-            if (woff >= 32u && wb + 32u < r1) {                // window exhausted: more rows may end here
-                wb += 32u;
-                woff = 0;
-                win.load(a, epi, wb, r1, lane);
-                continue;
-            }
-            break;
-        }
-        __syncwarp();
-        // keep the window ahead of the stream: the reload is in flight during the next chunk
-        if (endp >= e1) break;
-        if (woff >= 16u && wb + woff < r1) {
-            wb += woff;
-            woff = 0;
-            win.load(a, epi, wb, r1, lane);
-        }
+    WarpTileState<EPI> ts;
+    ts.wb = r0;
+    ts.woff = 0;
+    ts.carry = 0.0;
+    ts.win.load(a, epi, r0, r1, lane);
+    ChunkRegs ra, rb;
+    load_chunk(a.A, a0 + 4u * (uint32_t)lane, e0, e1, pol_stream, ra);
+    // two chunks per trip so that the register double buffer needs no copies; at least one chunk is processed
+    // even for a tile without entries, so that its (empty) rows still get their epilogue
+    for (uint32_t base = a0;;) {
+        warp_chunk<EPI>(a, epi, su, ts, ra, rb, base, r1, e0, e1, lane, pol_stream, pol_keep);
+        base += kChunk;
+        if (base >= e1) break;
+        warp_chunk<EPI>(a, epi, su, ts, rb, ra, base, r1, e0, e1, lane, pol_stream, pol_keep);
+        base += kChunk;
+        if (base >= e1) break;
     }
 }
 
@@ -214,6 +236,7 @@ spmv_warp_kernel(StreamArgs a)
     if (mode != MODE_FULL) {
         // elementwise part only (n-vectors): x += t1 w [; w' = v/alpha + t2 w]
         if (epi.upd) {
+            epi.load_update_coefficients(st);
             const int64_t n = a.A.nrows;
             for (int64_t i = (int64_t)blockIdx.x * kWThreads + tid; i < n; i += (int64_t)gridDim.x * kWThreads) {
                 const double wo = a.uw[i];

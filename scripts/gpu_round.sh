@@ -2,7 +2,7 @@
 # One GPU session: parity tests, smoke, kernel A/B bench, bench, ncu.  Logs land in gpurun_out/.
 #   scripts/gpu_round.sh [ncu] [quick]
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q -x 2>&1 | tail -40 > gpurun_out/pytest_gpu.log
+timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -40 > gpurun_out/pytest_gpu.log
 tail -8 gpurun_out/pytest_gpu.log
 timeout 300 python __graft_entry__.py --smoke > gpurun_out/smoke.log 2>&1
 tail -3 gpurun_out/smoke.log

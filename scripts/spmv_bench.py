@@ -88,6 +88,20 @@ def main():
                 out.update(itn=r.itn, istop=r.istop, loop_ms=round(kt["loop_ms"], 3),
                            us_per_iter=round(1e3 * kt["loop_ms"] / max(r.itn, 1), 2),
                            loop_frac=round(biter * r.itn / (kt["loop_ms"] * 1e-3) / 1e9 / peak, 4))
+                # true cost of one iteration: slope of the loop time between two fixed iteration counts
+                for graph in (1, 0):
+                    ms = {}
+                    for lim in (32, 96):
+                        s.set_tolerances(atol=0.0, btol=0.0, conlim=0.0, itnlim=lim, use_graph=bool(graph))
+                        s.solve(b, cfg["damp"], x=xo)
+                        rr = s.solve(b, cfg["damp"], x=xo)
+                        ms[lim] = s.kernel_times()["loop_ms"] if rr.itn == lim else float("nan")
+                    us = 1e3 * (ms[96] - ms[32]) / 64
+                    out["slope_us_graph" if graph else "slope_us_nograph"] = round(us, 2)
+                    if graph:
+                        out["slope_frac"] = round(biter / (us * 1e-6) / 1e9 / peak, 4)
+                s.set_tolerances(atol=1e-10, btol=1e-10, conlim=1e8, itnlim=100000, use_graph=True)
+                s.solve(b, cfg["damp"], x=xo)
                 key = "x"
                 xs = xo.clone()
                 if key in ref:
