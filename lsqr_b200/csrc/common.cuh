@@ -34,6 +34,7 @@ void set_last_error(const std::string &msg);
 constexpr int kNumSMs = 148;             // B200: 2 dies x 74 SMs
 constexpr int kMaxPartials = 148 * 16;   // upper bound on the grid of any reducing kernel
 constexpr int kRingSize = 256;           // per-iteration records in pinned mapped memory
+constexpr int kTraceSlots = 1024;
 
 // ---------------------------------------------------------------------------------------------
 // Device-resident solver state: every scalar of the LSQR recurrence (src/lsqr.f90:566-575)
@@ -44,6 +45,7 @@ struct DevState {
     // configuration (set by the host before the solve)
     double damp, atol, btol, ctol;
     int    itnlim, wantse, damped, dist;
+    int    tr_on, tr_n;      // LSQR_B200_TRACE: device-side timeline of the fused kernels (globaltimer)
 
     // Golub-Kahan scalars
     double alpha, beta, inv_alpha, inv_beta;
@@ -77,6 +79,9 @@ struct DevState {
     // partial sums of the reducing kernels (fixed slot per block => deterministic final sum)
     double partial[kMaxPartials];
     double partial2[kMaxPartials];   // second simultaneous reduction (fused Atprod + deferred update)
+
+    // trace[0]: first instruction of block 0, trace[1]: last block starts the final sum, trace[2]: scalar step done
+    unsigned long long trace[3][kTraceSlots];
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -90,6 +95,13 @@ __device__ __forceinline__ double d2norm(double a, double b)
     if (scale == 0.0) return 0.0;
     double p = a / scale, q = b / scale;
     return scale * sqrt(p * p + q * q);
+}
+
+__device__ __forceinline__ unsigned long long globaltimer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
 }
 
 __device__ __forceinline__ double warp_sum(double v)

@@ -172,6 +172,7 @@ struct Work {
         h.damp = damp; h.atol = atol; h.btol = btol;
         h.ctol = conlim > 0.0 ? 1.0 / conlim : 0.0;
         h.itnlim = itnlim; h.wantse = wantse; h.damped = damp > 0.0; h.dist = dist;
+        h.tr_on = env_int("LSQR_B200_TRACE", 0); h.tr_n = 0;
         h.cs2 = -1.0;
         h.inv_alpha = h.inv_beta = 1.0;
         h.g_c0 = h.g_c1 = h.g_c2 = h.g_c3 = 1.0;
@@ -184,7 +185,25 @@ struct Work {
     {
         LSQRB_CUDA(cudaMemcpyAsync(&h, st, offsetof(DevState, partial), cudaMemcpyDeviceToHost, stream));
         LSQRB_CUDA(cudaStreamSynchronize(stream));
+        if (h.tr_on) dump_trace();
         return LSQR_B200_OK;
+    }
+
+    // LSQR_B200_TRACE=1: timeline of the fused kernels of the last solve, to stderr (microseconds)
+    void dump_trace()
+    {
+        const int n = std::min(h.tr_n, kTraceSlots);
+        std::vector<unsigned long long> t((size_t)3 * kTraceSlots);
+        if (cudaMemcpy(t.data(), (const char *)st + offsetof(DevState, trace), sizeof(unsigned long long) * t.size(),
+                       cudaMemcpyDeviceToHost) != cudaSuccess) return;
+        fprintf(stderr, "[lsqr_b200 trace] %d fused kernels: idx start_us busy_us step_us gap_to_next_us\n", n);
+        for (int k = 0; k < n; ++k) {
+            const double t0 = (double)(t[k] - t[0]) * 1e-3;
+            const double busy = (double)(t[kTraceSlots + k] - t[k]) * 1e-3;
+            const double step = (double)(t[2 * kTraceSlots + k] - t[kTraceSlots + k]) * 1e-3;
+            const double gap = k + 1 < n ? (double)(t[k + 1] - t[2 * kTraceSlots + k]) * 1e-3 : 0.0;
+            if (k < 40 || k >= n - 4) fprintf(stderr, "[lsqr_b200 trace] %4d %10.2f %8.2f %6.2f %6.2f\n", k, t0, busy, step, gap);
+        }
     }
 };
 

@@ -148,7 +148,9 @@ struct RowEpilogue {
     }
     // `old` = out[row] fetched before the row sum (hides the DRAM latency behind the reduction)
     __device__ __forceinline__ bool needs_old() const { return EPI == SEPI_APROD || EPI == SEPI_ATPROD || EPI == SEPI_ACC || EPI == SEPI_ATPROD_UPD; }
-    __device__ __forceinline__ void apply(const StreamArgs &a, int64_t row, double s, double old)
+    // wo / xo: w[row], x[row] of the deferred update when the caller prefetched them (have_wx), else read here
+    __device__ __forceinline__ void apply(const StreamArgs &a, int64_t row, double s, double old,
+                                          bool have_wx = false, double wo = 0.0, double xo = 0.0)
     {
         if (EPI == SEPI_ACC) { a.out[row] = old + s; return; }
         if (EPI == SEPI_STORE) { a.out[row] = s; return; }
@@ -159,8 +161,8 @@ struct RowEpilogue {
         if (EPI == SEPI_ATPROD_UPD && upd) {
             const DevState *st = a.st;
             const double c1 = __ldg(&st->t1), c2 = __ldg(&st->t2), cia = __ldg(&st->inv_alpha);
-            const double wo = a.uw[row];
-            a.ux[row] = c1 * wo + a.ux[row];
+            if (!have_wx) { wo = a.uw[row]; xo = a.ux[row]; }
+            a.ux[row] = c1 * wo + xo;
             const double wn = c2 * wo + cia * old;
             a.uw[row] = wn;
             sq2 += wn * wn;

@@ -41,15 +41,18 @@ template <int EPI>
 struct RowWindow {
     uint32_t P, PE;
     double O;
+    double W, X;   // fused deferred update only: w[row], x[row]
     __device__ __forceinline__ void load(const StreamArgs &a, const RowEpilogue<EPI> &epi, uint32_t wb, uint32_t r1, int lane)
     {
         const uint32_t r = wb + (uint32_t)lane;
         P = PE = kPtrSentinel;
         O = 0.0;
+        if (EPI == SEPI_ATPROD_UPD) W = X = 0.0;
         if (r < r1) {
             P = a.A.ptr[r];
             PE = a.A.ptr[r + 1];
             if (epi.needs_old()) O = a.out[r];
+            if (EPI == SEPI_ATPROD_UPD && epi.upd) { W = a.uw[r]; X = a.ux[r]; }
         }
     }
 };
@@ -161,7 +164,8 @@ __device__ __forceinline__ void warp_chunk(const StreamArgs &a, RowEpilogue<EPI>
         const bool ends = (uint32_t)lane >= ts.woff && ts.win.PE <= endp;
         if (ends) {
             const double s = (ts.win.PE != ts.win.P) ? su[ts.win.PE - 1u - base] : 0.0;
-            epi.apply(a, (int64_t)ts.wb + lane, s, ts.win.O);
+            if (EPI == SEPI_ATPROD_UPD) epi.apply(a, (int64_t)ts.wb + lane, s, ts.win.O, true, ts.win.W, ts.win.X);
+            else epi.apply(a, (int64_t)ts.wb + lane, s, ts.win.O);
         }
         ts.woff += (uint32_t)__popc(__ballot_sync(0xffffffffu, ends));
         if (ts.woff >= 32u && ts.wb + 32u < r1) {          // window exhausted: more rows may end here
@@ -217,6 +221,8 @@ spmv_warp_kernel(StreamArgs a)
     DevState *st = a.st;
     RowEpilogue<EPI> epi;
     int mode = MODE_FULL;
+    const int tid = threadIdx.x;
+    bool tracing = false;
     if (kFused) {
         if (st->done) return;
         if (EPI == SEPI_APROD && st->istop != 0) return;   // stop already decided: only the deferred update is left
@@ -230,8 +236,9 @@ spmv_warp_kernel(StreamArgs a)
             else if (st->beta == 0.0) mode = MODE_UPDATE_ONLY;
         }
         epi.load(st);
+        tracing = st->tr_on != 0;
+        if (tracing && blockIdx.x == 0 && tid == 0) st->trace[0][st->tr_n & (kTraceSlots - 1)] = globaltimer_ns();
     }
-    const int tid = threadIdx.x;
 
     if (mode != MODE_FULL) {
         // elementwise part only (n-vectors): x += t1 w [; w' = v/alpha + t2 w]
@@ -267,6 +274,7 @@ spmv_warp_kernel(StreamArgs a)
         if (EPI == SEPI_ATPROD_UPD) {
             // sum(w'^2) of the deferred update closes iteration k; sum(v'^2) drives the step of iteration k+1
             if (finish_reduction2<kWThreads>(st, 0, epi.sq, epi.sq2, s_red, &total, &total_w)) {
+                if (tracing) st->trace[1][st->tr_n & (kTraceSlots - 1)] = globaltimer_ns();
                 if (st->upd_pending) {
                     __threadfence();
                     step_after_update(*st, total_w, __ldcg(a.ux), a.ring);
@@ -276,13 +284,16 @@ spmv_warp_kernel(StreamArgs a)
                     step_after_atprod(*st, total, mode == MODE_FULL);
                     st->upd_pending = 1;
                 }
+                if (tracing) { st->trace[2][st->tr_n & (kTraceSlots - 1)] = globaltimer_ns(); st->tr_n += 1; }
             }
         } else if (finish_reduction<kWThreads>(st, 0, epi.sq, s_red, &total)) {
+            if (tracing) st->trace[1][st->tr_n & (kTraceSlots - 1)] = globaltimer_ns();
             if (EPI == SEPI_APROD) {
                 if (a.aux) *a.aux = total; else step_after_aprod(*st, total);
             }
             else if (EPI == SEPI_ATPROD) step_after_atprod(*st, total, true);
             else step_init_alpha(*st, total);
+            if (tracing) { st->trace[2][st->tr_n & (kTraceSlots - 1)] = globaltimer_ns(); st->tr_n += 1; }
         }
     }
 }

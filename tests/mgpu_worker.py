@@ -1,0 +1,62 @@
+"""Multi-GPU parity worker (launched by torchrun, one rank per GPU): the row-partitioned engine (local Aprod,
+one NCCL all-reduce of [A_p'u_p | sum u_p^2] per iteration) against the serial CPU oracle on the same problem.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tests/mgpu_worker.py
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch
+import torch.distributed as td
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    td.init_process_group("nccl", device_id=dev)
+    import lsqr_b200
+    from lsqr_b200 import dist, synth, synth_device
+    from oracle import oracle as O      # the checker
+
+    for name, scale, tol, want_se in (("C2", 20, 1e-10, False), ("C3", 200, 1e-10, True), ("C4", 200, 1e-10, False)):
+        cfg = synth.scaled(name, scale)
+        m, n = cfg["m"], cfg["n"]
+        row0, row1 = dist.row_block(m, world, rank)
+        irow, icol, a = synth_device.coo_block(cfg["kind"], cfg["seed"], m, n, cfg["k"], row0, row1 - row0, dev)
+        uid = dist.exchange_unique_id(world, rank)
+        s = lsqr_b200.LsqrSolverEz().initialize(row1 - row0, n, a, irow, icol, atol=tol, btol=tol, conlim=1e8, itnlim=4000,
+                                                stream=torch.cuda.current_stream().cuda_stream,
+                                                world_size=world, rank=rank, nccl_unique_id=uid, m_global=m)
+        # the whole problem on the host for the oracle (every rank builds it: small)
+        I, J, A = synth.coo_block(cfg["kind"], cfg["seed"], m, n, cfg["k"])
+        b = synth.rhs_block(I, J, A, m, synth.x_true(cfg["seed"], n), cfg["seed"])
+        r = s.solve(np.ascontiguousarray(b[row0:row1]), cfg["damp"], want_se=want_se)
+        # every rank must hold the identical solution and scalars
+        xs = [torch.zeros(n, dtype=torch.float64, device=dev) for _ in range(world)]
+        td.all_gather(xs, torch.from_numpy(np.asarray(r.x)).to(dev))
+        assert all(torch.equal(xs[0], t) for t in xs), "ranks disagree on x"
+        if rank == 0:
+            ref = O.SolverEz(m, n, A, I, J, atol=tol, btol=tol, conlim=1e8, itnlim=4000).solve(b, cfg["damp"], wantse=want_se)
+            rel = np.linalg.norm(np.asarray(r.x) - ref.x) / np.linalg.norm(ref.x)
+            assert r.istop == ref.istop, (name, r.istop, ref.istop)
+            assert abs(r.itn - ref.itn) <= 2, (name, r.itn, ref.itn)
+            assert rel <= 1e-10, (name, rel)
+            assert abs(r.rnorm - ref.rnorm) <= 1e-10 * ref.rnorm, (name, r.rnorm, ref.rnorm)
+            if want_se:
+                rse = np.linalg.norm(np.asarray(r.se) - ref.se) / np.linalg.norm(ref.se)
+                assert rse <= 1e-8, (name, rse)
+            print(f"MGPU_OK {name}/{scale} world={world} istop={r.istop} itn={r.itn} (oracle {ref.itn}) rel_x={rel:.2e}", flush=True)
+        del s
+        td.barrier()
+    td.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -493,3 +493,17 @@ def test_device_generator_is_bit_identical_to_host(lb, kind, k):
         assert da.cpu().numpy().tobytes() == a.tobytes()
     assert synth_device.x_true(seed, n, dev).cpu().numpy().tobytes() == synth.x_true(seed, n).tobytes()
     assert synth_device.noise(seed, 77, 1000, dev).cpu().numpy().tobytes() == synth.noise(seed, 77, 1000).tobytes()
+
+
+# ------------------------------------------------------------------ K8: row-partitioned multi-GPU solve
+def test_two_gpu_row_partition_matches_oracle(lb):
+    """Needs >= 2 GPUs (skipped on a 1-GPU box): 2 ranks over NCCL against the serial oracle."""
+    import os, subprocess, sys
+    if lb.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29633", os.path.join(root, "tests", "mgpu_worker.py")],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-5000:]
+    assert r.stdout.count("MGPU_OK") == 3
