@@ -222,8 +222,9 @@ def main():
     torch.cuda.empty_cache()
 
     # b = A x_true + 1e-3 noise, formed on the device with the engine's own Aprod
-    xt = torch.from_numpy(synth.x_true(cfg["seed"], n)).to(dev)
-    b_dev = torch.from_numpy(synth.noise(cfg["seed"], row0, m_loc)).to(dev)
+    from lsqr_b200 import synth_device
+    xt = synth_device.x_true(cfg["seed"], n, dev)
+    b_dev = synth_device.noise(cfg["seed"], row0, m_loc, dev)
     solver.aprod(1, m_loc, n, xt, b_dev)
     x_dev = torch.empty(n, dtype=torch.float64, device=dev)
     b_host = b_dev.cpu().pin_memory()

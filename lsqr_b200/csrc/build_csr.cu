@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(kT) unsorted_flag_kernel(int64_t nnz, const in
 {
     int bad = 0;
     for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i + 1 < nnz; i += (int64_t)gridDim.x * kT)
-        bad |= (key[i] > key[i + 1]);
+        bad |= ((uint32_t)key[i] > (uint32_t)key[i + 1]);   // (composite keys of the blocked transpose use all 32 bits)
     if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
 }
 
@@ -58,7 +58,16 @@ __global__ void __launch_bounds__(kT) unsorted_flag_kernel(int64_t nnz, const in
 __global__ void __launch_bounds__(kT) histogram_kernel(int64_t nnz, const int32_t *__restrict__ key, uint32_t *counts)
 {
     for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < nnz; i += (int64_t)gridDim.x * kT)
-        atomicAdd(counts + (key[i] - 1), 1u);
+        atomicAdd(counts + ((uint32_t)key[i] - 1u), 1u);
+}
+
+// composite key of the row-blocked transpose: ((other-1)/block_rows)*nkeys + key   (1-based like key)
+__global__ void __launch_bounds__(kT)
+composite_key_kernel(int64_t nnz, const int32_t *__restrict__ key, const int32_t *__restrict__ other,
+                     uint32_t block_rows, uint32_t nkeys, int32_t *__restrict__ out)
+{
+    for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < nnz; i += (int64_t)gridDim.x * kT)
+        out[i] = (int32_t)(((uint32_t)(other[i] - 1) / block_rows) * nkeys + (uint32_t)key[i]);
 }
 
 __global__ void __launch_bounds__(kT) iota_kernel(int64_t nnz, uint32_t *p)
@@ -122,9 +131,31 @@ int coo_validate(cudaStream_t stream, int32_t m, int32_t n, int64_t nnz,
     return LSQR_B200_OK;
 }
 
-int coo_to_csr_device(cudaStream_t stream, int64_t nkeys, int64_t nnz,
-                      const int32_t *d_key, const int32_t *d_other, const double *d_a, Csr *out)
+int coo_to_csr_device(cudaStream_t stream, int64_t nkeys_one, int64_t nnz,
+                      const int32_t *d_key_in, const int32_t *d_other, const double *d_a, Csr *out,
+                      int64_t block_rows, int64_t nother)
 {
+    out->nkeys = nkeys_one;
+    out->nblocks = 1;
+    out->block_rows = 0;
+    int64_t nkeys = nkeys_one;
+    const int32_t *d_key = d_key_in;
+    int32_t *d_comp = nullptr;
+    if (block_rows > 0 && nother > block_rows && nnz > 0) {
+        const int64_t nb = (nother + block_rows - 1) / block_rows;
+        if (nb * nkeys_one >= (int64_t)0xFFFFFFF0ll || block_rows >= (int64_t)0xFFFFFFFFll) {
+            set_last_error("row-blocked transpose: blocks * columns exceeds 32 bits");
+            return LSQR_B200_ERR_TOO_LARGE;
+        }
+        out->nblocks = nb;
+        out->block_rows = block_rows;
+        nkeys = nb * nkeys_one;
+        LSQRB_CUDA(cudaMalloc(&d_comp, sizeof(int32_t) * (size_t)nnz));
+        composite_key_kernel<<<grid_for(nnz), kT, 0, stream>>>(nnz, d_key_in, d_other, (uint32_t)block_rows, (uint32_t)nkeys_one, d_comp);
+        LSQRB_CUDA(cudaGetLastError());
+        d_key = d_comp;
+    }
+    struct CompGuard { int32_t *p; cudaStream_t s; ~CompGuard() { if (p) { cudaStreamSynchronize(s); cudaFree(p); } } } comp_guard{d_comp, stream};
     out->nrows = nkeys;
     out->nnz = nnz;
     out->was_sorted = 1;

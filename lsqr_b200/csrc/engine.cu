@@ -220,11 +220,14 @@ static int pick_lanes(const Csr &M, const char *env_name)
     return lanes;
 }
 
+static inline CsrView view_of(const Csr &M) { return CsrView{M.ptr, M.idx, M.val, M.nrows}; }
+// block b of a row-blocked transpose (an ordinary CSR over nkeys rows whose entries start at ptr[b*nkeys])
+static inline CsrView view_of_block(const Csr &M, int64_t b) { return CsrView{M.ptr + b * M.nkeys, M.idx, M.val, M.nkeys}; }
+
 template <int EPI>
-static int launch_spmv(Work &wk, const Csr &M, int lanes, const double *x, double *out, double *aux)
+static int launch_spmv(Work &wk, const CsrView &V, int lanes, const double *x, double *out, double *aux)
 {
-    CsrView V{M.ptr, M.idx, M.val, M.nrows};
-    const int grid = wk.grid_for(M.nrows, kThreads / lanes);
+    const int grid = wk.grid_for(V.nrows, kThreads / lanes);
     switch (lanes) {
     case 1:  spmv_rowgroup_kernel<1, EPI><<<grid, kThreads, 0, wk.stream>>>(V, x, out, wk.st, aux); break;
     case 2:  spmv_rowgroup_kernel<2, EPI><<<grid, kThreads, 0, wk.stream>>>(V, x, out, wk.st, aux); break;
@@ -258,14 +261,15 @@ static uint32_t warp_tile_size(const Work &wk, int64_t nnz)
     return (uint32_t)std::max<int64_t>(512, (t + 3) & ~(int64_t)3);
 }
 
-static int build_tile_map(Work &wk, const Csr &M, int kind, TileMapOwner *out)
+// V: a whole CSR, or one block of a row-blocked transpose (nnz = its number of stored entries)
+static int build_tile_map(Work &wk, const CsrView &V, int64_t nnz, int kind, TileMapOwner *out)
 {
     out->kind = kind;
-    out->tile = kind == 3 ? warp_tile_size(wk, M.nnz) : (uint32_t)kTile;
-    const int64_t nt = std::max<int64_t>(1, (M.nnz + out->tile - 1) / out->tile);
+    out->tile = kind == 3 ? warp_tile_size(wk, nnz) : (uint32_t)kTile;
+    const int64_t nt = std::max<int64_t>(1, (nnz + out->tile - 1) / out->tile);
     out->ntiles = (int)nt;
     LSQRB_CUDA(cudaMalloc(&out->tiles, sizeof(uint2) * (size_t)(nt + 1)));
-    build_tiles_kernel<<<(int)((nt + 1 + 255) / 256), 256, 0, wk.stream>>>(M.ptr, M.nrows, M.nnz, (int)nt, out->tile, out->tiles);
+    build_tiles_kernel<<<(int)((nt + 1 + 255) / 256), 256, 0, wk.stream>>>(V.ptr, V.nrows, (int)nt, out->tile, out->tiles);
     LSQRB_CUDA(cudaGetLastError());
     return LSQR_B200_OK;
 }
@@ -294,11 +298,11 @@ struct StreamExtra {   // operands of the fused deferred update
 };
 
 template <int EPI>
-static int launch_stream(Work &wk, const Csr &M, const TileMapOwner &map, const double *x, double *out, double *aux,
+static int launch_stream(Work &wk, const CsrView &V, const TileMapOwner &map, const double *x, double *out, double *aux,
                          const StreamExtra &ex = StreamExtra())
 {
     StreamArgs a;
-    a.A = CsrView{M.ptr, M.idx, M.val, M.nrows};
+    a.A = V;
     a.map = TileMap{map.tiles, map.ntiles};
     a.x = x; a.out = out; a.st = wk.st; a.aux = aux;
     a.ux = ex.ux; a.uw = ex.uw; a.use = ex.use;
@@ -468,9 +472,12 @@ struct lsqr_b200_ez {
     int64_t nnz = 0;
     Csr A, AT;
     int lanes_a = 4, lanes_at = 32;
-    TileMapOwner mapA, mapAT;
-    bool stream = true;           // tile-streamed kernels (variant 2) vs sub-warp-per-row (variant 1)
-    bool deferred = true;         // single GPU, variant 2: x/w update fused into the next Atprod (2 kernels / iteration)
+    TileMapOwner mapA;
+    std::vector<TileMapOwner> mapAT;   // one per block of the row-blocked transpose
+    std::vector<int64_t> at_off;       // first stored entry of every block of A' (nblocks + 1 values)
+    bool stream = true;           // tiled kernels (variants 2, 3) vs sub-warp-per-row (variant 1)
+    bool blocked = false;         // A' is row-blocked (u does not fit in L2): Atprod = one launch per block into g
+    bool deferred = true;         // single GPU, tiled, unblocked: x/w update fused into the next Atprod (2 kernels / iteration)
     lsqr_b200_options opt;
     double *u = nullptr, *v = nullptr, *w = nullptr, *x = nullptr, *se = nullptr;
     double *g = nullptr;          // multi-GPU: [ A_p'u_p (n) | sum(u_p^2) ]
@@ -495,7 +502,7 @@ static void ez_free(lsqr_b200_ez *me)
     csr_free(&me->A);
     csr_free(&me->AT);
     if (me->mapA.tiles) cudaFree(me->mapA.tiles);
-    if (me->mapAT.tiles) cudaFree(me->mapAT.tiles);
+    for (auto &mp : me->mapAT) if (mp.tiles) cudaFree(mp.tiles);
     for (double *p : {me->u, me->v, me->w, me->x, me->se, me->g, me->tmp_m, me->tmp_n}) if (p) cudaFree(p);
     for (auto e : {me->ev_t0, me->ev_t1, me->ev_t2}) if (e) cudaEventDestroy(e);
     for (auto e : me->prof_ev) cudaEventDestroy(e);
@@ -590,7 +597,19 @@ static int ez_initialize_impl(lsqr_b200_ez *me, int64_t nnz, const double *a, co
     };
     int rc = coo_validate(wk.stream, me->m, me->n, nnz, d_irow, d_icol);
     if (rc == LSQR_B200_OK) rc = coo_to_csr_device(wk.stream, me->m, nnz, d_irow, d_icol, d_a, &me->A);
-    if (rc == LSQR_B200_OK) rc = coo_to_csr_device(wk.stream, me->n, nnz, d_icol, d_irow, d_a, &me->AT);
+    if (rc == LSQR_B200_OK) {
+        // Row-blocked transpose: when u (8 m bytes) cannot stay in L2 while A' streams past it, A' is stored as one
+        // CSR per block of rows of A, so that every Atprod launch gathers from a slice of u that does fit.
+        int64_t block_rows = env_int("LSQR_B200_UBLOCK_ROWS", 0);
+        if (block_rows <= 0) {
+            const int64_t budget_rows = (int64_t)env_int("LSQR_B200_UBLOCK_MB", 48) * (1 << 20) / 8;
+            if (me->m > budget_rows) {
+                const int64_t nb = (me->m + budget_rows - 1) / budget_rows;
+                block_rows = (me->m + nb - 1) / nb;
+            }
+        }
+        rc = coo_to_csr_device(wk.stream, me->n, nnz, d_icol, d_irow, d_a, &me->AT, block_rows, me->m);
+    }
     if (rc == LSQR_B200_OK && cudaStreamSynchronize(wk.stream) != cudaSuccess) rc = LSQR_B200_ERR_CUDA;
     release();
     LSQRB_TRY(rc);
@@ -599,19 +618,36 @@ static int ez_initialize_impl(lsqr_b200_ez *me, int64_t nnz, const double *a, co
     me->lanes_at = pick_lanes(me->AT, "LSQR_B200_LANES_AT");
     const int variant = me->opt.spmv_variant ? me->opt.spmv_variant : env_int("LSQR_B200_SPMV_VARIANT", 3);
     me->stream = variant != 1;
-    me->deferred = me->stream && me->opt.world_size == 1 && env_int("LSQR_B200_DEFERRED_UPDATE", 1) != 0;
+    me->blocked = me->AT.nblocks > 1;
+    me->deferred = me->stream && !me->blocked && me->opt.world_size == 1 && env_int("LSQR_B200_DEFERRED_UPDATE", 1) != 0;
+    {   // first stored entry of every block of A'
+        const int64_t nb = me->AT.nblocks;
+        me->at_off.assign((size_t)nb + 1, 0);
+        std::vector<uint32_t> off((size_t)nb + 1);
+        for (int64_t b = 0; b <= nb; ++b)
+            LSQRB_CUDA(cudaMemcpyAsync(&off[(size_t)b], me->AT.ptr + b * me->AT.nkeys, sizeof(uint32_t), cudaMemcpyDeviceToHost, wk.stream));
+        LSQRB_CUDA(cudaStreamSynchronize(wk.stream));
+        for (int64_t b = 0; b <= nb; ++b) me->at_off[(size_t)b] = off[(size_t)b];
+    }
     if (me->stream) {
-        LSQRB_TRY(build_tile_map(wk, me->A, variant == 2 ? 2 : 3, &me->mapA));
-        LSQRB_TRY(build_tile_map(wk, me->AT, variant == 2 ? 2 : 3, &me->mapAT));
+        LSQRB_TRY(build_tile_map(wk, view_of(me->A), me->A.nnz, variant == 2 ? 2 : 3, &me->mapA));
+        me->mapAT.resize((size_t)me->AT.nblocks);
+        for (int64_t b = 0; b < me->AT.nblocks; ++b)
+            LSQRB_TRY(build_tile_map(wk, view_of_block(me->AT, b), me->at_off[(size_t)b + 1] - me->at_off[(size_t)b],
+                                     variant == 2 ? 2 : 3, &me->mapAT[(size_t)b]));
         LSQRB_CUDA(cudaStreamSynchronize(wk.stream));
     }
+    if (env_int("LSQR_B200_VERBOSE", 0))
+        fprintf(stderr, "[lsqr_b200] m=%d n=%d nnz=%lld variant=%d A' blocks=%lld (block_rows=%lld) warp tile A=%u A'=%u\n", me->m, me->n,
+                (long long)me->nnz, variant, (long long)me->AT.nblocks, (long long)me->AT.block_rows, me->mapA.tile,
+                me->mapAT.empty() ? 0u : me->mapAT[0].tile);
 
     const size_t mm = (size_t)std::max<int32_t>(me->m, 1), nn = (size_t)std::max<int32_t>(me->n, 1);
     LSQRB_CUDA(cudaMalloc(&me->u, sizeof(double) * mm));
     LSQRB_CUDA(cudaMalloc(&me->v, sizeof(double) * nn));
     LSQRB_CUDA(cudaMalloc(&me->w, sizeof(double) * nn));
     LSQRB_CUDA(cudaMalloc(&me->x, sizeof(double) * nn));
-    if (me->opt.world_size > 1) LSQRB_CUDA(cudaMalloc(&me->g, sizeof(double) * (nn + 1)));
+    if (me->opt.world_size > 1 || me->blocked) LSQRB_CUDA(cudaMalloc(&me->g, sizeof(double) * (nn + 1)));
     LSQRB_CUDA(cudaEventCreate(&me->ev_t0));
     LSQRB_CUDA(cudaEventCreate(&me->ev_t1));
     LSQRB_CUDA(cudaEventCreate(&me->ev_t2));
@@ -671,6 +707,14 @@ int lsqr_b200_ez_set_options(lsqr_b200_ez *me, const lsqr_b200_options *o)
 
 int64_t lsqr_b200_ez_nnz(const lsqr_b200_ez *me) { return me ? me->nnz : -1; }
 
+int lsqr_b200_ez_transpose_blocks(const lsqr_b200_ez *me, int64_t *nblocks, int64_t *block_rows)
+{
+    if (!me) return LSQR_B200_ERR_ARG;
+    if (nblocks) *nblocks = me->AT.nblocks;
+    if (block_rows) *block_rows = me->AT.block_rows;
+    return LSQR_B200_OK;
+}
+
 int lsqr_b200_ez_get_csr(lsqr_b200_ez *me, int32_t which, int64_t *ptr, int32_t *idx, double *val, int64_t *perm)
 {
     if (!me || (which != 0 && which != 1)) return LSQR_B200_ERR_ARG;
@@ -706,10 +750,14 @@ int lsqr_b200_ez_aprod_device(void *handle, int32_t mode, int32_t m, int32_t n,
     cudaStream_t saved = wk.stream;
     if (stream) wk.stream = (cudaStream_t)stream;
     int rc;
-    if (mode == 1)      rc = me->stream ? launch_stream<SEPI_ACC>(wk, me->A, me->mapA, x_dev, y_dev, nullptr)
-                                        : launch_spmv<EPI_ACC>(wk, me->A, me->lanes_a, x_dev, y_dev, nullptr);    // y += A x
-    else if (mode == 2) rc = me->stream ? launch_stream<SEPI_ACC>(wk, me->AT, me->mapAT, y_dev, x_dev, nullptr)
-                                        : launch_spmv<EPI_ACC>(wk, me->AT, me->lanes_at, y_dev, x_dev, nullptr);  // x += A'y
+    if (mode == 1)      rc = me->stream ? launch_stream<SEPI_ACC>(wk, view_of(me->A), me->mapA, x_dev, y_dev, nullptr)
+                                        : launch_spmv<EPI_ACC>(wk, view_of(me->A), me->lanes_a, x_dev, y_dev, nullptr);    // y += A x
+    else if (mode == 2) {                                                                                                  // x += A'y
+        rc = LSQR_B200_OK;
+        for (int64_t b = 0; b < me->AT.nblocks && rc == LSQR_B200_OK; ++b)
+            rc = me->stream ? launch_stream<SEPI_ACC>(wk, view_of_block(me->AT, b), me->mapAT[(size_t)b], y_dev, x_dev, nullptr)
+                            : launch_spmv<EPI_ACC>(wk, view_of_block(me->AT, b), me->lanes_at, y_dev, x_dev, nullptr);
+    }
     else                rc = LSQR_B200_ERR_MODE;                                                     // :197
     wk.stream = saved;
     return rc;
@@ -773,39 +821,48 @@ static int allreduce_g(lsqr_b200_ez *me)
 // the SpMV flavours of one handle
 static int do_aprod_fused(lsqr_b200_ez *me, double *aux)
 {
-    return me->stream ? launch_stream<SEPI_APROD>(me->wk, me->A, me->mapA, me->v, me->u, aux)
-                      : launch_spmv<EPI_FUSED_APROD>(me->wk, me->A, me->lanes_a, me->v, me->u, aux);
+    return me->stream ? launch_stream<SEPI_APROD>(me->wk, view_of(me->A), me->mapA, me->v, me->u, aux)
+                      : launch_spmv<EPI_FUSED_APROD>(me->wk, view_of(me->A), me->lanes_a, me->v, me->u, aux);
 }
+// g = A'u (unfused: multi-GPU partial and/or row-blocked transpose): block 0 stores, the others accumulate
 static int do_atprod_store(lsqr_b200_ez *me)
 {
-    return me->stream ? launch_stream<SEPI_STORE>(me->wk, me->AT, me->mapAT, me->u, me->g, nullptr)
-                      : launch_spmv<EPI_STORE>(me->wk, me->AT, me->lanes_at, me->u, me->g, nullptr);
+    for (int64_t b = 0; b < me->AT.nblocks; ++b) {
+        const CsrView V = view_of_block(me->AT, b);
+        if (b == 0) LSQRB_TRY(me->stream ? launch_stream<SEPI_STORE>(me->wk, V, me->mapAT[0], me->u, me->g, nullptr)
+                                         : launch_spmv<EPI_STORE>(me->wk, V, me->lanes_at, me->u, me->g, nullptr));
+        else        LSQRB_TRY(me->stream ? launch_stream<SEPI_ACC>(me->wk, V, me->mapAT[(size_t)b], me->u, me->g, nullptr)
+                                         : launch_spmv<EPI_ACC>(me->wk, V, me->lanes_at, me->u, me->g, nullptr));
+    }
+    return LSQR_B200_OK;
 }
 static int do_atprod_fused(lsqr_b200_ez *me)
 {
-    return me->stream ? launch_stream<SEPI_ATPROD>(me->wk, me->AT, me->mapAT, me->u, me->v, nullptr)
-                      : launch_spmv<EPI_FUSED_ATPROD>(me->wk, me->AT, me->lanes_at, me->u, me->v, nullptr);
+    return me->stream ? launch_stream<SEPI_ATPROD>(me->wk, view_of(me->AT), me->mapAT[0], me->u, me->v, nullptr)
+                      : launch_spmv<EPI_FUSED_ATPROD>(me->wk, view_of(me->AT), me->lanes_at, me->u, me->v, nullptr);
 }
 static int do_atprod_init(lsqr_b200_ez *me)
 {
-    return me->stream ? launch_stream<SEPI_INIT_ATPROD>(me->wk, me->AT, me->mapAT, me->u, me->v, nullptr)
-                      : launch_spmv<EPI_INIT_ATPROD>(me->wk, me->AT, me->lanes_at, me->u, me->v, nullptr);
+    return me->stream ? launch_stream<SEPI_INIT_ATPROD>(me->wk, view_of(me->AT), me->mapAT[0], me->u, me->v, nullptr)
+                      : launch_spmv<EPI_INIT_ATPROD>(me->wk, view_of(me->AT), me->lanes_at, me->u, me->v, nullptr);
 }
 static int do_atprod_upd(lsqr_b200_ez *me)   // Atprod of this iteration + deferred x/w update of the previous one
 {
     StreamExtra ex;
     ex.ux = me->x; ex.uw = me->w; ex.use = me->se;
-    return launch_stream<SEPI_ATPROD_UPD>(me->wk, me->AT, me->mapAT, me->u, me->v, nullptr, ex);
+    return launch_stream<SEPI_ATPROD_UPD>(me->wk, view_of(me->AT), me->mapAT[0], me->u, me->v, nullptr, ex);
 }
 
 // one LSQR iteration, enqueued (no host synchronisation)
 static int enqueue_iteration(lsqr_b200_ez *me, bool wantse)
 {
     Work &wk = me->wk;
-    if (me->opt.world_size > 1) {
+    if (me->opt.world_size > 1 || me->blocked) {
+        // unfused pipeline: u' and its partial norm, g = [A'u' | sum u'^2] (all-reduced over the ranks), then
+        // v' = g/beta - (beta/alpha) v with both scalar steps, then the x/w update
         { ProfScope p(me, CLS_APROD);  LSQRB_TRY(do_aprod_fused(me, me->g + me->n)); }
         { ProfScope p(me, CLS_ATPROD); LSQRB_TRY(do_atprod_store(me)); }
-        { ProfScope p(me, CLS_OTHER);  LSQRB_TRY(allreduce_g(me)); }
+        if (me->opt.world_size > 1) { ProfScope p(me, CLS_OTHER);  LSQRB_TRY(allreduce_g(me)); }
         { ProfScope p(me, CLS_OTHER);
           vfinish_kernel<false><<<wk.grid_for(me->n, kThreads), kThreads, 0, wk.stream>>>(me->n, me->g, me->v, wk.st);
           wk.launches++; LSQRB_CUDA(cudaGetLastError()); }
@@ -849,6 +906,7 @@ static int ez_solve_fused(lsqr_b200_ez *me, const double *b, double damp, double
     const int64_t m = me->m, n = me->n;
     const bool wantse = se != nullptr;
     const bool dist = me->opt.world_size > 1;
+    const bool unfused = dist || me->blocked;
     LSQRB_CUDA(cudaSetDevice(wk.device));
     if (wantse && !me->se) LSQRB_CUDA(cudaMalloc(&me->se, sizeof(double) * (size_t)std::max<int64_t>(n, 1)));
     wk.launches = 0;
@@ -875,11 +933,11 @@ static int ez_solve_fused(lsqr_b200_ez *me, const double *b, double damp, double
         if (wantse) LSQRB_CUDA(cudaMemsetAsync(me->se, 0, sizeof(double) * (size_t)n, wk.stream));
     }
     // beta = ||u||; v = A'(u/beta); alpha = ||v||; w = v/alpha  (:632-644), lazily normalised
-    if (dist) {
+    if (unfused) {
         sumsq_kernel<POST_NONE><<<wk.grid_for(m, kThreads), kThreads, 0, wk.stream>>>(m, me->u, wk.st, me->g + n);
         wk.launches++;
         LSQRB_TRY(do_atprod_store(me));
-        LSQRB_TRY(allreduce_g(me));
+        if (dist) LSQRB_TRY(allreduce_g(me));
         vfinish_kernel<true><<<wk.grid_for(n, kThreads), kThreads, 0, wk.stream>>>(n, me->g, me->v, wk.st);
         wk.launches++;
     } else {
@@ -903,7 +961,7 @@ static int ez_solve_fused(lsqr_b200_ez *me, const double *b, double damp, double
     auto enqueue_batch = [&]() -> int {
         if (use_graph) {
             LSQRB_CUDA(cudaGraphLaunch(me->graph_exec, wk.stream));
-            wk.launches += (int64_t)B * (me->deferred ? 2 : 3);
+            wk.launches += (int64_t)B * (me->deferred ? 2 : me->blocked ? 3 + me->AT.nblocks : 3);
         } else {
             for (int i = 0; i < B; ++i) LSQRB_TRY(enqueue_iteration(me, wantse));
         }

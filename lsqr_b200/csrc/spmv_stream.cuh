@@ -88,12 +88,13 @@ __device__ __forceinline__ void fence_proxy_async_smem()
 // ---------------------------------------------------------------------------------------------
 // Tile map construction: tile t starts at the first row whose first entry is at or after t*tile.
 // ---------------------------------------------------------------------------------------------
-__global__ void build_tiles_kernel(const uint32_t *__restrict__ ptr, int64_t nrows, int64_t nnz, int ntiles, uint32_t tile, uint2 *tiles)
+// ptr may be the pointer array of one block of a row-blocked transpose: its entries then start at ptr[0] != 0.
+__global__ void build_tiles_kernel(const uint32_t *__restrict__ ptr, int64_t nrows, int ntiles, uint32_t tile, uint2 *tiles)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t > ntiles) return;
-    if (t == ntiles) { tiles[t] = make_uint2((uint32_t)nrows, (uint32_t)nnz); return; }
-    const uint64_t target = (uint64_t)t * tile;
+    if (t == ntiles) { tiles[t] = make_uint2((uint32_t)nrows, ptr[nrows]); return; }
+    const uint64_t target = (uint64_t)ptr[0] + (uint64_t)t * tile;
     int64_t lo = 0, hi = nrows;   // first r in [0, nrows] with ptr[r] >= target
     while (lo < hi) {
         const int64_t mid = (lo + hi) >> 1;

@@ -230,9 +230,16 @@ class LsqrSolverEz:
     def nnz(self) -> int:
         return int(_lib.load().lsqr_b200_ez_nnz(self._h))
 
+    def transpose_blocks(self):
+        """(nblocks, block_rows) of the stored transpose (row-blocked when u does not fit in L2)."""
+        nb, br = C.c_int64(), C.c_int64()
+        _lib.check(_lib.load().lsqr_b200_ez_transpose_blocks(self._h, C.byref(nb), C.byref(br)))
+        return nb.value, br.value
+
     def get_csr(self, transpose: bool = False):
-        """Host copies (ptr, idx, val, perm) of the device-built CSR of A (or of A')."""
-        nkeys = self.n if transpose else self.m
+        """Host copies (ptr, idx, val, perm) of the device-built CSR of A (or of A').  For a row-blocked
+        transpose ptr has nblocks*n + 1 entries (see ``transpose_blocks``)."""
+        nkeys = self.n * self.transpose_blocks()[0] if transpose else self.m
         nnz = self.nnz
         ptr = np.zeros(nkeys + 1, np.int64)
         idx = np.zeros(max(nnz, 1), np.int32)
