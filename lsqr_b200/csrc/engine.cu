@@ -225,16 +225,16 @@ static inline CsrView view_of(const Csr &M) { return CsrView{M.ptr, M.idx, M.val
 static inline CsrView view_of_block(const Csr &M, int64_t b) { return CsrView{M.ptr + b * M.nkeys, M.idx, M.val, M.nkeys}; }
 
 template <int EPI>
-static int launch_spmv(Work &wk, const CsrView &V, int lanes, const double *x, double *out, double *aux)
+static int launch_spmv(Work &wk, const CsrView &V, int lanes, const double *x, double *out, double *aux, int check_done = 0)
 {
     const int grid = wk.grid_for(V.nrows, kThreads / lanes);
     switch (lanes) {
-    case 1:  spmv_rowgroup_kernel<1, EPI><<<grid, kThreads, 0, wk.stream>>>(V, x, out, wk.st, aux); break;
-    case 2:  spmv_rowgroup_kernel<2, EPI><<<grid, kThreads, 0, wk.stream>>>(V, x, out, wk.st, aux); break;
-    case 4:  spmv_rowgroup_kernel<4, EPI><<<grid, kThreads, 0, wk.stream>>>(V, x, out, wk.st, aux); break;
-    case 8:  spmv_rowgroup_kernel<8, EPI><<<grid, kThreads, 0, wk.stream>>>(V, x, out, wk.st, aux); break;
-    case 16: spmv_rowgroup_kernel<16, EPI><<<grid, kThreads, 0, wk.stream>>>(V, x, out, wk.st, aux); break;
-    default: spmv_rowgroup_kernel<32, EPI><<<grid, kThreads, 0, wk.stream>>>(V, x, out, wk.st, aux); break;
+    case 1:  spmv_rowgroup_kernel<1, EPI><<<grid, kThreads, 0, wk.stream>>>(V, x, out, wk.st, aux, check_done); break;
+    case 2:  spmv_rowgroup_kernel<2, EPI><<<grid, kThreads, 0, wk.stream>>>(V, x, out, wk.st, aux, check_done); break;
+    case 4:  spmv_rowgroup_kernel<4, EPI><<<grid, kThreads, 0, wk.stream>>>(V, x, out, wk.st, aux, check_done); break;
+    case 8:  spmv_rowgroup_kernel<8, EPI><<<grid, kThreads, 0, wk.stream>>>(V, x, out, wk.st, aux, check_done); break;
+    case 16: spmv_rowgroup_kernel<16, EPI><<<grid, kThreads, 0, wk.stream>>>(V, x, out, wk.st, aux, check_done); break;
+    default: spmv_rowgroup_kernel<32, EPI><<<grid, kThreads, 0, wk.stream>>>(V, x, out, wk.st, aux, check_done); break;
     }
     wk.launches++;
     LSQRB_CUDA(cudaGetLastError());
@@ -295,6 +295,7 @@ static int stream_kernel_prepare(int *ctas_per_sm)
 
 struct StreamExtra {   // operands of the fused deferred update
     double *ux = nullptr, *uw = nullptr, *use = nullptr;
+    int check_done = 0;
 };
 
 template <int EPI>
@@ -308,6 +309,7 @@ static int launch_stream(Work &wk, const CsrView &V, const TileMapOwner &map, co
     a.ux = ex.ux; a.uw = ex.uw; a.use = ex.use;
     a.ring = wk.ring_d;
     a.out_aligned16 = ((uintptr_t)out & 15u) == 0;
+    a.check_done = ex.check_done;
     if (map.kind == 3) {
         const int grid = std::max(1, std::min((map.ntiles + kWWarps - 1) / kWWarps, wk.sms * kWMinBlocks));
         spmv_warp_kernel<EPI><<<grid, kWThreads, 0, wk.stream>>>(a);
@@ -673,7 +675,13 @@ int lsqr_b200_ez_initialize(lsqr_b200_ez **out, int32_t m, int32_t n,
     if (me->opt.world_size < 1) me->opt.world_size = 1;
     me->m = m; me->n = n; me->nnz = size_a;
     memset(&me->times, 0, sizeof me->times);
-    me->batch = std::max(1, std::min(env_int("LSQR_B200_BATCH", 8), kRingSize / 4));
+    {   // iterations per enqueue: enough to cover ~300 us of device time, so that the host's per-batch work (graph
+        // launch, event wait, record drain) stays hidden, but not more: iterations enqueued past the stop are waste
+        const double est_iter_us = 24.0 * (double)size_a / 2.5e6 + 20.0;   // ~2.5 TB/s effective + launch floor
+        int dflt = (int)std::ceil(300.0 / est_iter_us);
+        dflt = std::max(1, std::min(dflt, 8));
+        me->batch = std::max(1, std::min(env_int("LSQR_B200_BATCH", dflt), kRingSize / 4));
+    }
 
     int rc = me->wk.init(me->opt.device, me->opt.stream);
     if (rc == LSQR_B200_OK && me->opt.world_size > 1) {
@@ -827,12 +835,14 @@ static int do_aprod_fused(lsqr_b200_ez *me, double *aux)
 // g = A'u (unfused: multi-GPU partial and/or row-blocked transpose): block 0 stores, the others accumulate
 static int do_atprod_store(lsqr_b200_ez *me)
 {
+    StreamExtra ex;
+    ex.check_done = 1;   // over-enqueued iterations after the stop are no-ops
     for (int64_t b = 0; b < me->AT.nblocks; ++b) {
         const CsrView V = view_of_block(me->AT, b);
-        if (b == 0) LSQRB_TRY(me->stream ? launch_stream<SEPI_STORE>(me->wk, V, me->mapAT[0], me->u, me->g, nullptr)
-                                         : launch_spmv<EPI_STORE>(me->wk, V, me->lanes_at, me->u, me->g, nullptr));
-        else        LSQRB_TRY(me->stream ? launch_stream<SEPI_ACC>(me->wk, V, me->mapAT[(size_t)b], me->u, me->g, nullptr)
-                                         : launch_spmv<EPI_ACC>(me->wk, V, me->lanes_at, me->u, me->g, nullptr));
+        if (b == 0) LSQRB_TRY(me->stream ? launch_stream<SEPI_STORE>(me->wk, V, me->mapAT[0], me->u, me->g, nullptr, ex)
+                                         : launch_spmv<EPI_STORE>(me->wk, V, me->lanes_at, me->u, me->g, nullptr, 1));
+        else        LSQRB_TRY(me->stream ? launch_stream<SEPI_ACC>(me->wk, V, me->mapAT[(size_t)b], me->u, me->g, nullptr, ex)
+                                         : launch_spmv<EPI_ACC>(me->wk, V, me->lanes_at, me->u, me->g, nullptr, 1));
     }
     return LSQR_B200_OK;
 }

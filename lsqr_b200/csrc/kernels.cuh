@@ -322,7 +322,7 @@ enum SpmvEpilogue {
 // ---------------------------------------------------------------------------------------------
 template <int LANES, int EPI>
 __global__ void __launch_bounds__(kThreads)
-spmv_rowgroup_kernel(CsrView A, const double *__restrict__ x, double *out, DevState *st, double *aux)
+spmv_rowgroup_kernel(CsrView A, const double *__restrict__ x, double *out, DevState *st, double *aux, int check_done)
 {
     constexpr bool kFused = (EPI == EPI_FUSED_APROD || EPI == EPI_FUSED_ATPROD || EPI == EPI_INIT_ATPROD);
     __shared__ double s_red[kThreads / 32];
@@ -337,6 +337,8 @@ spmv_rowgroup_kernel(CsrView A, const double *__restrict__ x, double *out, DevSt
         }
         if (EPI == EPI_FUSED_APROD) { cm = st->ca_mat; cv = st->ca_vec; }
         else                        { cm = st->ct_mat; cv = st->ct_vec; }
+    } else if (check_done && st->done) {
+        return;   // unfused STORE / ACC launched from the solve loop after the solver has stopped
     }
 
     const uint64_t pol_stream = l2_policy_evict_first();

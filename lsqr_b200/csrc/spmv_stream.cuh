@@ -125,6 +125,7 @@ struct StreamArgs {
     double *aux;           // multi-GPU: where SEPI_APROD puts its partial sum(u'^2)
     double *ux, *uw, *use; // SEPI_ATPROD_UPD: solution, search direction, standard errors
     int out_aligned16;     // out[] may be the source of 16-byte aligned bulk copies
+    int check_done;        // unfused STORE / ACC launched from the solve loop: nothing to do once the solver has stopped
     volatile lsqr_b200_iter_record *ring;
 };
 
@@ -230,6 +231,8 @@ spmv_stream_kernel(StreamArgs a)
             else if (st->beta == 0.0) mode = MODE_UPDATE_ONLY;
         }
         epi.load(st);
+    } else if (a.check_done && st->done) {
+        return;
     }
 
     const uint64_t pol_stream = l2_policy_evict_first();

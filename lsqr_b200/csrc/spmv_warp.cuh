@@ -238,6 +238,8 @@ spmv_warp_kernel(StreamArgs a)
         epi.load(st);
         tracing = st->tr_on != 0;
         if (tracing && blockIdx.x == 0 && tid == 0) st->trace[0][st->tr_n & (kTraceSlots - 1)] = globaltimer_ns();
+    } else if (a.check_done && st->done) {
+        return;
     }
 
     if (mode != MODE_FULL) {
