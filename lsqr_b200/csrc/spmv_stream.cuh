@@ -125,6 +125,7 @@ struct StreamArgs {
     double *aux;           // multi-GPU: where SEPI_APROD puts its partial sum(u'^2)
     double *ux, *uw, *use; // SEPI_ATPROD_UPD: solution, search direction, standard errors
     int out_aligned16;     // out[] may be the source of 16-byte aligned bulk copies
+    int gather_interleaved;  // variant 3: lanes gather entries 32 k + lane instead of 4 lane + k (matrices with locality)
     int check_done;        // unfused STORE / ACC launched from the solve loop: nothing to do once the solver has stopped
     volatile lsqr_b200_iter_record *ring;
 };

@@ -545,3 +545,33 @@ def test_row_blocked_transpose(lb, variant, monkeypatch):
     assert r.istop == rr.istop and abs(r.itn - rr.itn) <= 2
     assert relerr(r.x, rr.x) <= RTOL
     assert relerr(r.se, rr.se) <= 1e-8
+
+
+# ------------------------------------------------------------------ the reference's own test programs, in C++
+def _run_cpp(name, *args, timeout=900):
+    import os, subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "tests", "cpp", "build", name)
+    if not os.path.exists(exe):
+        subprocess.run(["make", "-C", os.path.join(root, "tests", "cpp")], check=True, capture_output=True)
+    return subprocess.run([exe, *args], capture_output=True, text=True, timeout=timeout)
+
+
+def test_cpp_lsqrtest_ez(lb):
+    """tests/cpp/lsqrtest_ez.cpp = test/lsqrtest_ez.f90 through the C++ host mirror (include/lsqr_b200.hpp)."""
+    r = _run_cpp("lsqrtest_ez")
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert "ALL EZ TESTS PASSED" in r.stdout and "TEST FAILED" not in r.stdout
+    assert " Exit  LSQR.       istop  = 1" in r.stdout          # README.md:56
+
+
+def test_cpp_lstp_suite_through_the_operator_hook(lb, tmp_path):
+    """tests/cpp/lsqrtest.cu = test/lsqrtest.f90: the 18 LSTP problems through lsqr_solver%lsqr / acheck / xcheck with
+    a device-resident Householder operator, each compared with the oracle on the identical problem."""
+    lis = tmp_path / "LSQR_B200.LIS"
+    r = _run_cpp("lsqrtest", str(lis))
+    assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-2000:]
+    assert "ALL 18 LSTP PROBLEMS MATCH THE ORACLE" in r.stdout
+    text = lis.read_text()
+    assert text.count("Least-Squares Test Problem") == 18 and text.count("Enter xcheck.") == 18
+    assert text.count("aprod seems OK") == 18                    # test/LSQR.LIS:11 etc.
