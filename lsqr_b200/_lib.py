@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "liblsqr_b200.so")
+LIB_PATH = os.environ.get("LSQR_B200_LIB") or os.path.join(HERE, "lib", "liblsqr_b200.so")
 
 LOG_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_char_p)
 

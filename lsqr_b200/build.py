@@ -10,9 +10,13 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "build")
+# LSQR_B200_BUILD_TAG / LSQR_B200_EXTRA_NVCC_FLAGS build an experimental copy next to the product library
+# (lib/liblsqr_b200.<tag>.so, e.g. with -DLSQRB_WARP_MINBLOCKS=3); run with LSQR_B200_LIB pointing at it.
+TAG = os.environ.get("LSQR_B200_BUILD_TAG", "")
+EXTRA = os.environ.get("LSQR_B200_EXTRA_NVCC_FLAGS", "").split()
+OBJ = os.path.join(HERE, "build" + ("_" + TAG if TAG else ""))
 LIBDIR = os.path.join(HERE, "lib")
-LIB = os.path.join(LIBDIR, "liblsqr_b200.so")
+LIB = os.path.join(LIBDIR, "liblsqr_b200" + ("." + TAG if TAG else "") + ".so")
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
@@ -45,7 +49,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         obj = os.path.join(OBJ, src.replace(".cu", ".o"))
         objs.append(obj)
         if force or _stale(obj, _deps(src)):
-            cmd = [NVCC, *ARCH, *FLAGS, "-I", os.path.join(os.path.dirname(HERE), "include"),
+            cmd = [NVCC, *ARCH, *FLAGS, *EXTRA, "-I", os.path.join(os.path.dirname(HERE), "include"),
                    "-c", os.path.join(CSRC, src), "-o", obj]
             r = subprocess.run(cmd, capture_output=True, text=True)
             log = r.stdout + r.stderr

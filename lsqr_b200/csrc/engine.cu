@@ -245,7 +245,6 @@ static int launch_spmv(Work &wk, const CsrView &V, int lanes, const double *x, d
 struct TileMapOwner {
     uint2 *tiles = nullptr;
     int ntiles = 0;
-    int interleaved = 0;     // variant 3: interleaved gather (set per matrix at initialize)
     uint32_t tile = kTile;   // nominal stored entries per tile
     int kind = 2;            // 2 = CTA tiles of the TMA-streamed kernel, 3 = warp tiles of the segmented kernel
 };
@@ -311,11 +310,9 @@ static int launch_stream(Work &wk, const CsrView &V, const TileMapOwner &map, co
     a.ring = wk.ring_d;
     a.out_aligned16 = ((uintptr_t)out & 15u) == 0;
     a.check_done = ex.check_done;
-    a.gather_interleaved = map.interleaved;
     if (map.kind == 3) {
         const int grid = std::max(1, std::min((map.ntiles + kWWarps - 1) / kWWarps, wk.sms * kWMinBlocks));
-        if (map.interleaved) spmv_warp_kernel<EPI, true><<<grid, kWThreads, 0, wk.stream>>>(a);
-        else                 spmv_warp_kernel<EPI, false><<<grid, kWThreads, 0, wk.stream>>>(a);
+        spmv_warp_kernel<EPI><<<grid, kWThreads, 0, wk.stream>>>(a);
     } else {
         int occ = 1;
         LSQRB_TRY(stream_kernel_prepare<EPI>(&occ));
@@ -641,12 +638,6 @@ static int ez_initialize_impl(lsqr_b200_ez *me, int64_t nnz, const double *a, co
             LSQRB_TRY(build_tile_map(wk, view_of_block(me->AT, b), me->at_off[(size_t)b + 1] - me->at_off[(size_t)b],
                                      variant == 2 ? 2 : 3, &me->mapAT[(size_t)b]));
         LSQRB_CUDA(cudaStreamSynchronize(wk.stream));
-    }
-    {
-        const int ga = env_int("LSQR_B200_GATHER_A", env_int("LSQR_B200_GATHER", 0));
-        const int gt = env_int("LSQR_B200_GATHER_AT", env_int("LSQR_B200_GATHER", 0));
-        me->mapA.interleaved = ga;
-        for (auto &mp : me->mapAT) mp.interleaved = gt;
     }
     if (env_int("LSQR_B200_VERBOSE", 0))
         fprintf(stderr, "[lsqr_b200] m=%d n=%d nnz=%lld variant=%d A' blocks=%lld (block_rows=%lld) warp tile A=%u A'=%u\n", me->m, me->n,

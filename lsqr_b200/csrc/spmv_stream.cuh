@@ -125,12 +125,13 @@ struct StreamArgs {
     double *aux;           // multi-GPU: where SEPI_APROD puts its partial sum(u'^2)
     double *ux, *uw, *use; // SEPI_ATPROD_UPD: solution, search direction, standard errors
     int out_aligned16;     // out[] may be the source of 16-byte aligned bulk copies
-    int gather_interleaved;  // variant 3: lanes gather entries 32 k + lane instead of 4 lane + k (matrices with locality)
     int check_done;        // unfused STORE / ACC launched from the solve loop: nothing to do once the solver has stopped
     volatile lsqr_b200_iter_record *ring;
 };
 
-template <int EPI>
+// LAZY: the two epilogue coefficients are re-read from the (kernel-invariant, L1-resident) device state at every
+// use instead of living in registers for the whole kernel (the warp kernel is register-bound).
+template <int EPI, bool LAZY = false>
 struct RowEpilogue {
     double cm = 1.0, cv = 0.0;
     bool upd = false, wantse = false;
@@ -141,9 +142,21 @@ struct RowEpilogue {
 
     __device__ __forceinline__ void load(const DevState *st)
     {
-        if (EPI == SEPI_APROD) { cm = st->ca_mat; cv = st->ca_vec; }
-        if (EPI == SEPI_ATPROD || EPI == SEPI_INIT_ATPROD || EPI == SEPI_ATPROD_UPD) { cm = st->ct_mat; cv = st->ct_vec; }
+        if (!LAZY) {
+            if (EPI == SEPI_APROD) { cm = st->ca_mat; cv = st->ca_vec; }
+            if (EPI == SEPI_ATPROD || EPI == SEPI_INIT_ATPROD || EPI == SEPI_ATPROD_UPD) { cm = st->ct_mat; cv = st->ct_vec; }
+        }
         if (EPI == SEPI_ATPROD_UPD) { upd = st->upd_pending != 0; wantse = st->wantse != 0; }
+    }
+    __device__ __forceinline__ double coef_mat(const DevState *st) const
+    {
+        if (!LAZY) return cm;
+        return EPI == SEPI_APROD ? __ldg(&st->ca_mat) : __ldg(&st->ct_mat);
+    }
+    __device__ __forceinline__ double coef_vec(const DevState *st) const
+    {
+        if (!LAZY) return cv;
+        return EPI == SEPI_APROD ? __ldg(&st->ca_vec) : __ldg(&st->ct_vec);
     }
     __device__ __forceinline__ void load_update_coefficients(const DevState *st)
     {
@@ -157,8 +170,8 @@ struct RowEpilogue {
     {
         if (EPI == SEPI_ACC) { a.out[row] = old + s; return; }
         if (EPI == SEPI_STORE) { a.out[row] = s; return; }
-        if (EPI == SEPI_INIT_ATPROD) { const double r = cm * s; a.out[row] = r; sq += r * r; return; }
-        const double r = cm * s + cv * old;
+        if (EPI == SEPI_INIT_ATPROD) { const double r = coef_mat(a.st) * s; a.out[row] = r; sq += r * r; return; }
+        const double r = coef_mat(a.st) * s + coef_vec(a.st) * old;
         a.out[row] = r;
         sq += r * r;
         if (EPI == SEPI_ATPROD_UPD && upd) {

@@ -25,7 +25,10 @@ namespace lsqrb {
 
 constexpr int kWThreads = 256;               // 8 warps per CTA
 constexpr int kWWarps = kWThreads / 32;
-constexpr int kWMinBlocks = 4;               // 32 warps per SM, <= 64 registers per thread
+#ifndef LSQRB_WARP_MINBLOCKS
+#define LSQRB_WARP_MINBLOCKS 4
+#endif
+constexpr int kWMinBlocks = LSQRB_WARP_MINBLOCKS;   // 4: 32 warps per SM, <= 64 registers per thread
 constexpr uint32_t kChunk = 128;             // stored entries per warp step (4 per lane)
 constexpr uint32_t kPtrSentinel = 0xFFFFFFFFu;
 
@@ -42,7 +45,7 @@ struct RowWindow {
     uint32_t P, PE;
     double O;
     double W, X;   // fused deferred update only: w[row], x[row]
-    __device__ __forceinline__ void load(const StreamArgs &a, const RowEpilogue<EPI> &epi, uint32_t wb, uint32_t r1, int lane)
+    __device__ __forceinline__ void load(const StreamArgs &a, const RowEpilogue<EPI, true> &epi, uint32_t wb, uint32_t r1, int lane)
     {
         const uint32_t r = wb + (uint32_t)lane;
         P = PE = kPtrSentinel;
@@ -63,34 +66,28 @@ struct ChunkRegs {
     int32_t c[4];
 };
 
-// Loads one lane's share of the chunk that starts at entry `cb` of the tile [e0, e1): values of entries
-// [cb+4 lane, +4).  Entries outside the tile (they belong to the neighbouring tiles or to the allocation slack)
-// get the value 0 and so add nothing to any row.  Column indices: of the same four entries (blocked gather), or
-// of entries cb + 32 k + lane, k = 0..3 (interleaved gather: the 32 lanes of one gather instruction then touch 32
-// CONSECUTIVE stored entries, which for matrices with locality means a handful of cache lines instead of 32).
-// Indices of entries past the tile are replaced by 0: a harmless in-bounds gather.
-__device__ __forceinline__ void load_chunk(const CsrView &A, uint32_t cb, int lane, uint32_t e0, uint32_t e1, bool interleaved,
+// Loads one lane's share of the chunk that starts at entry `cb` of the tile [e0, e1): entries [cb+4 lane, +4).
+// Entries outside the tile (they belong to the neighbouring tiles or to the allocation slack) get the value 0
+// and so add nothing to any row; their column index stays a valid one.  Lanes entirely past the tile read
+// nothing (index 0: a harmless in-bounds gather).
+__device__ __forceinline__ void load_chunk(const CsrView &A, uint32_t cb, int lane, uint32_t e0, uint32_t e1,
                                            uint64_t pol_stream, ChunkRegs &r)
 {
     const uint32_t q = cb + 4u * (uint32_t)lane;
+    if (cb >= e0 && cb + kChunk <= e1) {   // steady state: the whole chunk lies inside the tile
+        ldg_stream_f64x4(A.val + q, r.v);
+        ldg_stream_s32x4(A.idx + q, r.c, pol_stream);
+        return;
+    }
     if (q < e1) {
         ldg_stream_f64x4(A.val + q, r.v);
-        if (!interleaved) ldg_stream_s32x4(A.idx + q, r.c, pol_stream);
-        if (q < e0 || q + 4u > e1) {   // only the first and the last chunk of a tile
+        ldg_stream_s32x4(A.idx + q, r.c, pol_stream);
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (q + k < e0 || q + k >= e1) r.v[k] = 0.0;
-        }
+        for (int k = 0; k < 4; ++k)
+            if (q + k < e0 || q + k >= e1) r.v[k] = 0.0;
     } else {
 #pragma unroll
         for (int k = 0; k < 4; ++k) { r.v[k] = 0.0; r.c[k] = 0; }
-    }
-    if (interleaved) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const uint32_t qi = cb + 32u * (uint32_t)k + (uint32_t)lane;
-            r.c[k] = qi < e1 ? ldg_stream_s32(A.idx + qi, pol_stream) : 0;
-        }
     }
 }
 
@@ -103,29 +100,18 @@ struct WarpTileState {
 
 // Processes the chunk [base, base+128) held in `cur`; `nxt` receives the following chunk, whose loads
 // stay in flight while this one is reduced.
-template <int EPI, bool IL>
-__device__ __forceinline__ void warp_chunk(const StreamArgs &a, RowEpilogue<EPI> &epi, double *su, WarpTileState<EPI> &ts,
+template <int EPI>
+__device__ __forceinline__ void warp_chunk(const StreamArgs &a, RowEpilogue<EPI, true> &epi, double *su, WarpTileState<EPI> &ts,
                                            const ChunkRegs &cur, ChunkRegs &nxt, uint32_t base, uint32_t r1, uint32_t e0, uint32_t e1,
                                            int lane, uint64_t pol_stream, uint64_t pol_keep)
 {
     const uint32_t endp = base + kChunk;
-    constexpr bool interleaved = IL;
     // ---- gathers of this chunk, then the stream of the next one
-    double x0 = ldg_keep_f64(a.x + cur.c[0], pol_keep);
-    double x1 = ldg_keep_f64(a.x + cur.c[1], pol_keep);
-    double x2 = ldg_keep_f64(a.x + cur.c[2], pol_keep);
-    double x3 = ldg_keep_f64(a.x + cur.c[3], pol_keep);
-    load_chunk(a.A, endp, lane, e0, e1, interleaved, pol_stream, nxt);
-    if (interleaved) {
-        // x_k belongs to entry 32 k + lane: transpose through the warp's buffer so that the lane holds the
-        // operands of its own entries 4 lane .. 4 lane + 3
-        su[lane] = x0; su[32 + lane] = x1; su[64 + lane] = x2; su[96 + lane] = x3;
-        __syncwarp();
-        const double2 a01 = *reinterpret_cast<const double2 *>(su + 4 * lane);
-        const double2 a23 = *reinterpret_cast<const double2 *>(su + 4 * lane + 2);
-        x0 = a01.x; x1 = a01.y; x2 = a23.x; x3 = a23.y;
-        __syncwarp();
-    }
+    const double x0 = ldg_keep_f64(a.x + cur.c[0], pol_keep);
+    const double x1 = ldg_keep_f64(a.x + cur.c[1], pol_keep);
+    const double x2 = ldg_keep_f64(a.x + cur.c[2], pol_keep);
+    const double x3 = ldg_keep_f64(a.x + cur.c[3], pol_keep);
+    load_chunk(a.A, endp, lane, e0, e1, pol_stream, nxt);
 
     // ---- head mask of the chunk: bit i set <=> a row starts at entry base+i
     uint32_t m0 = 0, m1 = 0, m2 = 0, m3 = 0;
@@ -208,8 +194,8 @@ __device__ __forceinline__ void warp_chunk(const StreamArgs &a, RowEpilogue<EPI>
     }
 }
 
-template <int EPI, bool IL>
-__device__ __forceinline__ void warp_tile(const StreamArgs &a, RowEpilogue<EPI> &epi, double *su /* 128 doubles, this warp's */,
+template <int EPI>
+__device__ __forceinline__ void warp_tile(const StreamArgs &a, RowEpilogue<EPI, true> &epi, double *su /* 128 doubles, this warp's */,
                                           uint32_t r0, uint32_t r1, uint32_t e0, uint32_t e1, int lane,
                                           uint64_t pol_stream, uint64_t pol_keep)
 {
@@ -220,20 +206,20 @@ __device__ __forceinline__ void warp_tile(const StreamArgs &a, RowEpilogue<EPI> 
     ts.carry = 0.0;
     ts.win.load(a, epi, r0, r1, lane);
     ChunkRegs ra, rb;
-    load_chunk(a.A, a0, lane, e0, e1, IL, pol_stream, ra);
+    load_chunk(a.A, a0, lane, e0, e1, pol_stream, ra);
     // two chunks per trip so that the register double buffer needs no copies; at least one chunk is processed
     // even for a tile without entries, so that its (empty) rows still get their epilogue
     for (uint32_t base = a0;;) {
-        warp_chunk<EPI, IL>(a, epi, su, ts, ra, rb, base, r1, e0, e1, lane, pol_stream, pol_keep);
+        warp_chunk<EPI>(a, epi, su, ts, ra, rb, base, r1, e0, e1, lane, pol_stream, pol_keep);
         base += kChunk;
         if (base >= e1) break;
-        warp_chunk<EPI, IL>(a, epi, su, ts, rb, ra, base, r1, e0, e1, lane, pol_stream, pol_keep);
+        warp_chunk<EPI>(a, epi, su, ts, rb, ra, base, r1, e0, e1, lane, pol_stream, pol_keep);
         base += kChunk;
         if (base >= e1) break;
     }
 }
 
-template <int EPI, bool IL>
+template <int EPI>
 __global__ void __launch_bounds__(kWThreads, kWMinBlocks)
 spmv_warp_kernel(StreamArgs a)
 {
@@ -242,7 +228,7 @@ spmv_warp_kernel(StreamArgs a)
     __shared__ __align__(16) double s_u[kWWarps][kChunk];
 
     DevState *st = a.st;
-    RowEpilogue<EPI> epi;
+    RowEpilogue<EPI, true> epi;
     int mode = MODE_FULL;
     const int tid = threadIdx.x;
     bool tracing = false;
@@ -290,7 +276,7 @@ spmv_warp_kernel(StreamArgs a)
         for (int t = (int)blockIdx.x * kWWarps + wib; t < a.map.ntiles; t += nw) {
             const uint2 d0 = tiles[t], d1 = tiles[t + 1];
             if (d0.x == d1.x) continue;                     // no row starts in this tile (inside a long row)
-            warp_tile<EPI, IL>(a, epi, s_u[wib], d0.x, d1.x, d0.y, d1.y, lane, pol_stream, pol_keep);
+            warp_tile<EPI>(a, epi, s_u[wib], d0.x, d1.x, d0.y, d1.y, lane, pol_stream, pol_keep);
         }
     }
 
