@@ -309,6 +309,12 @@ def main():
         "loop_frac": (bytes_iter * last.itn / (kt["loop_ms"] * 1e-3) / 1e9) / (peak * world) if kt["loop_ms"] > 0 else None,
     }
 
+    # orderly shutdown on every rank: the engine's communicator first (a collective), then torch's
+    solver.destroy()
+    if world > 1:
+        import torch.distributed as td
+        td.barrier()
+        td.destroy_process_group()
     if rank != 0:
         return
     value = bytes_iter * itn / (ms * 1e-3) / 1e9
@@ -339,9 +345,6 @@ def main():
         cb = run_cpu_reference(name, args.cpu_scale, 3, 1, budget_s=20.0)
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "iters_per_s")}
     print(json.dumps(line), flush=True)
-    if world > 1:
-        import torch.distributed as td
-        td.destroy_process_group()
 
 
 if __name__ == "__main__":
