@@ -479,7 +479,12 @@ struct lsqr_b200_ez {
     std::vector<int64_t> at_off;       // first stored entry of every block of A' (nblocks + 1 values)
     bool stream = true;           // tiled kernels (variants 2, 3) vs sub-warp-per-row (variant 1)
     bool blocked = false;         // A' is row-blocked (u does not fit in L2): Atprod = one launch per block into g
-    bool deferred = true;         // single GPU, tiled, unblocked: x/w update fused into the next Atprod (2 kernels / iteration)
+    bool deferred = false;        // single GPU, tiled, unblocked: x/w update fused into the next Atprod (2 kernels / iteration)
+    bool overlap_update = true;   // fused engine, 3 kernels / iteration: the x/w update of iteration k runs on a side
+                                  // stream next to the Aprod of iteration k+1 (they touch disjoint vectors)
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool side_pending = false;    // an update is in flight on the side stream that the main stream has not joined
     lsqr_b200_options opt;
     double *u = nullptr, *v = nullptr, *w = nullptr, *x = nullptr, *se = nullptr;
     double *g = nullptr;          // multi-GPU: [ A_p'u_p (n) | sum(u_p^2) ]
@@ -506,7 +511,8 @@ static void ez_free(lsqr_b200_ez *me)
     if (me->mapA.tiles) cudaFree(me->mapA.tiles);
     for (auto &mp : me->mapAT) if (mp.tiles) cudaFree(mp.tiles);
     for (double *p : {me->u, me->v, me->w, me->x, me->se, me->g, me->tmp_m, me->tmp_n}) if (p) cudaFree(p);
-    for (auto e : {me->ev_t0, me->ev_t1, me->ev_t2}) if (e) cudaEventDestroy(e);
+    for (auto e : {me->ev_t0, me->ev_t1, me->ev_t2, me->ev_fork, me->ev_join}) if (e) cudaEventDestroy(e);
+    if (me->side) cudaStreamDestroy(me->side);
     for (auto e : me->prof_ev) cudaEventDestroy(e);
     me->wk.destroy();
     delete me;
@@ -621,7 +627,13 @@ static int ez_initialize_impl(lsqr_b200_ez *me, int64_t nnz, const double *a, co
     const int variant = me->opt.spmv_variant ? me->opt.spmv_variant : env_int("LSQR_B200_SPMV_VARIANT", 3);
     me->stream = variant != 1;
     me->blocked = me->AT.nblocks > 1;
-    me->deferred = me->stream && !me->blocked && me->opt.world_size == 1 && env_int("LSQR_B200_DEFERRED_UPDATE", 1) != 0;
+    me->deferred = me->stream && !me->blocked && me->opt.world_size == 1 && env_int("LSQR_B200_DEFERRED_UPDATE", 0) != 0;
+    me->overlap_update = !me->deferred && !me->blocked && me->opt.world_size == 1 && env_int("LSQR_B200_OVERLAP_UPDATE", 1) != 0;
+    if (me->overlap_update) {
+        LSQRB_CUDA(cudaStreamCreateWithFlags(&me->side, cudaStreamNonBlocking));
+        LSQRB_CUDA(cudaEventCreateWithFlags(&me->ev_fork, cudaEventDisableTiming));
+        LSQRB_CUDA(cudaEventCreateWithFlags(&me->ev_join, cudaEventDisableTiming));
+    }
     {   // first stored entry of every block of A'
         const int64_t nb = me->AT.nblocks;
         me->at_off.assign((size_t)nb + 1, 0);
@@ -880,11 +892,39 @@ static int enqueue_iteration(lsqr_b200_ez *me, bool wantse)
         { ProfScope p(me, CLS_APROD);  LSQRB_TRY(do_aprod_fused(me, nullptr)); }
         { ProfScope p(me, CLS_ATPROD); LSQRB_TRY(do_atprod_upd(me)); }
         return LSQR_B200_OK;
+    } else if (me->overlap_update) {
+        // K3(k+1) reads v, writes u; K5(k) reads v, writes x, w: disjoint, so the update leaves the critical path.
+        // K4 overwrites v and needs ||w||^2, so it joins the side stream first.
+        { ProfScope p(me, CLS_APROD);  LSQRB_TRY(do_aprod_fused(me, nullptr)); }
+        if (me->side_pending) { LSQRB_CUDA(cudaStreamWaitEvent(wk.stream, me->ev_join, 0)); me->side_pending = false; }
+        { ProfScope p(me, CLS_ATPROD); LSQRB_TRY(do_atprod_fused(me)); }
+        LSQRB_CUDA(cudaEventRecord(me->ev_fork, wk.stream));
+        LSQRB_CUDA(cudaStreamWaitEvent(me->side, me->ev_fork, 0));
+        {
+            cudaStream_t main_stream = wk.stream;
+            wk.stream = me->side;
+            int rc = launch_update<true>(wk, me->n, me->x, me->w, me->v, me->se, wantse);
+            wk.stream = main_stream;
+            LSQRB_TRY(rc);
+        }
+        LSQRB_CUDA(cudaEventRecord(me->ev_join, me->side));
+        me->side_pending = true;
+        return LSQR_B200_OK;
     } else {
         { ProfScope p(me, CLS_APROD);  LSQRB_TRY(do_aprod_fused(me, nullptr)); }
         { ProfScope p(me, CLS_ATPROD); LSQRB_TRY(do_atprod_fused(me)); }
     }
     { ProfScope p(me, CLS_UPDATE); LSQRB_TRY(launch_update<true>(wk, me->n, me->x, me->w, me->v, me->se, wantse)); }
+    return LSQR_B200_OK;
+}
+
+// the side stream must be joined before anything else (graph capture end, result copies, the next batch's bookkeeping)
+static int join_side(lsqr_b200_ez *me)
+{
+    if (me->side_pending) {
+        LSQRB_CUDA(cudaStreamWaitEvent(me->wk.stream, me->ev_join, 0));
+        me->side_pending = false;
+    }
     return LSQR_B200_OK;
 }
 
@@ -898,6 +938,8 @@ static int build_graph(lsqr_b200_ez *me, bool wantse)
     LSQRB_CUDA(cudaStreamBeginCapture(wk.stream, cudaStreamCaptureModeThreadLocal));
     int rc = LSQR_B200_OK;
     for (int i = 0; i < me->batch && rc == LSQR_B200_OK; ++i) rc = enqueue_iteration(me, wantse);
+    if (rc == LSQR_B200_OK) rc = join_side(me);   // every fork rejoins the origin stream before the capture ends
+    me->side_pending = false;
     cudaError_t e = cudaStreamEndCapture(wk.stream, &graph);
     wk.launches = saved;
     if (rc != LSQR_B200_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
@@ -974,6 +1016,7 @@ static int ez_solve_fused(lsqr_b200_ez *me, const double *b, double damp, double
             wk.launches += (int64_t)B * (me->deferred ? 2 : me->blocked ? 3 + me->AT.nblocks : 3);
         } else {
             for (int i = 0; i < B; ++i) LSQRB_TRY(enqueue_iteration(me, wantse));
+            LSQRB_TRY(join_side(me));
         }
         LSQRB_CUDA(cudaEventRecord(wk.ev[nb & 3], wk.stream));
         enq += B;

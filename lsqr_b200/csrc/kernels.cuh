@@ -238,14 +238,16 @@ __device__ __forceinline__ void step_after_update(DevState &s, double sum_w2, do
 // that draws the last ticket sums the slots in index order with a fixed tree, so the result does
 // not depend on block scheduling.  Returns true in thread 0 of the last block only.
 // =============================================================================================
+// `slots`: which partial array to use (two kernels that may run concurrently must not share one)
 template <int THREADS>
 __device__ __forceinline__ bool finish_reduction(DevState *st, int cslot, double thread_val,
-                                                 double *smem, double *total)
+                                                 double *smem, double *total, double *slots = nullptr)
 {
     __shared__ int s_is_last;
+    if (!slots) slots = st->partial;
     const double bs = block_sum<THREADS>(thread_val, smem);
     if (threadIdx.x == 0) {
-        __stcg(&st->partial[blockIdx.x], bs);
+        __stcg(&slots[blockIdx.x], bs);
         __threadfence();
         const unsigned int ticket = atomicAdd(&st->counter[cslot], 1u);
         s_is_last = (ticket == gridDim.x - 1);
@@ -254,7 +256,7 @@ __device__ __forceinline__ bool finish_reduction(DevState *st, int cslot, double
     if (!s_is_last) return false;
     __threadfence();
     double acc = 0.0;
-    for (int i = threadIdx.x; i < (int)gridDim.x; i += THREADS) acc += __ldcg(&st->partial[i]);
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += THREADS) acc += __ldcg(&slots[i]);
     const double tot = block_sum<THREADS>(acc, smem);
     if (threadIdx.x == 0) {
         st->counter[cslot] = 0;
@@ -445,7 +447,8 @@ xw_update_kernel(int64_t n, double *__restrict__ x, double *__restrict__ w, cons
         if (WANTSE) se[i] += (t3 * wo) * (t3 * wo);
     }
     double total;
-    if (finish_reduction<kThreads>(st, 1, sq, s_red, &total)) {
+    // own partial slots and ticket: this kernel may run next to the Aprod of the following iteration
+    if (finish_reduction<kThreads>(st, 1, sq, s_red, &total, st->partial2)) {
         __threadfence();
         const double x1 = __ldcg(x);   // x(1) after the update
         step_after_update(*st, total, x1, ring);
