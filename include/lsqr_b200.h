@@ -158,12 +158,14 @@ LSQR_B200_API int lsqr_b200_ez_set_options(lsqr_b200_ez *me, const lsqr_b200_opt
 LSQR_B200_API int lsqr_b200_ez_get_csr(lsqr_b200_ez *me, int32_t which,
                          int64_t *ptr, int32_t *idx, double *val, int64_t *perm);
 LSQR_B200_API int64_t lsqr_b200_ez_nnz(const lsqr_b200_ez *me);
-/* Layout of the stored transpose.  When u (8 m bytes) cannot stay in L2, A' is kept ROW-BLOCKED: one CSR per block
- * of block_rows consecutive rows of A, stored back to back, so that every Atprod launch gathers from a slice of
- * u that fits in L2.  lsqr_b200_ez_get_csr(which = 1) then returns ptr[nblocks*n + 1]: block b is the stable
- * (by COO position) column sort of the entries whose row lies in [b*block_rows, (b+1)*block_rows).
- * nblocks = 1 (block_rows = 0) is the plain CSR of A'. */
-LSQR_B200_API int lsqr_b200_ez_transpose_blocks(const lsqr_b200_ez *me, int64_t *nblocks, int64_t *block_rows);
+/* Layout of the stored matrices.  When the gathered vector of a product cannot stay in L2 the matrix is kept
+ * BLOCKED along the gathered coordinate, one CSR per block, stored back to back:
+ *   which = 1 (A', gathers u, 8 m bytes): blocks of block_size consecutive ROWS of A;
+ *   which = 0 (A,  gathers v, 8 n bytes): blocks of block_size consecutive COLUMNS of A.
+ * lsqr_b200_ez_get_csr(which) then returns ptr[nblocks*nkeys + 1]: block b is the stable (by COO position) sort by
+ * key of the entries whose other coordinate lies in [b*block_size, (b+1)*block_size).
+ * nblocks = 1 (block_size = 0) is the plain CSR. */
+LSQR_B200_API int lsqr_b200_ez_blocks(const lsqr_b200_ez *me, int32_t which, int64_t *nblocks, int64_t *block_size);
 
 /* Kernel timing of the most recent solve.  loop_ms / init_ms / total_launches are always
  * filled; the per-kernel averages only when options.profile = 1 (CUDA-event pairs around every

@@ -99,8 +99,8 @@ def load() -> C.CDLL:
     L.lsqr_b200_ez_set_options.argtypes = [vp, C.POINTER(Options)]
     L.lsqr_b200_ez_get_csr.restype = C.c_int
     L.lsqr_b200_ez_get_csr.argtypes = [vp, C.c_int32, vp, vp, vp, vp]
-    L.lsqr_b200_ez_transpose_blocks.restype = C.c_int
-    L.lsqr_b200_ez_transpose_blocks.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    L.lsqr_b200_ez_blocks.restype = C.c_int
+    L.lsqr_b200_ez_blocks.argtypes = [vp, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.lsqr_b200_ez_nnz.restype = C.c_int64
     L.lsqr_b200_ez_nnz.argtypes = [vp]
     L.lsqr_b200_ez_get_kernel_times.restype = C.c_int

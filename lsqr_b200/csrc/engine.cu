@@ -474,8 +474,11 @@ struct lsqr_b200_ez {
     int64_t nnz = 0;
     Csr A, AT;
     int lanes_a = 4, lanes_at = 32;
-    TileMapOwner mapA;
+    std::vector<TileMapOwner> mapA;    // one per block of the column-blocked A
     std::vector<TileMapOwner> mapAT;   // one per block of the row-blocked transpose
+    std::vector<int64_t> a_off;        // first stored entry of every block of A (nblocks + 1 values)
+    bool a_blocked = false;            // A is column-blocked (v does not fit in L2): Aprod = one launch per block into gu
+    double *gu = nullptr;              // [m] A v of the column-blocked Aprod
     std::vector<int64_t> at_off;       // first stored entry of every block of A' (nblocks + 1 values)
     bool stream = true;           // tiled kernels (variants 2, 3) vs sub-warp-per-row (variant 1)
     bool blocked = false;         // A' is row-blocked (u does not fit in L2): Atprod = one launch per block into g
@@ -508,8 +511,9 @@ static void ez_free(lsqr_b200_ez *me)
     if (me->comm) { NcclApi *a = nccl_api(); if (a) a->CommDestroy(me->comm); }
     csr_free(&me->A);
     csr_free(&me->AT);
-    if (me->mapA.tiles) cudaFree(me->mapA.tiles);
+    for (auto &mp : me->mapA) if (mp.tiles) cudaFree(mp.tiles);
     for (auto &mp : me->mapAT) if (mp.tiles) cudaFree(mp.tiles);
+    if (me->gu) cudaFree(me->gu);
     for (double *p : {me->u, me->v, me->w, me->x, me->se, me->g, me->tmp_m, me->tmp_n}) if (p) cudaFree(p);
     for (auto e : {me->ev_t0, me->ev_t1, me->ev_t2, me->ev_fork, me->ev_join}) if (e) cudaEventDestroy(e);
     if (me->side) cudaStreamDestroy(me->side);
@@ -604,7 +608,18 @@ static int ez_initialize_impl(lsqr_b200_ez *me, int64_t nnz, const double *a, co
         if (!dev_src) { cudaFree(d_irow); cudaFree(d_icol); cudaFree(d_a); }
     };
     int rc = coo_validate(wk.stream, me->m, me->n, nnz, d_irow, d_icol);
-    if (rc == LSQR_B200_OK) rc = coo_to_csr_device(wk.stream, me->m, nnz, d_irow, d_icol, d_a, &me->A);
+    if (rc == LSQR_B200_OK) {
+        // Column-blocked A: the mirror image of the row-blocked transpose below, for a v (8 n bytes) beyond the L2 budget
+        int64_t block_cols = env_int("LSQR_B200_VBLOCK_COLS", 0);
+        if (block_cols <= 0) {
+            const int64_t budget = (int64_t)env_int("LSQR_B200_VBLOCK_MB", 48) * (1 << 20) / 8;
+            if (me->n > budget) {
+                const int64_t nb = (me->n + budget - 1) / budget;
+                block_cols = (me->n + nb - 1) / nb;
+            }
+        }
+        rc = coo_to_csr_device(wk.stream, me->m, nnz, d_irow, d_icol, d_a, &me->A, block_cols, me->n);
+    }
     if (rc == LSQR_B200_OK) {
         // Row-blocked transpose: when u (8 m bytes) cannot stay in L2 while A' streams past it, A' is stored as one
         // CSR per block of rows of A, so that every Atprod launch gathers from a slice of u that does fit.
@@ -627,34 +642,44 @@ static int ez_initialize_impl(lsqr_b200_ez *me, int64_t nnz, const double *a, co
     const int variant = me->opt.spmv_variant ? me->opt.spmv_variant : env_int("LSQR_B200_SPMV_VARIANT", 3);
     me->stream = variant != 1;
     me->blocked = me->AT.nblocks > 1;
-    me->deferred = me->stream && !me->blocked && me->opt.world_size == 1 && env_int("LSQR_B200_DEFERRED_UPDATE", 0) != 0;
-    me->overlap_update = !me->deferred && !me->blocked && me->opt.world_size == 1 && env_int("LSQR_B200_OVERLAP_UPDATE", 1) != 0;
+    me->a_blocked = me->A.nblocks > 1;
+    me->deferred = me->stream && !me->blocked && !me->a_blocked && me->opt.world_size == 1 && env_int("LSQR_B200_DEFERRED_UPDATE", 0) != 0;
+    me->overlap_update = !me->deferred && !me->blocked && !me->a_blocked && me->opt.world_size == 1 && env_int("LSQR_B200_OVERLAP_UPDATE", 1) != 0;
     if (me->overlap_update) {
         LSQRB_CUDA(cudaStreamCreateWithFlags(&me->side, cudaStreamNonBlocking));
         LSQRB_CUDA(cudaEventCreateWithFlags(&me->ev_fork, cudaEventDisableTiming));
         LSQRB_CUDA(cudaEventCreateWithFlags(&me->ev_join, cudaEventDisableTiming));
     }
-    {   // first stored entry of every block of A'
-        const int64_t nb = me->AT.nblocks;
-        me->at_off.assign((size_t)nb + 1, 0);
+    // first stored entry of every block of A and of A'
+    auto block_offsets = [&](const Csr &M, std::vector<int64_t> *out) -> int {
+        const int64_t nb = M.nblocks;
+        out->assign((size_t)nb + 1, 0);
         std::vector<uint32_t> off((size_t)nb + 1);
         for (int64_t b = 0; b <= nb; ++b)
-            LSQRB_CUDA(cudaMemcpyAsync(&off[(size_t)b], me->AT.ptr + b * me->AT.nkeys, sizeof(uint32_t), cudaMemcpyDeviceToHost, wk.stream));
+            LSQRB_CUDA(cudaMemcpyAsync(&off[(size_t)b], M.ptr + b * M.nkeys, sizeof(uint32_t), cudaMemcpyDeviceToHost, wk.stream));
         LSQRB_CUDA(cudaStreamSynchronize(wk.stream));
-        for (int64_t b = 0; b <= nb; ++b) me->at_off[(size_t)b] = off[(size_t)b];
-    }
+        for (int64_t b = 0; b <= nb; ++b) (*out)[(size_t)b] = off[(size_t)b];
+        return LSQR_B200_OK;
+    };
+    LSQRB_TRY(block_offsets(me->A, &me->a_off));
+    LSQRB_TRY(block_offsets(me->AT, &me->at_off));
     if (me->stream) {
-        LSQRB_TRY(build_tile_map(wk, view_of(me->A), me->A.nnz, variant == 2 ? 2 : 3, &me->mapA));
+        me->mapA.resize((size_t)me->A.nblocks);
+        for (int64_t b = 0; b < me->A.nblocks; ++b)
+            LSQRB_TRY(build_tile_map(wk, view_of_block(me->A, b), me->a_off[(size_t)b + 1] - me->a_off[(size_t)b],
+                                     variant == 2 ? 2 : 3, &me->mapA[(size_t)b]));
         me->mapAT.resize((size_t)me->AT.nblocks);
         for (int64_t b = 0; b < me->AT.nblocks; ++b)
             LSQRB_TRY(build_tile_map(wk, view_of_block(me->AT, b), me->at_off[(size_t)b + 1] - me->at_off[(size_t)b],
                                      variant == 2 ? 2 : 3, &me->mapAT[(size_t)b]));
         LSQRB_CUDA(cudaStreamSynchronize(wk.stream));
     }
+    if (me->a_blocked) LSQRB_CUDA(cudaMalloc(&me->gu, sizeof(double) * (size_t)std::max<int32_t>(me->m, 1)));
     if (env_int("LSQR_B200_VERBOSE", 0))
-        fprintf(stderr, "[lsqr_b200] m=%d n=%d nnz=%lld variant=%d A' blocks=%lld (block_rows=%lld) warp tile A=%u A'=%u\n", me->m, me->n,
-                (long long)me->nnz, variant, (long long)me->AT.nblocks, (long long)me->AT.block_rows, me->mapA.tile,
-                me->mapAT.empty() ? 0u : me->mapAT[0].tile);
+        fprintf(stderr, "[lsqr_b200] m=%d n=%d nnz=%lld variant=%d A blocks=%lld (block_cols=%lld) A' blocks=%lld (block_rows=%lld) "
+                        "warp tile A=%u A'=%u\n", me->m, me->n, (long long)me->nnz, variant,
+                (long long)me->A.nblocks, (long long)me->A.block_rows, (long long)me->AT.nblocks, (long long)me->AT.block_rows,
+                me->mapA.empty() ? 0u : me->mapA[0].tile, me->mapAT.empty() ? 0u : me->mapAT[0].tile);
 
     const size_t mm = (size_t)std::max<int32_t>(me->m, 1), nn = (size_t)std::max<int32_t>(me->n, 1);
     LSQRB_CUDA(cudaMalloc(&me->u, sizeof(double) * mm));
@@ -727,11 +752,12 @@ int lsqr_b200_ez_set_options(lsqr_b200_ez *me, const lsqr_b200_options *o)
 
 int64_t lsqr_b200_ez_nnz(const lsqr_b200_ez *me) { return me ? me->nnz : -1; }
 
-int lsqr_b200_ez_transpose_blocks(const lsqr_b200_ez *me, int64_t *nblocks, int64_t *block_rows)
+int lsqr_b200_ez_blocks(const lsqr_b200_ez *me, int32_t which, int64_t *nblocks, int64_t *block_size)
 {
-    if (!me) return LSQR_B200_ERR_ARG;
-    if (nblocks) *nblocks = me->AT.nblocks;
-    if (block_rows) *block_rows = me->AT.block_rows;
+    if (!me || (which != 0 && which != 1)) return LSQR_B200_ERR_ARG;
+    const Csr &M = which == 0 ? me->A : me->AT;
+    if (nblocks) *nblocks = M.nblocks;
+    if (block_size) *block_size = M.block_rows;
     return LSQR_B200_OK;
 }
 
@@ -770,8 +796,12 @@ int lsqr_b200_ez_aprod_device(void *handle, int32_t mode, int32_t m, int32_t n,
     cudaStream_t saved = wk.stream;
     if (stream) wk.stream = (cudaStream_t)stream;
     int rc;
-    if (mode == 1)      rc = me->stream ? launch_stream<SEPI_ACC>(wk, view_of(me->A), me->mapA, x_dev, y_dev, nullptr)
-                                        : launch_spmv<EPI_ACC>(wk, view_of(me->A), me->lanes_a, x_dev, y_dev, nullptr);    // y += A x
+    if (mode == 1) {                                                                                                       // y += A x
+        rc = LSQR_B200_OK;
+        for (int64_t b = 0; b < me->A.nblocks && rc == LSQR_B200_OK; ++b)
+            rc = me->stream ? launch_stream<SEPI_ACC>(wk, view_of_block(me->A, b), me->mapA[(size_t)b], x_dev, y_dev, nullptr)
+                            : launch_spmv<EPI_ACC>(wk, view_of_block(me->A, b), me->lanes_a, x_dev, y_dev, nullptr);
+    }
     else if (mode == 2) {                                                                                                  // x += A'y
         rc = LSQR_B200_OK;
         for (int64_t b = 0; b < me->AT.nblocks && rc == LSQR_B200_OK; ++b)
@@ -841,8 +871,24 @@ static int allreduce_g(lsqr_b200_ez *me)
 // the SpMV flavours of one handle
 static int do_aprod_fused(lsqr_b200_ez *me, double *aux)
 {
-    return me->stream ? launch_stream<SEPI_APROD>(me->wk, view_of(me->A), me->mapA, me->v, me->u, aux)
-                      : launch_spmv<EPI_FUSED_APROD>(me->wk, view_of(me->A), me->lanes_a, me->v, me->u, aux);
+    if (!me->a_blocked)
+        return me->stream ? launch_stream<SEPI_APROD>(me->wk, view_of(me->A), me->mapA[0], me->v, me->u, aux)
+                          : launch_spmv<EPI_FUSED_APROD>(me->wk, view_of(me->A), me->lanes_a, me->v, me->u, aux);
+    // column-blocked A: gu = A v block by block (block 0 stores, the others accumulate), then the fused finish
+    Work &wk = me->wk;
+    StreamExtra ex;
+    ex.check_done = 1;
+    for (int64_t b = 0; b < me->A.nblocks; ++b) {
+        const CsrView V = view_of_block(me->A, b);
+        if (b == 0) LSQRB_TRY(me->stream ? launch_stream<SEPI_STORE>(wk, V, me->mapA[0], me->v, me->gu, nullptr, ex)
+                                         : launch_spmv<EPI_STORE>(wk, V, me->lanes_a, me->v, me->gu, nullptr, 1));
+        else        LSQRB_TRY(me->stream ? launch_stream<SEPI_ACC>(wk, V, me->mapA[(size_t)b], me->v, me->gu, nullptr, ex)
+                                         : launch_spmv<EPI_ACC>(wk, V, me->lanes_a, me->v, me->gu, nullptr, 1));
+    }
+    ufinish_kernel<<<wk.grid_for(me->m, kThreads), kThreads, 0, wk.stream>>>(me->m, me->gu, me->u, wk.st, aux);
+    wk.launches++;
+    LSQRB_CUDA(cudaGetLastError());
+    return LSQR_B200_OK;
 }
 // g = A'u (unfused: multi-GPU partial and/or row-blocked transpose): block 0 stores, the others accumulate
 static int do_atprod_store(lsqr_b200_ez *me)
@@ -1013,7 +1059,7 @@ static int ez_solve_fused(lsqr_b200_ez *me, const double *b, double damp, double
     auto enqueue_batch = [&]() -> int {
         if (use_graph) {
             LSQRB_CUDA(cudaGraphLaunch(me->graph_exec, wk.stream));
-            wk.launches += (int64_t)B * (me->deferred ? 2 : me->blocked ? 3 + me->AT.nblocks : 3);
+            wk.launches += (int64_t)B * (me->deferred ? 2 : (me->blocked ? 2 + me->AT.nblocks : 2) + (me->a_blocked ? 1 + me->A.nblocks : 1));
         } else {
             for (int i = 0; i < B; ++i) LSQRB_TRY(enqueue_iteration(me, wantse));
             LSQRB_TRY(join_side(me));

@@ -541,6 +541,28 @@ axpy_kernel(int64_t n, double a, const double *__restrict__ x, double *__restric
 }
 
 // =============================================================================================
+// Column-blocked A (v does not fit in L2): gu = A v has been formed block by block; finish the Aprod step
+//   u' = ca_mat * gu + ca_vec * u ;  sum(u'^2)  ->  step_after_aprod (or the partial to aux, multi-GPU)
+// =============================================================================================
+__global__ void __launch_bounds__(kThreads)
+ufinish_kernel(int64_t m, const double *__restrict__ gu, double *__restrict__ u, DevState *st, double *aux)
+{
+    __shared__ double s_red[kThreads / 32];
+    if (st->done || st->istop != 0) return;
+    const double cm = st->ca_mat, cv = st->ca_vec;
+    double sq = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < m; i += (int64_t)gridDim.x * kThreads) {
+        const double r = cm * gu[i] + cv * u[i];
+        u[i] = r;
+        sq += r * r;
+    }
+    double total;
+    if (finish_reduction<kThreads>(st, 0, sq, s_red, &total)) {
+        if (aux) *aux = total; else step_after_aprod(*st, total);
+    }
+}
+
+// =============================================================================================
 // K8 (multi-GPU): after the all-reduce of g = [ A'u' (n entries) | sum(u'^2) ] every rank forms
 //   beta = sqrt(g[n]);  v' = g/beta - (beta/alpha) v;  sum(v'^2)
 // redundantly (v is replicated), so alpha, the rotations and the stop decision are bit-identical

@@ -230,16 +230,20 @@ class LsqrSolverEz:
     def nnz(self) -> int:
         return int(_lib.load().lsqr_b200_ez_nnz(self._h))
 
+    def blocks(self, transpose: bool = False):
+        """(nblocks, block_size) of the stored A (column-blocked when v does not fit in L2) or A' (row-blocked
+        when u does not)."""
+        nb, bs = C.c_int64(), C.c_int64()
+        _lib.check(_lib.load().lsqr_b200_ez_blocks(self._h, int(transpose), C.byref(nb), C.byref(bs)))
+        return nb.value, bs.value
+
     def transpose_blocks(self):
-        """(nblocks, block_rows) of the stored transpose (row-blocked when u does not fit in L2)."""
-        nb, br = C.c_int64(), C.c_int64()
-        _lib.check(_lib.load().lsqr_b200_ez_transpose_blocks(self._h, C.byref(nb), C.byref(br)))
-        return nb.value, br.value
+        return self.blocks(True)
 
     def get_csr(self, transpose: bool = False):
-        """Host copies (ptr, idx, val, perm) of the device-built CSR of A (or of A').  For a row-blocked
-        transpose ptr has nblocks*n + 1 entries (see ``transpose_blocks``)."""
-        nkeys = self.n * self.transpose_blocks()[0] if transpose else self.m
+        """Host copies (ptr, idx, val, perm) of the device-built CSR of A (or of A').  For a blocked layout ptr
+        has nblocks*nkeys + 1 entries (see ``blocks``)."""
+        nkeys = (self.n if transpose else self.m) * self.blocks(transpose)[0]
         nnz = self.nnz
         ptr = np.zeros(nkeys + 1, np.int64)
         idx = np.zeros(max(nnz, 1), np.int32)

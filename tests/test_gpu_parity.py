@@ -547,6 +547,47 @@ def test_row_blocked_transpose(lb, variant, monkeypatch):
     assert relerr(r.se, rr.se) <= 1e-8
 
 
+@pytest.mark.parametrize("variant", [1, 2, 3])
+@pytest.mark.parametrize("also_rows", [False, True])
+def test_column_blocked_matrix(lb, variant, also_rows, monkeypatch):
+    """Forces small column blocks of A (and, optionally, row blocks of A' as well): blocked CSR bit-exact against
+    the oracle's per-block row sort; products and solves (damped, with se) agree with the oracle."""
+    from lsqr_b200 import synth
+    monkeypatch.setenv("LSQR_B200_VBLOCK_COLS", "900")
+    if also_rows:
+        monkeypatch.setenv("LSQR_B200_UBLOCK_ROWS", "9000")
+    cfg = synth.scaled("C3", 400)                             # 25 000 x 5 000 banded, damp 1e-3
+    m, n = cfg["m"], cfg["n"]
+    irow, icol, a = synth.coo_block(cfg["kind"], cfg["seed"], m, n, cfg["k"])
+    irow, icol, a = synth.shuffle_coo(irow, icol, a, 5)
+    b = synth.rhs_block(irow, icol, a, m, synth.x_true(cfg["seed"], n), cfg["seed"])
+    s = lb.LsqrSolverEz().initialize(m, n, a, irow, icol, atol=1e-9, btol=1e-9, conlim=1e8, itnlim=2000, spmv_variant=variant)
+    nb, bs = s.blocks(False)
+    assert (nb, bs) == (6, 900)
+    assert s.blocks(True) == ((3, 9000) if also_rows else (1, 0))
+    ptr, idx, val, perm = s.get_csr(False)
+    assert ptr.size == nb * m + 1
+    pos = np.arange(irow.size)
+    for blk in range(nb):
+        sel = pos[(icol - 1) // bs == blk]
+        rptr, ridx, rval, rperm = O.coo_to_csr(m, irow[sel], icol[sel], a[sel], by_col=False)
+        lo, hi = ptr[blk * m], ptr[(blk + 1) * m]
+        np.testing.assert_array_equal(ptr[blk * m:(blk + 1) * m + 1] - lo, rptr)
+        np.testing.assert_array_equal(perm[lo:hi], sel[rperm])
+        np.testing.assert_array_equal(idx[lo:hi], ridx)
+        assert val[lo:hi].tobytes() == rval.tobytes()
+    ref = O.SolverEz(m, n, a, irow, icol, atol=1e-9, btol=1e-9, conlim=1e8, itnlim=2000)
+    rng = np.random.default_rng(6)
+    x, y = rng.standard_normal(n), rng.standard_normal(m)
+    y1, yr = y.copy(), y.copy()
+    s.aprod(1, m, n, x, y1); ref.aprod(1, x.copy(), yr)
+    assert relerr(y1, yr) <= 1e-14
+    r, rr = s.solve(b, cfg["damp"], want_se=True), ref.solve(b, cfg["damp"], wantse=True)
+    assert r.istop == rr.istop == 3 and abs(r.itn - rr.itn) <= 2
+    assert relerr(r.x, rr.x) <= RTOL
+    assert relerr(r.se, rr.se) <= 1e-8
+
+
 # ------------------------------------------------------------------ the reference's own test programs, in C++
 def _run_cpp(name, *args, timeout=900):
     import os, subprocess
