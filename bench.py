@@ -26,9 +26,11 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
-# stdout carries exactly one JSON line: keep NCCL's version banner (printed at NCCL_DEBUG=VERSION) out of it
-if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-    os.environ["NCCL_DEBUG"] = "WARN"
+# stdout carries exactly ONE JSON line.  Libraries (NCCL prints its version banner at NCCL_DEBUG=WARN/VERSION) write
+# to file descriptor 1 directly, so fd 1 is pointed at stderr for the life of the process and the JSON line goes to
+# a private duplicate of the original stdout.
+_JSON_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
 
 import numpy as np
 
@@ -173,7 +175,7 @@ def reference_main(args):
         "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -347,7 +349,7 @@ def main():
     if world == 1 and not args.no_cpu_baseline:
         cb = run_cpu_reference(name, args.cpu_scale, 3, 1, budget_s=20.0)
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "iters_per_s")}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
 
 
 if __name__ == "__main__":

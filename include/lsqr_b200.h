@@ -157,6 +157,10 @@ LSQR_B200_API int lsqr_b200_ez_set_options(lsqr_b200_ez *me, const lsqr_b200_opt
  * Any output may be NULL. */
 LSQR_B200_API int lsqr_b200_ez_get_csr(lsqr_b200_ez *me, int32_t which,
                          int64_t *ptr, int32_t *idx, double *val, int64_t *perm);
+/* The same arrays in place, as DEVICE pointers owned by the handle (ptr is 32-bit on the device; any output may
+ * be NULL): lets full-size property tests inspect the layout without a 10 GB host copy. */
+LSQR_B200_API int lsqr_b200_ez_get_csr_device(lsqr_b200_ez *me, int32_t which, const uint32_t **ptr_dev,
+                                const int32_t **idx_dev, const double **val_dev, const uint32_t **perm_dev);
 LSQR_B200_API int64_t lsqr_b200_ez_nnz(const lsqr_b200_ez *me);
 /* Layout of the stored matrices.  When the gathered vector of a product cannot stay in L2 the matrix is kept
  * BLOCKED along the gathered coordinate, one CSR per block, stored back to back:

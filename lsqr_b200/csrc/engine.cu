@@ -750,6 +750,18 @@ int lsqr_b200_ez_set_options(lsqr_b200_ez *me, const lsqr_b200_options *o)
     return LSQR_B200_OK;
 }
 
+int lsqr_b200_ez_get_csr_device(lsqr_b200_ez *me, int32_t which, const uint32_t **ptr_dev, const int32_t **idx_dev,
+                                const double **val_dev, const uint32_t **perm_dev)
+{
+    if (!me || (which != 0 && which != 1)) return LSQR_B200_ERR_ARG;
+    const Csr &M = which == 0 ? me->A : me->AT;
+    if (ptr_dev) *ptr_dev = M.ptr;
+    if (idx_dev) *idx_dev = M.idx;
+    if (val_dev) *val_dev = M.val;
+    if (perm_dev) *perm_dev = M.perm;
+    return LSQR_B200_OK;
+}
+
 int64_t lsqr_b200_ez_nnz(const lsqr_b200_ez *me) { return me ? me->nnz : -1; }
 
 int lsqr_b200_ez_blocks(const lsqr_b200_ez *me, int32_t which, int64_t *nblocks, int64_t *block_size)

@@ -253,6 +253,24 @@ class LsqrSolverEz:
                                                    val.ctypes.data, perm.ctypes.data))
         return ptr, idx[:nnz], val[:nnz], perm[:nnz]
 
+    def csr_device(self, transpose: bool = False) -> dict:
+        """The device-resident CSR arrays of A (or A') as zero-copy torch views (valid while the solver lives):
+        ptr (int32 view of the 32-bit unsigned pointers), idx (int32), val (float64), perm (int32 view of uint32)."""
+        import torch
+        p = [C.c_void_p() for _ in range(4)]
+        _lib.check(_lib.load().lsqr_b200_ez_get_csr_device(self._h, int(transpose), *[C.byref(q) for q in p]))
+        nkeys = (self.n if transpose else self.m) * self.blocks(transpose)[0]
+        nnz = self.nnz
+
+        class _View:   # minimal __cuda_array_interface__ holder
+            def __init__(self, ptr, count, typestr):
+                self.__cuda_array_interface__ = {"shape": (count,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+        def view(q, count, typestr):
+            return torch.as_tensor(_View(q.value, count, typestr), device="cuda")
+        return {"ptr": view(p[0], nkeys + 1, "<i4"), "idx": view(p[1], max(nnz, 1), "<i4")[:nnz],
+                "val": view(p[2], max(nnz, 1), "<f8")[:nnz], "perm": view(p[3], max(nnz, 1), "<i4")[:nnz]}
+
     def kernel_times(self) -> dict:
         t = KernelTimes()
         _lib.check(_lib.load().lsqr_b200_ez_get_kernel_times(self._h, C.byref(t)))

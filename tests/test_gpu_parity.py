@@ -617,3 +617,66 @@ def test_cpp_lstp_suite_through_the_operator_hook(lb, tmp_path):
     text = lis.read_text()
     assert text.count("Least-Squares Test Problem") == 18 and text.count("Enter xcheck.") == 18
     assert text.count("aprod seems OK") == 18                    # test/LSQR.LIS:11 etc.
+
+
+# ------------------------------------------------------------------ BASELINE full sizes: size-independent properties
+@pytest.mark.parametrize("name", ["C3", "C4"])
+def test_full_size_properties(lb, name):
+    """C3 (10M x 2M, 5e8 entries, damped) and C4 (20M x 5M power law, ~5.4e8 entries) at BASELINE.json's full size,
+    where the serial oracle would need minutes: the device-built CSR / CSR' are verified COMPLETELY against their
+    definition (stable sort by key of the COO triplets: perm is a permutation, keys non-decreasing, COO order kept
+    inside a key, idx/val are the permuted triplets bit for bit, ptr is the key histogram's prefix sum), aprod is
+    checked for adjointness (acheck), the solution by xcheck's true residuals, and solves for linearity and
+    bitwise reproducibility."""
+    import torch
+    from lsqr_b200 import synth, synth_device
+    dev = torch.device("cuda", 0)
+    cfg = synth.CONFIGS[name]
+    m, n = cfg["m"], cfg["n"]
+    irow, icol, a = synth_device.coo_block(cfg["kind"], cfg["seed"], m, n, cfg["k"], 0, m, dev)
+    nnz = a.numel()
+    s = lb.LsqrSolverEz().initialize(m, n, a, irow, icol, atol=1e-10, btol=1e-10, conlim=1e8, itnlim=3000)
+    for transpose in (False, True):
+        key, other = (icol, irow) if transpose else (irow, icol)
+        nkeys_one = n if transpose else m
+        nb, bs = s.blocks(transpose)
+        c = s.csr_device(transpose)
+        perm = c["perm"].to(torch.int64)                      # nnz < 2^31 here
+        seen = torch.zeros(nnz, dtype=torch.bool, device=dev)
+        seen[perm] = True
+        assert bool(seen.all())                               # a permutation
+        del seen
+        k = key.to(torch.int64)[perm]
+        if nb > 1:
+            k = k + ((other.to(torch.int64)[perm] - 1) // bs) * nkeys_one      # composite key of the blocked layout
+        ok = (k[1:] > k[:-1]) | ((k[1:] == k[:-1]) & (perm[1:] > perm[:-1]))
+        assert bool(ok.all())                                 # sorted by key, COO order kept inside a key (stable)
+        del ok
+        assert torch.equal(c["idx"], other[perm] - 1)
+        assert torch.equal(c["val"].view(torch.int64), a[perm].view(torch.int64))      # bit for bit
+        counts = torch.bincount(k - 1, minlength=nb * nkeys_one)
+        ptr = c["ptr"].to(torch.int64)
+        assert int(ptr[0]) == 0 and int(ptr[-1]) == nnz
+        assert torch.equal(ptr[1:], torch.cumsum(counts, 0))
+        del k, perm, counts, ptr
+    # adjointness of the products (acheck, src/lsqr.f90:908-994) through the operator hook
+    op = lb.EzAsOperator(s)
+    v, x = torch.empty(n, dtype=torch.float64, device=dev), torch.empty(n, dtype=torch.float64, device=dev)
+    w, y = torch.empty(m, dtype=torch.float64, device=dev), torch.empty(m, dtype=torch.float64, device=dev)
+    inform, rel = op.acheck(m, n, v, w, x, y)
+    assert inform == 0 and rel <= 1e-12
+    # solve; true residuals by xcheck (src/lsqr.f90:1015-1154); linearity; reproducibility
+    xt = synth_device.x_true(cfg["seed"], n, dev)
+    b = synth_device.noise(cfg["seed"], 0, m, dev)
+    s.aprod(1, m, n, xt, b)                                    # b = A x_true + 1e-3 noise
+    r1 = s.solve(b, cfg["damp"])
+    assert r1.istop in (1, 2, 3) and 5 <= r1.itn < 3000
+    chk = op.xcheck(m, n, r1.anorm, cfg["damp"], b, w, v, x, r1.x)
+    assert chk["inform"] in (1, 2, 3)
+    assert abs(chk["rho2"] - r1.rnorm) <= 1e-6 * r1.rnorm      # LSQR's rnorm estimate equals the true (damped) residual
+    x1 = r1.x.clone()
+    r2 = s.solve(b, cfg["damp"])
+    assert r2.itn == r1.itn and torch.equal(r2.x.view(torch.int64), x1.view(torch.int64))
+    r3 = s.solve(2.0 * b, cfg["damp"])
+    assert r3.istop == r1.istop and abs(r3.itn - r1.itn) <= 1
+    assert float((r3.x - 2.0 * x1).norm() / x1.norm()) <= 1e-8
