@@ -477,6 +477,14 @@ struct lsqr_b200_ez {
     std::vector<TileMapOwner> mapA;    // one per block of the column-blocked A
     std::vector<TileMapOwner> mapAT;   // one per block of the row-blocked transpose
     std::vector<int64_t> a_off;        // first stored entry of every block of A (nblocks + 1 values)
+    // multi-GPU: the columns of A' are cut into comm_chunks ranges; the all-reduce of range c runs on comm_stream
+    // while the SpMV launches of range c+1 compute (mapATc[b * comm_chunks + c], chunk c = columns [cc[c], cc[c+1]))
+    int comm_chunks = 1;
+    std::vector<int64_t> cc;
+    std::vector<TileMapOwner> mapATc;
+    cudaStream_t comm_stream = nullptr;
+    cudaEvent_t ev_chunk[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_comm = nullptr;
     bool a_blocked = false;            // A is column-blocked (v does not fit in L2): Aprod = one launch per block into gu
     double *gu = nullptr;              // [m] A v of the column-blocked Aprod
     std::vector<int64_t> at_off;       // first stored entry of every block of A' (nblocks + 1 values)
@@ -513,6 +521,10 @@ static void ez_free(lsqr_b200_ez *me)
     csr_free(&me->AT);
     for (auto &mp : me->mapA) if (mp.tiles) cudaFree(mp.tiles);
     for (auto &mp : me->mapAT) if (mp.tiles) cudaFree(mp.tiles);
+    for (auto &mp : me->mapATc) if (mp.tiles) cudaFree(mp.tiles);
+    for (auto e : me->ev_chunk) if (e) cudaEventDestroy(e);
+    if (me->ev_comm) cudaEventDestroy(me->ev_comm);
+    if (me->comm_stream) cudaStreamDestroy(me->comm_stream);
     if (me->gu) cudaFree(me->gu);
     for (double *p : {me->u, me->v, me->w, me->x, me->se, me->g, me->tmp_m, me->tmp_n}) if (p) cudaFree(p);
     for (auto e : {me->ev_t0, me->ev_t1, me->ev_t2, me->ev_fork, me->ev_join}) if (e) cudaEventDestroy(e);
@@ -675,6 +687,36 @@ static int ez_initialize_impl(lsqr_b200_ez *me, int64_t nnz, const double *a, co
         LSQRB_CUDA(cudaStreamSynchronize(wk.stream));
     }
     if (me->a_blocked) LSQRB_CUDA(cudaMalloc(&me->gu, sizeof(double) * (size_t)std::max<int32_t>(me->m, 1)));
+    if (me->opt.world_size > 1 && me->stream) {
+        // column chunks for the pipelined all-reduce (only worth it when a chunk is a sizeable message)
+        int k = env_int("LSQR_B200_COMM_CHUNKS", me->n >= (1 << 21) ? 4 : 1);
+        k = std::max(1, std::min(k, 8));
+        me->comm_chunks = k;
+        if (k > 1) {
+            me->cc.assign((size_t)k + 1, 0);
+            for (int c = 0; c <= k; ++c) me->cc[(size_t)c] = c == k ? (int64_t)me->n : (((int64_t)me->n * c / k) & ~(int64_t)1);
+            const int64_t nb = me->AT.nblocks;
+            std::vector<uint32_t> off((size_t)(nb * (k + 1)));
+            for (int64_t b = 0; b < nb; ++b)
+                for (int c = 0; c <= k; ++c)
+                    LSQRB_CUDA(cudaMemcpyAsync(&off[(size_t)(b * (k + 1) + c)], me->AT.ptr + b * me->AT.nkeys + me->cc[(size_t)c],
+                                               sizeof(uint32_t), cudaMemcpyDeviceToHost, wk.stream));
+            LSQRB_CUDA(cudaStreamSynchronize(wk.stream));
+            me->mapATc.resize((size_t)(nb * k));
+            for (int64_t b = 0; b < nb; ++b)
+                for (int c = 0; c < k; ++c) {
+                    CsrView V = view_of_block(me->AT, b);
+                    V.ptr += me->cc[(size_t)c];
+                    V.nrows = me->cc[(size_t)c + 1] - me->cc[(size_t)c];
+                    const int64_t nz = (int64_t)off[(size_t)(b * (k + 1) + c + 1)] - (int64_t)off[(size_t)(b * (k + 1) + c)];
+                    LSQRB_TRY(build_tile_map(wk, V, nz, variant == 2 ? 2 : 3, &me->mapATc[(size_t)(b * k + c)]));
+                }
+            LSQRB_CUDA(cudaStreamSynchronize(wk.stream));
+            LSQRB_CUDA(cudaStreamCreateWithFlags(&me->comm_stream, cudaStreamNonBlocking));
+            for (int c = 0; c < k; ++c) LSQRB_CUDA(cudaEventCreateWithFlags(&me->ev_chunk[c], cudaEventDisableTiming));
+            LSQRB_CUDA(cudaEventCreateWithFlags(&me->ev_comm, cudaEventDisableTiming));
+        }
+    }
     if (env_int("LSQR_B200_VERBOSE", 0))
         fprintf(stderr, "[lsqr_b200] m=%d n=%d nnz=%lld variant=%d A blocks=%lld (block_cols=%lld) A' blocks=%lld (block_rows=%lld) "
                         "warp tile A=%u A'=%u\n", me->m, me->n, (long long)me->nnz, variant,
@@ -916,6 +958,40 @@ static int do_atprod_store(lsqr_b200_ez *me)
     }
     return LSQR_B200_OK;
 }
+// multi-GPU: g = sum over ranks of [A_p'u_p | sum u_p^2].  With comm_chunks > 1 the all-reduce of column range c
+// (on comm_stream) overlaps the SpMV launches of range c+1; the Atprod is then ordered chunk-major, block-minor.
+static int do_atprod_allreduce(lsqr_b200_ez *me)
+{
+    Work &wk = me->wk;
+    NcclApi *api = nccl_api();
+    const int k = me->comm_chunks;
+    if (k <= 1) {
+        LSQRB_TRY(do_atprod_store(me));
+        return allreduce_g(me);
+    }
+    StreamExtra ex;
+    ex.check_done = 1;
+    const int64_t nb = me->AT.nblocks;
+    for (int c = 0; c < k; ++c) {
+        const int64_t c0 = me->cc[(size_t)c], c1 = me->cc[(size_t)c + 1];
+        for (int64_t b = 0; b < nb; ++b) {
+            CsrView V = view_of_block(me->AT, b);
+            V.ptr += c0;
+            V.nrows = c1 - c0;
+            const TileMapOwner &mp = me->mapATc[(size_t)(b * k + c)];
+            if (b == 0) LSQRB_TRY(launch_stream<SEPI_STORE>(wk, V, mp, me->u, me->g + c0, nullptr, ex));
+            else        LSQRB_TRY(launch_stream<SEPI_ACC>(wk, V, mp, me->u, me->g + c0, nullptr, ex));
+        }
+        LSQRB_CUDA(cudaEventRecord(me->ev_chunk[c], wk.stream));
+        LSQRB_CUDA(cudaStreamWaitEvent(me->comm_stream, me->ev_chunk[c], 0));
+        const size_t count = (size_t)(c1 - c0) + (c == k - 1 ? 1 : 0);     // the last range carries sum(u_p^2) in g[n]
+        LSQRB_NCCL(api->AllReduce(me->g + c0, me->g + c0, count, ncclFloat64, ncclSum, me->comm, me->comm_stream));
+    }
+    LSQRB_CUDA(cudaEventRecord(me->ev_comm, me->comm_stream));
+    LSQRB_CUDA(cudaStreamWaitEvent(wk.stream, me->ev_comm, 0));
+    return LSQR_B200_OK;
+}
+
 static int do_atprod_fused(lsqr_b200_ez *me)
 {
     return me->stream ? launch_stream<SEPI_ATPROD>(me->wk, view_of(me->AT), me->mapAT[0], me->u, me->v, nullptr)
@@ -941,8 +1017,8 @@ static int enqueue_iteration(lsqr_b200_ez *me, bool wantse)
         // unfused pipeline: u' and its partial norm, g = [A'u' | sum u'^2] (all-reduced over the ranks), then
         // v' = g/beta - (beta/alpha) v with both scalar steps, then the x/w update
         { ProfScope p(me, CLS_APROD);  LSQRB_TRY(do_aprod_fused(me, me->g + me->n)); }
-        { ProfScope p(me, CLS_ATPROD); LSQRB_TRY(do_atprod_store(me)); }
-        if (me->opt.world_size > 1) { ProfScope p(me, CLS_OTHER);  LSQRB_TRY(allreduce_g(me)); }
+        if (me->opt.world_size > 1) { ProfScope p(me, CLS_ATPROD); LSQRB_TRY(do_atprod_allreduce(me)); }   // (timed together)
+        else                        { ProfScope p(me, CLS_ATPROD); LSQRB_TRY(do_atprod_store(me)); }
         { ProfScope p(me, CLS_OTHER);
           vfinish_kernel<false><<<wk.grid_for(me->n, kThreads), kThreads, 0, wk.stream>>>(me->n, me->g, me->v, wk.st);
           wk.launches++; LSQRB_CUDA(cudaGetLastError()); }
@@ -1046,8 +1122,8 @@ static int ez_solve_fused(lsqr_b200_ez *me, const double *b, double damp, double
     if (unfused) {
         sumsq_kernel<POST_NONE><<<wk.grid_for(m, kThreads), kThreads, 0, wk.stream>>>(m, me->u, wk.st, me->g + n);
         wk.launches++;
-        LSQRB_TRY(do_atprod_store(me));
-        if (dist) LSQRB_TRY(allreduce_g(me));
+        if (dist) LSQRB_TRY(do_atprod_allreduce(me));
+        else      LSQRB_TRY(do_atprod_store(me));
         vfinish_kernel<true><<<wk.grid_for(n, kThreads), kThreads, 0, wk.stream>>>(n, me->g, me->v, wk.st);
         wk.launches++;
     } else {
