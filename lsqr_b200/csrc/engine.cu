@@ -477,8 +477,8 @@ struct lsqr_b200_ez {
     std::vector<TileMapOwner> mapA;    // one per block of the column-blocked A
     std::vector<TileMapOwner> mapAT;   // one per block of the row-blocked transpose
     std::vector<int64_t> a_off;        // first stored entry of every block of A (nblocks + 1 values)
-    // multi-GPU: the columns of A' are cut into comm_chunks ranges; the all-reduce of range c runs on comm_stream
-    // while the SpMV launches of range c+1 compute (mapATc[b * comm_chunks + c], chunk c = columns [cc[c], cc[c+1]))
+    // multi-GPU: the LAST row block of A' is cut into comm_chunks column ranges; the all-reduce of range c runs on
+    // comm_stream while the SpMV launch of range c+1 computes (mapATc[c], chunk c = columns [cc[c], cc[c+1]))
     int comm_chunks = 1;
     std::vector<int64_t> cc;
     std::vector<TileMapOwner> mapATc;
@@ -695,22 +695,20 @@ static int ez_initialize_impl(lsqr_b200_ez *me, int64_t nnz, const double *a, co
         if (k > 1) {
             me->cc.assign((size_t)k + 1, 0);
             for (int c = 0; c <= k; ++c) me->cc[(size_t)c] = c == k ? (int64_t)me->n : (((int64_t)me->n * c / k) & ~(int64_t)1);
-            const int64_t nb = me->AT.nblocks;
-            std::vector<uint32_t> off((size_t)(nb * (k + 1)));
-            for (int64_t b = 0; b < nb; ++b)
-                for (int c = 0; c <= k; ++c)
-                    LSQRB_CUDA(cudaMemcpyAsync(&off[(size_t)(b * (k + 1) + c)], me->AT.ptr + b * me->AT.nkeys + me->cc[(size_t)c],
-                                               sizeof(uint32_t), cudaMemcpyDeviceToHost, wk.stream));
+            const int64_t bl = me->AT.nblocks - 1;          // only the last block is pipelined (no extra passes over u)
+            std::vector<uint32_t> off((size_t)k + 1);
+            for (int c = 0; c <= k; ++c)
+                LSQRB_CUDA(cudaMemcpyAsync(&off[(size_t)c], me->AT.ptr + bl * me->AT.nkeys + me->cc[(size_t)c],
+                                           sizeof(uint32_t), cudaMemcpyDeviceToHost, wk.stream));
             LSQRB_CUDA(cudaStreamSynchronize(wk.stream));
-            me->mapATc.resize((size_t)(nb * k));
-            for (int64_t b = 0; b < nb; ++b)
-                for (int c = 0; c < k; ++c) {
-                    CsrView V = view_of_block(me->AT, b);
-                    V.ptr += me->cc[(size_t)c];
-                    V.nrows = me->cc[(size_t)c + 1] - me->cc[(size_t)c];
-                    const int64_t nz = (int64_t)off[(size_t)(b * (k + 1) + c + 1)] - (int64_t)off[(size_t)(b * (k + 1) + c)];
-                    LSQRB_TRY(build_tile_map(wk, V, nz, variant == 2 ? 2 : 3, &me->mapATc[(size_t)(b * k + c)]));
-                }
+            me->mapATc.resize((size_t)k);
+            for (int c = 0; c < k; ++c) {
+                CsrView V = view_of_block(me->AT, bl);
+                V.ptr += me->cc[(size_t)c];
+                V.nrows = me->cc[(size_t)c + 1] - me->cc[(size_t)c];
+                LSQRB_TRY(build_tile_map(wk, V, (int64_t)off[(size_t)c + 1] - (int64_t)off[(size_t)c], variant == 2 ? 2 : 3,
+                                         &me->mapATc[(size_t)c]));
+            }
             LSQRB_CUDA(cudaStreamSynchronize(wk.stream));
             LSQRB_CUDA(cudaStreamCreateWithFlags(&me->comm_stream, cudaStreamNonBlocking));
             for (int c = 0; c < k; ++c) LSQRB_CUDA(cudaEventCreateWithFlags(&me->ev_chunk[c], cudaEventDisableTiming));
@@ -972,16 +970,18 @@ static int do_atprod_allreduce(lsqr_b200_ez *me)
     StreamExtra ex;
     ex.check_done = 1;
     const int64_t nb = me->AT.nblocks;
-    for (int c = 0; c < k; ++c) {
+    for (int64_t b = 0; b + 1 < nb; ++b) {               // all but the last block: whole-width launches
+        const CsrView V = view_of_block(me->AT, b);
+        if (b == 0) LSQRB_TRY(launch_stream<SEPI_STORE>(wk, V, me->mapAT[0], me->u, me->g, nullptr, ex));
+        else        LSQRB_TRY(launch_stream<SEPI_ACC>(wk, V, me->mapAT[(size_t)b], me->u, me->g, nullptr, ex));
+    }
+    for (int c = 0; c < k; ++c) {                        // last block, range by range, each followed by its all-reduce
         const int64_t c0 = me->cc[(size_t)c], c1 = me->cc[(size_t)c + 1];
-        for (int64_t b = 0; b < nb; ++b) {
-            CsrView V = view_of_block(me->AT, b);
-            V.ptr += c0;
-            V.nrows = c1 - c0;
-            const TileMapOwner &mp = me->mapATc[(size_t)(b * k + c)];
-            if (b == 0) LSQRB_TRY(launch_stream<SEPI_STORE>(wk, V, mp, me->u, me->g + c0, nullptr, ex));
-            else        LSQRB_TRY(launch_stream<SEPI_ACC>(wk, V, mp, me->u, me->g + c0, nullptr, ex));
-        }
+        CsrView V = view_of_block(me->AT, nb - 1);
+        V.ptr += c0;
+        V.nrows = c1 - c0;
+        if (nb == 1) LSQRB_TRY(launch_stream<SEPI_STORE>(wk, V, me->mapATc[(size_t)c], me->u, me->g + c0, nullptr, ex));
+        else         LSQRB_TRY(launch_stream<SEPI_ACC>(wk, V, me->mapATc[(size_t)c], me->u, me->g + c0, nullptr, ex));
         LSQRB_CUDA(cudaEventRecord(me->ev_chunk[c], wk.stream));
         LSQRB_CUDA(cudaStreamWaitEvent(me->comm_stream, me->ev_chunk[c], 0));
         const size_t count = (size_t)(c1 - c0) + (c == k - 1 ? 1 : 0);     // the last range carries sum(u_p^2) in g[n]
