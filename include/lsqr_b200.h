@@ -170,6 +170,12 @@ LSQR_B200_API int64_t lsqr_b200_ez_nnz(const lsqr_b200_ez *me);
  * key of the entries whose other coordinate lies in [b*block_size, (b+1)*block_size).
  * nblocks = 1 (block_size = 0) is the plain CSR. */
 LSQR_B200_API int lsqr_b200_ez_blocks(const lsqr_b200_ez *me, int32_t which, int64_t *nblocks, int64_t *block_size);
+/* Work schedule of the SpMV kernel over block `block` of the stored A (which = 0) or A' (which = 1): number of
+ * row-aligned tiles, nominal stored entries per tile, whether the tiles are dealt to the warps by the balanced
+ * (largest-first) schedule used for very uneven row lengths instead of round robin, and the load of the most
+ * loaded warp relative to the mean under the schedule in use.  Diagnostic; no reference counterpart. */
+LSQR_B200_API int lsqr_b200_ez_schedule(const lsqr_b200_ez *me, int32_t which, int64_t block, int64_t *ntiles,
+                          int64_t *tile_entries, int32_t *balanced, double *imbalance);
 
 /* Kernel timing of the most recent solve.  loop_ms / init_ms / total_launches are always
  * filled; the per-kernel averages only when options.profile = 1 (CUDA-event pairs around every

@@ -101,6 +101,9 @@ def load() -> C.CDLL:
     L.lsqr_b200_ez_get_csr.argtypes = [vp, C.c_int32, vp, vp, vp, vp]
     L.lsqr_b200_ez_blocks.restype = C.c_int
     L.lsqr_b200_ez_blocks.argtypes = [vp, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    L.lsqr_b200_ez_schedule.restype = C.c_int
+    L.lsqr_b200_ez_schedule.argtypes = [vp, C.c_int32, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                                        C.POINTER(C.c_int32), C.POINTER(C.c_double)]
     L.lsqr_b200_ez_get_csr_device.restype = C.c_int
     L.lsqr_b200_ez_get_csr_device.argtypes = [vp, C.c_int32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     L.lsqr_b200_ez_nnz.restype = C.c_int64

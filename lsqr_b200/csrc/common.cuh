@@ -80,8 +80,9 @@ struct DevState {
     double partial[kMaxPartials];
     double partial2[kMaxPartials];   // second simultaneous reduction (fused Atprod + deferred update)
 
-    // trace[0]: first instruction of block 0, trace[1]: last block starts the final sum, trace[2]: scalar step done
-    unsigned long long trace[3][kTraceSlots];
+    // trace[0]: first instruction of block 0, trace[1]: last block has the final sums, trace[2]: scalar step done,
+    // trace[3]: (fused Atprod + update only) between step_after_update and step_after_atprod
+    unsigned long long trace[4][kTraceSlots];
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -167,6 +168,10 @@ __device__ __forceinline__ void ldg_stream_s32x8(const int32_t *p, int32_t (&v)[
     asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v8.s32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                  : "l"(p));
+}
+__device__ __forceinline__ void prefetch_l2(const void *p)
+{
+    asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
 }
 // Gathered dense vector: read-only path, keep in L2.
 __device__ __forceinline__ double ldg_keep_f64(const double *p, uint64_t pol)

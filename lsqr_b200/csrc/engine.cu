@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <queue>
 #include <vector>
 
 #include "build_csr.h"
@@ -193,16 +194,18 @@ struct Work {
     void dump_trace()
     {
         const int n = std::min(h.tr_n, kTraceSlots);
-        std::vector<unsigned long long> t((size_t)3 * kTraceSlots);
+        std::vector<unsigned long long> t((size_t)4 * kTraceSlots);
         if (cudaMemcpy(t.data(), (const char *)st + offsetof(DevState, trace), sizeof(unsigned long long) * t.size(),
                        cudaMemcpyDeviceToHost) != cudaSuccess) return;
-        fprintf(stderr, "[lsqr_b200 trace] %d fused kernels: idx start_us busy_us step_us gap_to_next_us\n", n);
+        fprintf(stderr, "[lsqr_b200 trace] %d fused kernels: idx start_us busy_us step_us gap_to_next_us upd_step_us\n", n);
         for (int k = 0; k < n; ++k) {
             const double t0 = (double)(t[k] - t[0]) * 1e-3;
             const double busy = (double)(t[kTraceSlots + k] - t[k]) * 1e-3;
             const double step = (double)(t[2 * kTraceSlots + k] - t[kTraceSlots + k]) * 1e-3;
             const double gap = k + 1 < n ? (double)(t[k + 1] - t[2 * kTraceSlots + k]) * 1e-3 : 0.0;
-            if (k < 40 || k >= n - 4) fprintf(stderr, "[lsqr_b200 trace] %4d %10.2f %8.2f %6.2f %6.2f\n", k, t0, busy, step, gap);
+            const unsigned long long tm = t[3 * kTraceSlots + k];
+            const double ustep = tm > t[kTraceSlots + k] && tm <= t[2 * kTraceSlots + k] ? (double)(tm - t[kTraceSlots + k]) * 1e-3 : 0.0;
+            if (k < 40 || k >= n - 4) fprintf(stderr, "[lsqr_b200 trace] %4d %10.2f %8.2f %6.2f %6.2f %6.2f\n", k, t0, busy, step, gap, ustep);
         }
     }
 };
@@ -247,7 +250,18 @@ struct TileMapOwner {
     int ntiles = 0;
     uint32_t tile = kTile;   // nominal stored entries per tile
     int kind = 2;            // 2 = CTA tiles of the TMA-streamed kernel, 3 = warp tiles of the segmented kernel
+    // kind 3, very uneven rows only: balanced tile schedule (see TileMap::order); the grid is then the full persistent grid
+    uint32_t *order = nullptr;
+    int nslots = 0;
+    double imbalance = 1.0;  // most loaded warp / mean load under the schedule in use (diagnostic)
 };
+
+static void tile_map_free(TileMapOwner &mp)
+{
+    if (mp.tiles) cudaFree(mp.tiles);
+    if (mp.order) cudaFree(mp.order);
+    mp.tiles = nullptr; mp.order = nullptr;
+}
 
 // Variant 3 sizes its tiles so that every warp of the persistent grid gets the same number of them
 // (k tiles of ~8K entries or less each): a small matrix is cut into exactly one tile per warp.
@@ -261,16 +275,94 @@ static uint32_t warp_tile_size(const Work &wk, int64_t nnz)
     return (uint32_t)std::max<int64_t>(512, (t + 3) & ~(int64_t)3);
 }
 
+static int build_tiles(Work &wk, const CsrView &V, int64_t nnz, uint32_t tile, TileMapOwner *out)
+{
+    if (out->tiles) { cudaFree(out->tiles); out->tiles = nullptr; }
+    out->tile = tile;
+    const int64_t nt = std::max<int64_t>(1, (nnz + tile - 1) / tile);
+    out->ntiles = (int)nt;
+    LSQRB_CUDA(cudaMalloc(&out->tiles, sizeof(uint2) * (size_t)(nt + 1)));
+    build_tiles_kernel<<<(int)((nt + 1 + 255) / 256), 256, 0, wk.stream>>>(V.ptr, V.nrows, (int)nt, tile, out->tiles);
+    LSQRB_CUDA(cudaGetLastError());
+    return LSQR_B200_OK;
+}
+
+// Cost of a warp tile in units of one 128-entry chunk: its chunks plus its row-window reloads.
+static inline double tile_cost(const uint2 &a, const uint2 &b)
+{
+    if (a.x == b.x) return 0.0;   // no row starts here: skipped by the kernel
+    return std::ceil((double)(b.y - a.y + 3u) / 128.0) + 0.25 * std::ceil((double)(b.x - a.x) / 32.0) + 1.0;
+}
+
+// Tiles are row-aligned, so a row of 10 000 entries makes a tile of more than 10 000: with round-robin assignment the
+// most loaded warp of a power-law matrix (C4) carries ~1.5x the mean and the whole grid waits for it.  When that
+// happens the matrix is re-cut into smaller tiles and the tiles are dealt to the warps by LPT (largest first, to the
+// least loaded warp).  The schedule is a pure function of ptr[], so results stay reproducible run to run.
+static int balance_tile_map(Work &wk, const CsrView &V, int64_t nnz, TileMapOwner *out)
+{
+    const int nw = wk.sms * kWMinBlocks * kWWarps;
+    std::vector<uint2> t;
+    std::vector<double> cost;
+    double total = 0.0;
+    auto fetch = [&]() -> int {   // tile bounds and costs of the current cut
+        t.resize((size_t)out->ntiles + 1);
+        LSQRB_CUDA(cudaMemcpyAsync(t.data(), out->tiles, sizeof(uint2) * t.size(), cudaMemcpyDeviceToHost, wk.stream));
+        LSQRB_CUDA(cudaStreamSynchronize(wk.stream));
+        cost.resize((size_t)out->ntiles);
+        total = 0.0;
+        for (int i = 0; i < out->ntiles; ++i) total += (cost[(size_t)i] = tile_cost(t[(size_t)i], t[(size_t)i + 1]));
+        return LSQR_B200_OK;
+    };
+    LSQRB_TRY(fetch());
+    {   // round robin: tile i belongs to warp i mod (warps of the grid)
+        const int gw = std::max(1, std::min((out->ntiles + kWWarps - 1) / kWWarps, wk.sms * kWMinBlocks)) * kWWarps;
+        std::vector<double> load((size_t)gw, 0.0);
+        for (int i = 0; i < out->ntiles; ++i) load[(size_t)(i % gw)] += cost[(size_t)i];
+        out->imbalance = total > 0 ? *std::max_element(load.begin(), load.end()) / (total / nw) : 1.0;
+    }
+    if (env_int("LSQR_B200_BALANCE", 1) == 0 || nnz <= (int64_t)nw * 512) return LSQR_B200_OK;   // nothing to deal out
+    if (out->imbalance <= 1.0 + 1e-3 * env_int("LSQR_B200_BALANCE_PERMILLE", 60)) return LSQR_B200_OK;
+
+    // finer tiles pack better (the long rows stay as long as they are)
+    const uint32_t fine = (uint32_t)std::max(512, std::min<int>((int)out->tile / 4, env_int("LSQR_B200_BALANCE_TILE", 2048))) & ~3u;
+    if (fine < out->tile) { LSQRB_TRY(build_tiles(wk, V, nnz, fine, out)); LSQRB_TRY(fetch()); }
+    const int nt = out->ntiles;
+    if (nt <= nw) return LSQR_B200_OK;
+    std::vector<int> ids;
+    ids.reserve((size_t)nt);
+    for (int i = 0; i < nt; ++i) if (cost[(size_t)i] > 0.0) ids.push_back(i);
+    std::stable_sort(ids.begin(), ids.end(), [&](int a, int b) { return cost[(size_t)a] > cost[(size_t)b]; });
+    typedef std::pair<double, int> Slot;   // (load, warp): the least loaded warp first, ties by warp number
+    std::priority_queue<Slot, std::vector<Slot>, std::greater<Slot>> heap;
+    for (int w = 0; w < nw; ++w) heap.push(Slot(0.0, w));
+    std::vector<std::vector<uint32_t>> lists((size_t)nw);
+    for (int id : ids) {
+        Slot sl = heap.top(); heap.pop();
+        lists[(size_t)sl.second].push_back((uint32_t)id);
+        sl.first += cost[(size_t)id];
+        heap.push(sl);
+    }
+    size_t depth = 0;
+    double worst = 0.0;
+    while (!heap.empty()) { worst = std::max(worst, heap.top().first); heap.pop(); }
+    for (auto &l : lists) { std::sort(l.begin(), l.end()); depth = std::max(depth, l.size()); }   // each warp walks its tiles in matrix order
+    std::vector<uint32_t> order(depth * (size_t)nw, kNoTile);
+    for (int w = 0; w < nw; ++w)
+        for (size_t k = 0; k < lists[(size_t)w].size(); ++k) order[k * (size_t)nw + (size_t)w] = lists[(size_t)w][k];
+    out->nslots = (int)order.size();
+    out->imbalance = total > 0 ? worst / (total / nw) : 1.0;
+    LSQRB_CUDA(cudaMalloc(&out->order, sizeof(uint32_t) * std::max<size_t>(order.size(), 1)));
+    LSQRB_CUDA(cudaMemcpyAsync(out->order, order.data(), sizeof(uint32_t) * order.size(), cudaMemcpyHostToDevice, wk.stream));
+    LSQRB_CUDA(cudaStreamSynchronize(wk.stream));
+    return LSQR_B200_OK;
+}
+
 // V: a whole CSR, or one block of a row-blocked transpose (nnz = its number of stored entries)
 static int build_tile_map(Work &wk, const CsrView &V, int64_t nnz, int kind, TileMapOwner *out)
 {
     out->kind = kind;
-    out->tile = kind == 3 ? warp_tile_size(wk, nnz) : (uint32_t)kTile;
-    const int64_t nt = std::max<int64_t>(1, (nnz + out->tile - 1) / out->tile);
-    out->ntiles = (int)nt;
-    LSQRB_CUDA(cudaMalloc(&out->tiles, sizeof(uint2) * (size_t)(nt + 1)));
-    build_tiles_kernel<<<(int)((nt + 1 + 255) / 256), 256, 0, wk.stream>>>(V.ptr, V.nrows, (int)nt, out->tile, out->tiles);
-    LSQRB_CUDA(cudaGetLastError());
+    LSQRB_TRY(build_tiles(wk, V, nnz, kind == 3 ? warp_tile_size(wk, nnz) : (uint32_t)kTile, out));
+    if (kind == 3) LSQRB_TRY(balance_tile_map(wk, V, nnz, out));
     return LSQR_B200_OK;
 }
 
@@ -304,14 +396,15 @@ static int launch_stream(Work &wk, const CsrView &V, const TileMapOwner &map, co
 {
     StreamArgs a;
     a.A = V;
-    a.map = TileMap{map.tiles, map.ntiles};
+    a.map = TileMap{map.tiles, map.ntiles, map.order, map.nslots};
     a.x = x; a.out = out; a.st = wk.st; a.aux = aux;
     a.ux = ex.ux; a.uw = ex.uw; a.use = ex.use;
     a.ring = wk.ring_d;
     a.out_aligned16 = ((uintptr_t)out & 15u) == 0;
     a.check_done = ex.check_done;
     if (map.kind == 3) {
-        const int grid = std::max(1, std::min((map.ntiles + kWWarps - 1) / kWWarps, wk.sms * kWMinBlocks));
+        const int grid = map.order ? wk.sms * kWMinBlocks
+                                   : std::max(1, std::min((map.ntiles + kWWarps - 1) / kWWarps, wk.sms * kWMinBlocks));
         spmv_warp_kernel<EPI><<<grid, kWThreads, 0, wk.stream>>>(a);
     } else {
         int occ = 1;
@@ -519,9 +612,9 @@ static void ez_free(lsqr_b200_ez *me)
     if (me->comm) { NcclApi *a = nccl_api(); if (a) a->CommDestroy(me->comm); }
     csr_free(&me->A);
     csr_free(&me->AT);
-    for (auto &mp : me->mapA) if (mp.tiles) cudaFree(mp.tiles);
-    for (auto &mp : me->mapAT) if (mp.tiles) cudaFree(mp.tiles);
-    for (auto &mp : me->mapATc) if (mp.tiles) cudaFree(mp.tiles);
+    for (auto &mp : me->mapA) tile_map_free(mp);
+    for (auto &mp : me->mapAT) tile_map_free(mp);
+    for (auto &mp : me->mapATc) tile_map_free(mp);
     for (auto e : me->ev_chunk) if (e) cudaEventDestroy(e);
     if (me->ev_comm) cudaEventDestroy(me->ev_comm);
     if (me->comm_stream) cudaStreamDestroy(me->comm_stream);
@@ -717,9 +810,12 @@ static int ez_initialize_impl(lsqr_b200_ez *me, int64_t nnz, const double *a, co
     }
     if (env_int("LSQR_B200_VERBOSE", 0))
         fprintf(stderr, "[lsqr_b200] m=%d n=%d nnz=%lld variant=%d A blocks=%lld (block_cols=%lld) A' blocks=%lld (block_rows=%lld) "
-                        "warp tile A=%u A'=%u\n", me->m, me->n, (long long)me->nnz, variant,
+                        "warp tile A=%u%s (imbalance %.3f) A'=%u%s (imbalance %.3f)\n", me->m, me->n, (long long)me->nnz, variant,
                 (long long)me->A.nblocks, (long long)me->A.block_rows, (long long)me->AT.nblocks, (long long)me->AT.block_rows,
-                me->mapA.empty() ? 0u : me->mapA[0].tile, me->mapAT.empty() ? 0u : me->mapAT[0].tile);
+                me->mapA.empty() ? 0u : me->mapA[0].tile, !me->mapA.empty() && me->mapA[0].order ? " LPT" : "",
+                me->mapA.empty() ? 1.0 : me->mapA[0].imbalance,
+                me->mapAT.empty() ? 0u : me->mapAT[0].tile, !me->mapAT.empty() && me->mapAT[0].order ? " LPT" : "",
+                me->mapAT.empty() ? 1.0 : me->mapAT[0].imbalance);
 
     const size_t mm = (size_t)std::max<int32_t>(me->m, 1), nn = (size_t)std::max<int32_t>(me->n, 1);
     LSQRB_CUDA(cudaMalloc(&me->u, sizeof(double) * mm));
@@ -810,6 +906,20 @@ int lsqr_b200_ez_blocks(const lsqr_b200_ez *me, int32_t which, int64_t *nblocks,
     const Csr &M = which == 0 ? me->A : me->AT;
     if (nblocks) *nblocks = M.nblocks;
     if (block_size) *block_size = M.block_rows;
+    return LSQR_B200_OK;
+}
+
+int lsqr_b200_ez_schedule(const lsqr_b200_ez *me, int32_t which, int64_t block, int64_t *ntiles,
+                          int64_t *tile_entries, int32_t *balanced, double *imbalance)
+{
+    if (!me) return LSQR_B200_ERR_ARG;
+    const std::vector<TileMapOwner> &maps = which ? me->mapAT : me->mapA;
+    if (block < 0 || (size_t)block >= maps.size()) { set_last_error("no such block / no tiled schedule"); return LSQR_B200_ERR_ARG; }
+    const TileMapOwner &mp = maps[(size_t)block];
+    if (ntiles) *ntiles = mp.ntiles;
+    if (tile_entries) *tile_entries = mp.tile;
+    if (balanced) *balanced = mp.order != nullptr;
+    if (imbalance) *imbalance = mp.imbalance;
     return LSQR_B200_OK;
 }
 

@@ -31,7 +31,12 @@ static_assert(kSlotBytes % 16 == 0 && (kCapS * 8) % 16 == 0, "TMA alignment");
 struct TileMap {
     const uint2 *tiles;   // [ntiles+1]  {first row, first stored entry}; tiles[ntiles] = {nrows, nnz}
     int ntiles;
+    // Warp kernel only: balanced schedule for matrices with very uneven rows.  Slot s = k * (warps of the grid) + w is
+    // the k-th tile of warp w (kNoTile = none); nullptr = round robin (tile t belongs to warp t mod warps).
+    const uint32_t *order;
+    int nslots;
 };
+constexpr uint32_t kNoTile = 0xFFFFFFFFu;
 
 // ---------------------------------------------------------------------------------------------
 // PTX wrappers: mbarrier + 1-D bulk TMA

@@ -30,6 +30,13 @@ constexpr int kWWarps = kWThreads / 32;
 #endif
 constexpr int kWMinBlocks = LSQRB_WARP_MINBLOCKS;   // 4: 32 warps per SM, <= 64 registers per thread
 constexpr uint32_t kChunk = 128;             // stored entries per warp step (4 per lane)
+#ifndef LSQRB_WIN_PREFETCH
+#define LSQRB_WIN_PREFETCH 0                 // 1: prefetch the ptr / out lines of the next row window into L2 (measured: no gain)
+#endif
+#ifndef LSQRB_GATHER_AHEAD
+#define LSQRB_GATHER_AHEAD 0                 // 1: gathers issued one chunk ahead of their use (measured 15-25 % SLOWER: the kernel is
+                                             // bound by L1TEX wavefronts, not by gather latency, and the extra registers spill)
+#endif
 constexpr uint32_t kPtrSentinel = 0xFFFFFFFFu;
 
 __device__ __forceinline__ void ldg_stream_s32x4(const int32_t *p, int32_t (&v)[4], uint64_t pol)
@@ -57,6 +64,14 @@ struct RowWindow {
             if (epi.needs_old()) O = a.out[r];
             if (EPI == SEPI_ATPROD_UPD && epi.upd) { W = a.uw[r]; X = a.ux[r]; }
         }
+#if LSQRB_WIN_PREFETCH
+        // the next window is needed a chunk or two from now and its reload sits on the critical path of the head
+        // mask: pull its lines (ptr: one line per 32 rows, out: two) towards the SM now; no registers are held
+        if (r + 32u < r1) {
+            if ((lane & 15) == 0) prefetch_l2(a.A.ptr + r + 32u + (lane ? 16u : 0u));
+            if (epi.needs_old() && (lane & 7) == 0) prefetch_l2(a.out + r + 32u);
+        }
+#endif
     }
 };
 
@@ -98,21 +113,13 @@ struct WarpTileState {
     double carry;          // running sum of the row that is open at the chunk boundary
 };
 
-// Processes the chunk [base, base+128) held in `cur`; `nxt` receives the following chunk, whose loads
-// stay in flight while this one is reduced.
+// Reduces the chunk [base, base+128): `cv` = the lane's 4 stored values, x0..x3 = the gathered vector entries.
 template <int EPI>
-__device__ __forceinline__ void warp_chunk(const StreamArgs &a, RowEpilogue<EPI, true> &epi, double *su, WarpTileState<EPI> &ts,
-                                           const ChunkRegs &cur, ChunkRegs &nxt, uint32_t base, uint32_t r1, uint32_t e0, uint32_t e1,
-                                           int lane, uint64_t pol_stream, uint64_t pol_keep)
+__device__ __forceinline__ void warp_chunk_core(const StreamArgs &a, RowEpilogue<EPI, true> &epi, double *su, WarpTileState<EPI> &ts,
+                                                const double (&cv)[4], double x0, double x1, double x2, double x3,
+                                                uint32_t base, uint32_t r1, uint32_t e1, int lane)
 {
     const uint32_t endp = base + kChunk;
-    // ---- gathers of this chunk, then the stream of the next one
-    const double x0 = ldg_keep_f64(a.x + cur.c[0], pol_keep);
-    const double x1 = ldg_keep_f64(a.x + cur.c[1], pol_keep);
-    const double x2 = ldg_keep_f64(a.x + cur.c[2], pol_keep);
-    const double x3 = ldg_keep_f64(a.x + cur.c[3], pol_keep);
-    load_chunk(a.A, endp, lane, e0, e1, pol_stream, nxt);
-
     // ---- head mask of the chunk: bit i set <=> a row starts at entry base+i
     uint32_t m0 = 0, m1 = 0, m2 = 0, m3 = 0;
     {
@@ -138,13 +145,13 @@ __device__ __forceinline__ void warp_chunk(const StreamArgs &a, RowEpilogue<EPI,
 
     // ---- products; segmented running sums inside the lane (t_k = sum of the lane's entries of the segment
     // that entry k belongs to, up to and including k)
-    double t0 = cur.v[0] * x0;
+    double t0 = cv[0] * x0;
     if (lane == 0 && !(f & 1u)) t0 = ts.carry + t0;        // row that began in an earlier chunk
-    double t1 = cur.v[1] * x1;
+    double t1 = cv[1] * x1;
     if (!(f & 2u)) t1 += t0;
-    double t2 = cur.v[2] * x2;
+    double t2 = cv[2] * x2;
     if (!(f & 4u)) t2 += t1;
-    double t3 = cur.v[3] * x3;
+    double t3 = cv[3] * x3;
     if (!(f & 8u)) t3 += t2;
     // ---- ... and across lanes (Kogge-Stone; lane l takes lane l-d iff no head lies in lanes (l-d, l])
     const uint32_t hb = __ballot_sync(0xffffffffu, f != 0u);
@@ -194,6 +201,110 @@ __device__ __forceinline__ void warp_chunk(const StreamArgs &a, RowEpilogue<EPI,
     }
 }
 
+// Processes the chunk [base, base+128) held in `cur`; `nxt` receives the following chunk, whose loads
+// stay in flight while this one is reduced.  (LSQRB_GATHER_AHEAD = 0: gathers are issued and consumed in the
+// same step.)
+template <int EPI>
+__device__ __forceinline__ void warp_chunk(const StreamArgs &a, RowEpilogue<EPI, true> &epi, double *su, WarpTileState<EPI> &ts,
+                                           const ChunkRegs &cur, ChunkRegs &nxt, uint32_t base, uint32_t r1, uint32_t e0, uint32_t e1,
+                                           int lane, uint64_t pol_stream, uint64_t pol_keep)
+{
+    // ---- gathers of this chunk, then the stream of the next one
+    const double x0 = ldg_keep_f64(a.x + cur.c[0], pol_keep);
+    const double x1 = ldg_keep_f64(a.x + cur.c[1], pol_keep);
+    const double x2 = ldg_keep_f64(a.x + cur.c[2], pol_keep);
+    const double x3 = ldg_keep_f64(a.x + cur.c[3], pol_keep);
+    load_chunk(a.A, base + kChunk, lane, e0, e1, pol_stream, nxt);
+    warp_chunk_core<EPI>(a, epi, su, ts, cur.v, x0, x1, x2, x3, base, r1, e1, lane);
+}
+
+#if LSQRB_GATHER_AHEAD
+// Gather-ahead pipeline: three chunks are in flight per warp.  While chunk c is reduced, the gathers x[idx] of
+// chunk c+1 (issued at the start of the step, from indices that arrived during the previous step), the values of
+// chunk c+1 and the indices of chunk c+2 are outstanding, so a warp never waits for the L2 round trip of a gather
+// it has just issued.  The index registers are reused as soon as the gathers that read them have been issued.
+struct ChunkStage {
+    double v[4];
+    double x[4];
+};
+
+__device__ __forceinline__ void load_chunk_idx(const CsrView &A, uint32_t cb, int lane, uint32_t e1, uint64_t pol_stream, int32_t (&c)[4])
+{
+    const uint32_t q = cb + 4u * (uint32_t)lane;
+    if (q < e1) {
+        ldg_stream_s32x4(A.idx + q, c, pol_stream);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) c[k] = 0;          // a harmless in-bounds gather
+    }
+}
+
+// values outside the tile [e0, e1) become 0 and so add nothing to any row
+__device__ __forceinline__ void load_chunk_val(const CsrView &A, uint32_t cb, int lane, uint32_t e0, uint32_t e1, double (&v)[4])
+{
+    const uint32_t q = cb + 4u * (uint32_t)lane;
+    if (cb >= e0 && cb + kChunk <= e1) {               // steady state: the whole chunk lies inside the tile
+        ldg_stream_f64x4(A.val + q, v);
+        return;
+    }
+    if (q < e1) {
+        ldg_stream_f64x4(A.val + q, v);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (q + k < e0 || q + k >= e1) v[k] = 0.0;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = 0.0;
+    }
+}
+
+// issue the loads of the two following chunks: gathers + values of [nb, nb+128), indices of [nb+128, nb+256)
+__device__ __forceinline__ void stage_issue(const StreamArgs &a, ChunkStage &s, int32_t (&c)[4], uint32_t nb, int lane,
+                                            uint32_t e0, uint32_t e1, uint64_t pol_stream, uint64_t pol_keep)
+{
+    if (nb >= e1) return;                              // (warp-uniform) no following chunk
+    s.x[0] = ldg_keep_f64(a.x + c[0], pol_keep);
+    s.x[1] = ldg_keep_f64(a.x + c[1], pol_keep);
+    s.x[2] = ldg_keep_f64(a.x + c[2], pol_keep);
+    s.x[3] = ldg_keep_f64(a.x + c[3], pol_keep);
+    load_chunk_val(a.A, nb, lane, e0, e1, s.v);
+    load_chunk_idx(a.A, nb + kChunk, lane, e1, pol_stream, c);
+}
+
+template <int EPI>
+__device__ __forceinline__ void warp_tile(const StreamArgs &a, RowEpilogue<EPI, true> &epi, double *su /* 128 doubles, this warp's */,
+                                          uint32_t r0, uint32_t r1, uint32_t e0, uint32_t e1, int lane,
+                                          uint64_t pol_stream, uint64_t pol_keep)
+{
+    const uint32_t a0 = e0 & ~3u;
+    int32_t c[4];
+    ChunkStage sa, sb;
+    load_chunk_idx(a.A, a0, lane, e1, pol_stream, c);
+    load_chunk_val(a.A, a0, lane, e0, e1, sa.v);
+    WarpTileState<EPI> ts;
+    ts.wb = r0;
+    ts.woff = 0;
+    ts.carry = 0.0;
+    ts.win.load(a, epi, r0, r1, lane);
+    sa.x[0] = ldg_keep_f64(a.x + c[0], pol_keep);
+    sa.x[1] = ldg_keep_f64(a.x + c[1], pol_keep);
+    sa.x[2] = ldg_keep_f64(a.x + c[2], pol_keep);
+    sa.x[3] = ldg_keep_f64(a.x + c[3], pol_keep);
+    load_chunk_idx(a.A, a0 + kChunk, lane, e1, pol_stream, c);
+    // two chunks per trip so that the stage registers need no copies; at least one chunk is processed even for a
+    // tile without entries, so that its (empty) rows still get their epilogue
+    for (uint32_t base = a0;;) {
+        stage_issue(a, sb, c, base + kChunk, lane, e0, e1, pol_stream, pol_keep);
+        warp_chunk_core<EPI>(a, epi, su, ts, sa.v, sa.x[0], sa.x[1], sa.x[2], sa.x[3], base, r1, e1, lane);
+        base += kChunk;
+        if (base >= e1) break;
+        stage_issue(a, sa, c, base + kChunk, lane, e0, e1, pol_stream, pol_keep);
+        warp_chunk_core<EPI>(a, epi, su, ts, sb.v, sb.x[0], sb.x[1], sb.x[2], sb.x[3], base, r1, e1, lane);
+        base += kChunk;
+        if (base >= e1) break;
+    }
+}
+#else
 template <int EPI>
 __device__ __forceinline__ void warp_tile(const StreamArgs &a, RowEpilogue<EPI, true> &epi, double *su /* 128 doubles, this warp's */,
                                           uint32_t r0, uint32_t r1, uint32_t e0, uint32_t e1, int lane,
@@ -218,6 +329,8 @@ __device__ __forceinline__ void warp_tile(const StreamArgs &a, RowEpilogue<EPI, 
         if (base >= e1) break;
     }
 }
+
+#endif
 
 template <int EPI>
 __global__ void __launch_bounds__(kWThreads, kWMinBlocks)
@@ -273,7 +386,11 @@ spmv_warp_kernel(StreamArgs a)
         const int lane = tid & 31, wib = tid >> 5;
         const int nw = (int)gridDim.x * kWWarps;
         const uint2 *__restrict__ tiles = a.map.tiles;
-        for (int t = (int)blockIdx.x * kWWarps + wib; t < a.map.ntiles; t += nw) {
+        const uint32_t *__restrict__ order = a.map.order;
+        const int nslots = order ? a.map.nslots : a.map.ntiles;
+        for (int s = (int)blockIdx.x * kWWarps + wib; s < nslots; s += nw) {
+            const uint32_t t = order ? order[s] : (uint32_t)s;
+            if (t == kNoTile) break;                        // this warp's list is exhausted
             const uint2 d0 = tiles[t], d1 = tiles[t + 1];
             if (d0.x == d1.x) continue;                     // no row starts in this tile (inside a long row)
             warp_tile<EPI>(a, epi, s_u[wib], d0.x, d1.x, d0.y, d1.y, lane, pol_stream, pol_keep);
@@ -291,6 +408,7 @@ spmv_warp_kernel(StreamArgs a)
                     step_after_update(*st, total_w, __ldcg(a.ux), a.ring);
                     st->upd_pending = 0;
                 }
+                if (tracing) st->trace[3][st->tr_n & (kTraceSlots - 1)] = globaltimer_ns();
                 if (!st->done) {
                     step_after_atprod(*st, total, mode == MODE_FULL);
                     st->upd_pending = 1;

@@ -237,6 +237,14 @@ class LsqrSolverEz:
         _lib.check(_lib.load().lsqr_b200_ez_blocks(self._h, int(transpose), C.byref(nb), C.byref(bs)))
         return nb.value, bs.value
 
+    def schedule(self, transpose: bool = False, block: int = 0) -> dict:
+        """Work schedule of the SpMV kernel over one block of A (or A'): tiles, entries per tile, whether the
+        balanced (largest-first) schedule for uneven rows is in use, most-loaded-warp / mean load."""
+        nt, te, bal, imb = C.c_int64(), C.c_int64(), C.c_int32(), C.c_double()
+        _lib.check(_lib.load().lsqr_b200_ez_schedule(self._h, int(transpose), int(block), C.byref(nt), C.byref(te),
+                                                     C.byref(bal), C.byref(imb)))
+        return {"ntiles": nt.value, "tile_entries": te.value, "balanced": bool(bal.value), "imbalance": imb.value}
+
     def transpose_blocks(self):
         return self.blocks(True)
 
