@@ -47,6 +47,8 @@ def parse_args():
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--workload", default="auto", choices=["auto", "C2", "C3", "C4", "C5"])
     p.add_argument("--scale", type=float, default=1.0, help="divide m and n by this factor")
+    p.add_argument("--secondary", default="C2", choices=["none", "C2", "C3", "C4"],
+                   help="N = 1 only: a second workload measured the same way and reported under `secondary`")
     p.add_argument("--cpu-scale", type=float, default=0.0, help="scale of the CPU-baseline sample (0 = auto)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-graph", action="store_true")
@@ -56,8 +58,10 @@ def parse_args():
 def pick_workload(args) -> str:
     if args.workload != "auto":
         return args.workload
-    # configs[1] (C2) is the 1 x B200 configuration of BASELINE.json; the multi-GPU target is C5.
-    return "C2" if args.gpus == 1 else "C5"
+    # C5 (100M x 10M, 2e9 entries) is the configuration BASELINE.json's metric and target are quoted on
+    # ("row-partitioned across 1/2/4/8 B200"); it fits one B200 (about 70 GB), so every N runs the SAME problem and
+    # the 1 -> 8 GPU numbers are a strong-scaling series.  At N = 1 configs[1] (C2) rides along as `secondary`.
+    return "C5"
 
 
 def measured_peak():
@@ -203,6 +207,48 @@ def main():
         td.init_process_group("nccl", device_id=dev)
 
     name = pick_workload(args)
+    res = run_workload(name, args, args.steps, world, rank, dev, with_roofline=True)
+
+    # N = 1 only: BASELINE.json's 1 x B200 configuration (configs[1], C2) rides along as a secondary record
+    secondary = None
+    if world == 1 and args.secondary != "none" and args.secondary != name and args.scale == 1.0:
+        sec = run_workload(args.secondary, args, max(args.steps, 20), world, rank, dev, with_roofline=True)
+        secondary = {k: sec[k] for k in ("workload", "value", "iters_per_s", "ms_per_iteration", "frac_of_hbm_roofline",
+                                         "itn_per_step", "istop")}
+        secondary["e2e_value"] = sec["e2e"]["value"]
+        secondary["roofline"] = {k: sec["roofline"][k] for k in ("kernel", "achieved", "frac", "traffic", "avg_launch_ms")}
+
+    if world > 1:
+        import torch.distributed as td
+        td.barrier()
+        td.destroy_process_group()
+    if rank != 0:
+        return
+    line = {
+        "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "iters_per_s": res["iters_per_s"], "itn_per_step": res["itn_per_step"], "ms_per_iteration": res["ms_per_iteration"],
+        "frac_of_hbm_roofline": res["frac_of_hbm_roofline"],
+        "config": res["config"], "e2e": res["e2e"], "gpu_launches": res["gpu_launches"],
+        "roofline": res["roofline"], "clocks": res["clocks"],
+    }
+    if secondary:
+        line["secondary"] = secondary
+    if world == 1 and not args.no_cpu_baseline:
+        cb = run_cpu_reference(name, args.cpu_scale, 3, 1, budget_s=20.0)
+        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "iters_per_s")}
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
+
+
+def run_workload(name, args, steps, world, rank, dev, with_roofline=True):
+    """Builds one workload on the device(s), times `steps` solves (device-resident b/x, then host b/x), profiles
+    one solve per kernel, destroys the solver.  Returns the pieces of the JSON line."""
+    import torch
+    import lsqr_b200
+    from lsqr_b200 import synth, dist as ldist
+    local_rank = dev.index
+
     cfg = synth.scaled(name, args.scale) if args.scale != 1.0 else dict(synth.CONFIGS[name])
     m, n = cfg["m"], cfg["n"]
     row0, row1 = ldist.row_block(m, world, rank)
@@ -279,11 +325,11 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ms, wall, itn, launches, last = timed(b_dev, x_dev, args.steps)
+    ms, wall, itn, launches, last = timed(b_dev, x_dev, steps)
     clocks = sampler.stop() if rank == 0 else {}
     for _ in range(2):
         solver.solve(b_host, cfg["damp"], x=x_host)
-    ms_e2e, wall_e2e, itn_e2e, _, last_e2e = timed(b_host, x_host, args.steps)
+    ms_e2e, wall_e2e, itn_e2e, _, last_e2e = timed(b_host, x_host, steps)
 
     # ---- roofline of the dominant kernel: CUDA-event pairs around every launch inside the real loop
     solver.set_tolerances(profile=True)
@@ -291,6 +337,7 @@ def main():
     kt = solver.kernel_times()
     solver.set_tolerances(profile=False)
     peak, peak_src = measured_peak()
+    nblk_a, nblk_at = solver.blocks(False)[0], solver.blocks(True)[0]
     kb = {   # algorithmic bytes per launch on this rank
         "aprod": 12 * nnz_loc + 4 * (m_loc + 1) + 8 * n + 16 * m_loc,
         "atprod": 12 * nnz_loc + 4 * (n + 1) + 8 * m_loc + 16 * n,
@@ -309,30 +356,26 @@ def main():
         "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
         "algorithmic_bytes_per_launch": kb[dom], "avg_launch_ms": kms[dom],
+        "launch_note": "one product = %d (Aprod) / %d (Atprod) block launches timed as a group between one CUDA-event pair "
+                       "(A column-blocked / A' row-blocked when the gathered vector exceeds the L2 budget)" % (nblk_a, nblk_at),
         "per_kernel": {k: {"ms": kms[k], "GBps": (kb[k] / (kms[k] * 1e-3) / 1e9 if kms[k] > 0 else 0.0),
                            "frac": (kb[k] / (kms[k] * 1e-3) / 1e9 / peak if kms[k] > 0 else 0.0)} for k in kms},
         "loop_frac": (bytes_iter * last.itn / (kt["loop_ms"] * 1e-3) / 1e9) / (peak * world) if kt["loop_ms"] > 0 else None,
     }
 
-    # orderly shutdown on every rank: the engine's communicator first (a collective), then torch's
     solver.destroy()
-    if world > 1:
-        import torch.distributed as td
-        td.barrier()
-        td.destroy_process_group()
-    if rank != 0:
-        return
+    del b_dev, x_dev, b_host, x_host, xt
+    torch.cuda.empty_cache()
     value = bytes_iter * itn / (ms * 1e-3) / 1e9
     e2e_value = bytes_iter * itn_e2e / (ms_e2e * 1e-3) / 1e9
-    line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "iters_per_s": itn / (ms * 1e-3), "itn_per_step": itn / args.steps, "ms_per_iteration": ms / max(itn, 1),
-        "frac_of_hbm_roofline": value / (peak * world),
+    workload = (f"{name}: {cfg['kind']} {m}x{n}, nnz={nnz}, damp={cfg['damp']}, via lsqr_solver_ez "
+                f"(atol=btol=1e-10, conlim=1e8), row-partitioned over {world} GPU(s)")
+    return {
+        "workload": workload, "value": value, "ms_per_step": ms / steps, "iters_per_s": itn / (ms * 1e-3),
+        "itn_per_step": itn / steps, "ms_per_iteration": ms / max(itn, 1), "frac_of_hbm_roofline": value / (peak * world),
+        "istop": last.istop,
         "config": {
-            "workload": f"{name}: {cfg['kind']} {m}x{n}, nnz={nnz}, damp={cfg['damp']}, via lsqr_solver_ez "
-                        f"(atol=btol=1e-10, conlim=1e8), row-partitioned over {world} GPU(s)",
+            "workload": workload,
             "step": "one full solve: b -> x, all LSQR iterations to the reference's stopping rule",
             "b_iter_bytes": bytes_iter, "istop": last.istop,
             "l2_note": "inputs larger than L2: CSR(A)+CSR(A') = %.0f MB per GPU stream through every iteration"
@@ -340,16 +383,10 @@ def main():
             "wall_s": wall, "initialize_s": t_init, "generate_s": t_gen,
         },
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * m_loc, "d2h_bytes_per_step": 8 * n,
-                "iters_per_s": itn_e2e / (ms_e2e * 1e-3), "ms_per_step": ms_e2e / args.steps, "wall_s": wall_e2e,
+                "iters_per_s": itn_e2e / (ms_e2e * 1e-3), "ms_per_step": ms_e2e / steps, "wall_s": wall_e2e,
                 "api": "lsqr_b200_ez_solve with pinned host b and x (C ABI, via LsqrSolverEz.solve)"},
-        "gpu_launches": launches,
-        "roofline": roofline,
-        "clocks": clocks,
+        "gpu_launches": launches, "roofline": roofline, "clocks": clocks,
     }
-    if world == 1 and not args.no_cpu_baseline:
-        cb = run_cpu_reference(name, args.cpu_scale, 3, 1, budget_s=20.0)
-        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "iters_per_s")}
-    print(json.dumps(line), file=_JSON_OUT, flush=True)
 
 
 if __name__ == "__main__":

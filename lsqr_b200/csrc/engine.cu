@@ -253,6 +253,8 @@ struct TileMapOwner {
     // kind 3, very uneven rows only: balanced tile schedule (see TileMap::order); the grid is then the full persistent grid
     uint32_t *order = nullptr;
     int nslots = 0;
+    int ctas = 0;            // kind 3: persistent grid this map was cut for (0 = sms * CTAs per SM); the chunk launches
+                             // that overlap an all-reduce leave a few SMs to the collective's own kernels
     double imbalance = 1.0;  // most loaded warp / mean load under the schedule in use (diagnostic)
 };
 
@@ -265,11 +267,11 @@ static void tile_map_free(TileMapOwner &mp)
 
 // Variant 3 sizes its tiles so that every warp of the persistent grid gets the same number of them
 // (k tiles of ~8K entries or less each): a small matrix is cut into exactly one tile per warp.
-static uint32_t warp_tile_size(const Work &wk, int64_t nnz)
+static uint32_t warp_tile_size(int ctas, int64_t nnz)
 {
     const int forced = env_int("LSQR_B200_WARP_TILE", 0);
     if (forced >= 128) return (uint32_t)forced;
-    const int64_t nwarps = (int64_t)wk.sms * kWMinBlocks * kWWarps;
+    const int64_t nwarps = (int64_t)ctas * kWWarps;
     const int64_t k = std::max<int64_t>(1, (nnz + nwarps * 8192 - 1) / (nwarps * 8192));
     const int64_t t = (nnz + nwarps * k - 1) / (nwarps * k);
     return (uint32_t)std::max<int64_t>(512, (t + 3) & ~(int64_t)3);
@@ -300,7 +302,7 @@ static inline double tile_cost(const uint2 &a, const uint2 &b)
 // least loaded warp).  The schedule is a pure function of ptr[], so results stay reproducible run to run.
 static int balance_tile_map(Work &wk, const CsrView &V, int64_t nnz, TileMapOwner *out)
 {
-    const int nw = wk.sms * kWMinBlocks * kWWarps;
+    const int nw = out->ctas * kWWarps;
     std::vector<uint2> t;
     std::vector<double> cost;
     double total = 0.0;
@@ -315,7 +317,7 @@ static int balance_tile_map(Work &wk, const CsrView &V, int64_t nnz, TileMapOwne
     };
     LSQRB_TRY(fetch());
     {   // round robin: tile i belongs to warp i mod (warps of the grid)
-        const int gw = std::max(1, std::min((out->ntiles + kWWarps - 1) / kWWarps, wk.sms * kWMinBlocks)) * kWWarps;
+        const int gw = std::max(1, std::min((out->ntiles + kWWarps - 1) / kWWarps, out->ctas)) * kWWarps;
         std::vector<double> load((size_t)gw, 0.0);
         for (int i = 0; i < out->ntiles; ++i) load[(size_t)(i % gw)] += cost[(size_t)i];
         out->imbalance = total > 0 ? *std::max_element(load.begin(), load.end()) / (total / nw) : 1.0;
@@ -358,10 +360,11 @@ static int balance_tile_map(Work &wk, const CsrView &V, int64_t nnz, TileMapOwne
 }
 
 // V: a whole CSR, or one block of a row-blocked transpose (nnz = its number of stored entries)
-static int build_tile_map(Work &wk, const CsrView &V, int64_t nnz, int kind, TileMapOwner *out)
+static int build_tile_map(Work &wk, const CsrView &V, int64_t nnz, int kind, TileMapOwner *out, int reserve_sms = 0)
 {
     out->kind = kind;
-    LSQRB_TRY(build_tiles(wk, V, nnz, kind == 3 ? warp_tile_size(wk, nnz) : (uint32_t)kTile, out));
+    out->ctas = std::max(1, wk.sms - reserve_sms) * kWMinBlocks;
+    LSQRB_TRY(build_tiles(wk, V, nnz, kind == 3 ? warp_tile_size(out->ctas, nnz) : (uint32_t)kTile, out));
     if (kind == 3) LSQRB_TRY(balance_tile_map(wk, V, nnz, out));
     return LSQR_B200_OK;
 }
@@ -403,8 +406,8 @@ static int launch_stream(Work &wk, const CsrView &V, const TileMapOwner &map, co
     a.out_aligned16 = ((uintptr_t)out & 15u) == 0;
     a.check_done = ex.check_done;
     if (map.kind == 3) {
-        const int grid = map.order ? wk.sms * kWMinBlocks
-                                   : std::max(1, std::min((map.ntiles + kWWarps - 1) / kWWarps, wk.sms * kWMinBlocks));
+        const int ctas = map.ctas > 0 ? map.ctas : wk.sms * kWMinBlocks;
+        const int grid = map.order ? ctas : std::max(1, std::min((map.ntiles + kWWarps - 1) / kWWarps, ctas));
         spmv_warp_kernel<EPI><<<grid, kWThreads, 0, wk.stream>>>(a);
     } else {
         int occ = 1;
@@ -781,8 +784,11 @@ static int ez_initialize_impl(lsqr_b200_ez *me, int64_t nnz, const double *a, co
     }
     if (me->a_blocked) LSQRB_CUDA(cudaMalloc(&me->gu, sizeof(double) * (size_t)std::max<int32_t>(me->m, 1)));
     if (me->opt.world_size > 1 && me->stream) {
-        // column chunks for the pipelined all-reduce (only worth it when a chunk is a sizeable message)
-        int k = env_int("LSQR_B200_COMM_CHUNKS", me->n >= (1 << 21) ? 4 : 1);
+        // Column chunks for the pipelined all-reduce.  Off by default: measured on 8 x B200 (C5, n = 1e7, 80 MB per
+        // all-reduce) 1 / 4 / 8 chunks give 3.05 / 3.14 / 3.26 ms per iteration -- the persistent SpMV grids hold every
+        // SM's registers, so NCCL's CTAs only start when a launch drains and the smaller launches pay more in tails
+        // than the overlap returns (profiles/r01/run2/n8_allreduce_pipelining_ab.txt).
+        int k = env_int("LSQR_B200_COMM_CHUNKS", 1);
         k = std::max(1, std::min(k, 8));
         me->comm_chunks = k;
         if (k > 1) {
@@ -799,11 +805,17 @@ static int ez_initialize_impl(lsqr_b200_ez *me, int64_t nnz, const double *a, co
                 CsrView V = view_of_block(me->AT, bl);
                 V.ptr += me->cc[(size_t)c];
                 V.nrows = me->cc[(size_t)c + 1] - me->cc[(size_t)c];
+                // every range but the first runs next to the all-reduce of the previous one: leave NCCL some SMs
                 LSQRB_TRY(build_tile_map(wk, V, (int64_t)off[(size_t)c + 1] - (int64_t)off[(size_t)c], variant == 2 ? 2 : 3,
-                                         &me->mapATc[(size_t)c]));
+                                         &me->mapATc[(size_t)c], c > 0 ? env_int("LSQR_B200_COMM_RESERVE_SMS", 0) : 0));
             }
             LSQRB_CUDA(cudaStreamSynchronize(wk.stream));
-            LSQRB_CUDA(cudaStreamCreateWithFlags(&me->comm_stream, cudaStreamNonBlocking));
+            // highest priority: the SpMV grids are persistent and fill every SM, so the collective's CTAs can only
+            // start on resources freed by a finishing SpMV launch -- they must win those against the next launch
+            int prio_lo = 0, prio_hi = 0;
+            LSQRB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+            LSQRB_CUDA(cudaStreamCreateWithPriority(&me->comm_stream, cudaStreamNonBlocking,
+                                                    env_int("LSQR_B200_COMM_PRIORITY", 1) ? prio_hi : prio_lo));
             for (int c = 0; c < k; ++c) LSQRB_CUDA(cudaEventCreateWithFlags(&me->ev_chunk[c], cudaEventDisableTiming));
             LSQRB_CUDA(cudaEventCreateWithFlags(&me->ev_comm, cudaEventDisableTiming));
         }
