@@ -169,6 +169,11 @@ __device__ __forceinline__ void ldg_stream_s32x8(const int32_t *p, int32_t (&v)[
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                  : "l"(p));
 }
+// Bulk L2 prefetch (sm_90+): pulls `bytes` (multiple of 16, 16-byte aligned) from HBM into L2 without holding registers.
+__device__ __forceinline__ void prefetch_l2_bulk(const void *p, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(p), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void prefetch_l2(const void *p)
 {
     asm volatile("prefetch.global.L2 [%0];" :: "l"(p));

@@ -581,6 +581,7 @@ struct lsqr_b200_ez {
     cudaStream_t comm_stream = nullptr;
     cudaEvent_t ev_chunk[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_comm = nullptr;
+    bool fuse_last = false;            // column-blocked A, tiled kernels: the last block's launch finishes the Aprod step
     bool a_blocked = false;            // A is column-blocked (v does not fit in L2): Aprod = one launch per block into gu
     double *gu = nullptr;              // [m] A v of the column-blocked Aprod
     std::vector<int64_t> at_off;       // first stored entry of every block of A' (nblocks + 1 values)
@@ -751,6 +752,7 @@ static int ez_initialize_impl(lsqr_b200_ez *me, int64_t nnz, const double *a, co
     me->stream = variant != 1;
     me->blocked = me->AT.nblocks > 1;
     me->a_blocked = me->A.nblocks > 1;
+    me->fuse_last = me->a_blocked && me->stream && env_int("LSQR_B200_FUSE_LAST_BLOCK", 1) != 0;
     me->deferred = me->stream && !me->blocked && !me->a_blocked && me->opt.world_size == 1 && env_int("LSQR_B200_DEFERRED_UPDATE", 0) != 0;
     me->overlap_update = !me->deferred && !me->blocked && !me->a_blocked && me->opt.world_size == 1 && env_int("LSQR_B200_OVERLAP_UPDATE", 1) != 0;
     if (me->overlap_update) {
@@ -1052,10 +1054,18 @@ static int do_aprod_fused(lsqr_b200_ez *me, double *aux)
     Work &wk = me->wk;
     StreamExtra ex;
     ex.check_done = 1;
+    // tiled kernels: the LAST block's launch finishes the step itself (u' = ca_mat*(gu + s) + ca_vec*u, sum u'^2), which
+    // saves one write and one read of gu and a pass over u
+    const bool fuse_last = me->fuse_last;
     for (int64_t b = 0; b < me->A.nblocks; ++b) {
         const CsrView V = view_of_block(me->A, b);
         if (b == 0) LSQRB_TRY(me->stream ? launch_stream<SEPI_STORE>(wk, V, me->mapA[0], me->v, me->gu, nullptr, ex)
                                          : launch_spmv<EPI_STORE>(wk, V, me->lanes_a, me->v, me->gu, nullptr, 1));
+        else if (fuse_last && b == me->A.nblocks - 1) {
+            StreamExtra fx;
+            fx.uw = me->gu;
+            return launch_stream<SEPI_APROD_ACC>(wk, V, me->mapA[(size_t)b], me->v, me->u, aux, fx);
+        }
         else        LSQRB_TRY(me->stream ? launch_stream<SEPI_ACC>(wk, V, me->mapA[(size_t)b], me->v, me->gu, nullptr, ex)
                                          : launch_spmv<EPI_ACC>(wk, V, me->lanes_a, me->v, me->gu, nullptr, 1));
     }
@@ -1269,7 +1279,7 @@ static int ez_solve_fused(lsqr_b200_ez *me, const double *b, double damp, double
     auto enqueue_batch = [&]() -> int {
         if (use_graph) {
             LSQRB_CUDA(cudaGraphLaunch(me->graph_exec, wk.stream));
-            wk.launches += (int64_t)B * (me->deferred ? 2 : (me->blocked ? 2 + me->AT.nblocks : 2) + (me->a_blocked ? 1 + me->A.nblocks : 1));
+            wk.launches += (int64_t)B * (me->deferred ? 2 : (me->blocked ? 2 + me->AT.nblocks : 2) + (me->a_blocked ? (me->fuse_last ? 0 : 1) + me->A.nblocks : 1));
         } else {
             for (int i = 0; i < B; ++i) LSQRB_TRY(enqueue_iteration(me, wantse));
             LSQRB_TRY(join_side(me));

@@ -117,9 +117,12 @@ enum StreamEpilogue {
     SEPI_INIT_ATPROD = 2,  // v  = ct_mat*s            ; sum v^2  ; step_init_alpha
     SEPI_ACC = 3,          // out += s
     SEPI_STORE = 4,        // out  = s
-    SEPI_ATPROD_UPD = 5    // SEPI_ATPROD fused with the DEFERRED x/w update of the previous iteration:
+    SEPI_ATPROD_UPD = 5,   // SEPI_ATPROD fused with the DEFERRED x/w update of the previous iteration:
                            //   x += t1 w ; w' = v/alpha + t2 w ; sum w'^2   (v = old v, read anyway)
+    SEPI_APROD_ACC = 6     // last block of a column-blocked A: u' = ca_mat*(gu + s) + ca_vec*u ; sum u'^2 ; step_after_aprod
+                           //   (gu = the partial A v of the earlier blocks, passed in uw)
 };
+constexpr bool sepi_is_aprod(int epi) { return epi == SEPI_APROD || epi == SEPI_APROD_ACC; }
 
 struct StreamArgs {
     CsrView A;
@@ -148,7 +151,7 @@ struct RowEpilogue {
     __device__ __forceinline__ void load(const DevState *st)
     {
         if (!LAZY) {
-            if (EPI == SEPI_APROD) { cm = st->ca_mat; cv = st->ca_vec; }
+            if (sepi_is_aprod(EPI)) { cm = st->ca_mat; cv = st->ca_vec; }
             if (EPI == SEPI_ATPROD || EPI == SEPI_INIT_ATPROD || EPI == SEPI_ATPROD_UPD) { cm = st->ct_mat; cv = st->ct_vec; }
         }
         if (EPI == SEPI_ATPROD_UPD) { upd = st->upd_pending != 0; wantse = st->wantse != 0; }
@@ -156,19 +159,19 @@ struct RowEpilogue {
     __device__ __forceinline__ double coef_mat(const DevState *st) const
     {
         if (!LAZY) return cm;
-        return EPI == SEPI_APROD ? __ldg(&st->ca_mat) : __ldg(&st->ct_mat);
+        return sepi_is_aprod(EPI) ? __ldg(&st->ca_mat) : __ldg(&st->ct_mat);
     }
     __device__ __forceinline__ double coef_vec(const DevState *st) const
     {
         if (!LAZY) return cv;
-        return EPI == SEPI_APROD ? __ldg(&st->ca_vec) : __ldg(&st->ct_vec);
+        return sepi_is_aprod(EPI) ? __ldg(&st->ca_vec) : __ldg(&st->ct_vec);
     }
     __device__ __forceinline__ void load_update_coefficients(const DevState *st)
     {
         t1 = st->t1; t2 = st->t2; t3 = st->t3; ia = st->inv_alpha;
     }
     // `old` = out[row] fetched before the row sum (hides the DRAM latency behind the reduction)
-    __device__ __forceinline__ bool needs_old() const { return EPI == SEPI_APROD || EPI == SEPI_ATPROD || EPI == SEPI_ACC || EPI == SEPI_ATPROD_UPD; }
+    __device__ __forceinline__ bool needs_old() const { return sepi_is_aprod(EPI) || EPI == SEPI_ATPROD || EPI == SEPI_ACC || EPI == SEPI_ATPROD_UPD; }
     // wo / xo: w[row], x[row] of the deferred update when the caller prefetched them (have_wx), else read here
     __device__ __forceinline__ void apply(const StreamArgs &a, int64_t row, double s, double old,
                                           bool have_wx = false, double wo = 0.0, double xo = 0.0)
@@ -176,6 +179,7 @@ struct RowEpilogue {
         if (EPI == SEPI_ACC) { a.out[row] = old + s; return; }
         if (EPI == SEPI_STORE) { a.out[row] = s; return; }
         if (EPI == SEPI_INIT_ATPROD) { const double r = coef_mat(a.st) * s; a.out[row] = r; sq += r * r; return; }
+        if (EPI == SEPI_APROD_ACC) s += have_wx ? wo : a.uw[row];   // + the partial sum of the earlier column blocks
         const double r = coef_mat(a.st) * s + coef_vec(a.st) * old;
         a.out[row] = r;
         sq += r * r;
@@ -227,7 +231,7 @@ template <int EPI>
 __global__ void __launch_bounds__(kStreamThreads)
 spmv_stream_kernel(StreamArgs a)
 {
-    constexpr bool kFused = (EPI == SEPI_APROD || EPI == SEPI_ATPROD || EPI == SEPI_INIT_ATPROD || EPI == SEPI_ATPROD_UPD);
+    constexpr bool kFused = (sepi_is_aprod(EPI) || EPI == SEPI_ATPROD || EPI == SEPI_INIT_ATPROD || EPI == SEPI_ATPROD_UPD);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)kStages * kSlotBytes);
     auto slot_val = [&](int s) { return reinterpret_cast<double *>(smem_raw + (size_t)s * kSlotBytes); };
@@ -239,7 +243,7 @@ spmv_stream_kernel(StreamArgs a)
     int mode = MODE_FULL;
     if (kFused) {
         if (st->done) return;
-        if (EPI == SEPI_APROD && st->istop != 0) return;   // stop already decided: only the deferred update is left
+        if (sepi_is_aprod(EPI) && st->istop != 0) return;   // stop already decided: only the deferred update is left
         if (EPI == SEPI_ATPROD && st->beta == 0.0) {
             // beta = 0: the reference skips the A' half and keeps alpha (src/lsqr.f90:691-699)
             if (blockIdx.x == 0 && threadIdx.x == 0) step_after_atprod(*st, 0.0, false);
@@ -431,7 +435,7 @@ spmv_stream_kernel(StreamArgs a)
                 }
             }
         } else if (finish_reduction<kStreamThreads>(st, 0, epi.sq, s_red, &total)) {
-            if (EPI == SEPI_APROD) {
+            if (sepi_is_aprod(EPI)) {
                 if (a.aux) *a.aux = total; else step_after_aprod(*st, total);
             }
             else if (EPI == SEPI_ATPROD) step_after_atprod(*st, total, true);

@@ -30,6 +30,9 @@ constexpr int kWWarps = kWThreads / 32;
 #endif
 constexpr int kWMinBlocks = LSQRB_WARP_MINBLOCKS;   // 4: 32 warps per SM, <= 64 registers per thread
 constexpr uint32_t kChunk = 128;             // stored entries per warp step (4 per lane)
+#ifndef LSQRB_L2_PREFETCH_CHUNKS
+#define LSQRB_L2_PREFETCH_CHUNKS 0           // D > 0: one lane bulk-prefetches val/idx of the chunk D steps past the register
+#endif                                       // double buffer into L2 (more bytes in flight towards HBM at no register cost)
 #ifndef LSQRB_WIN_PREFETCH
 #define LSQRB_WIN_PREFETCH 0                 // 1: prefetch the ptr / out lines of the next row window into L2 (measured: no gain)
 #endif
@@ -58,11 +61,13 @@ struct RowWindow {
         P = PE = kPtrSentinel;
         O = 0.0;
         if (EPI == SEPI_ATPROD_UPD) W = X = 0.0;
+        if (EPI == SEPI_APROD_ACC) W = 0.0;
         if (r < r1) {
             P = a.A.ptr[r];
             PE = a.A.ptr[r + 1];
             if (epi.needs_old()) O = a.out[r];
             if (EPI == SEPI_ATPROD_UPD && epi.upd) { W = a.uw[r]; X = a.ux[r]; }
+            if (EPI == SEPI_APROD_ACC) W = a.uw[r];
         }
 #if LSQRB_WIN_PREFETCH
         // the next window is needed a chunk or two from now and its reload sits on the critical path of the head
@@ -104,6 +109,17 @@ __device__ __forceinline__ void load_chunk(const CsrView &A, uint32_t cb, int la
 #pragma unroll
         for (int k = 0; k < 4; ++k) { r.v[k] = 0.0; r.c[k] = 0; }
     }
+}
+
+// L2 prefetch of the chunk that starts at entry cb (whole chunks inside the tile only)
+__device__ __forceinline__ void prefetch_chunk(const CsrView &A, uint32_t cb, uint32_t e1, int lane)
+{
+#if LSQRB_L2_PREFETCH_CHUNKS > 0
+    if (lane == 0 && cb + kChunk <= e1) {
+        prefetch_l2_bulk(A.val + cb, kChunk * 8u);
+        prefetch_l2_bulk(A.idx + cb, kChunk * 4u);
+    }
+#endif
 }
 
 template <int EPI>
@@ -181,6 +197,7 @@ __device__ __forceinline__ void warp_chunk_core(const StreamArgs &a, RowEpilogue
         if (ends) {
             const double s = (ts.win.PE != ts.win.P) ? su[ts.win.PE - 1u - base] : 0.0;
             if (EPI == SEPI_ATPROD_UPD) epi.apply(a, (int64_t)ts.wb + lane, s, ts.win.O, true, ts.win.W, ts.win.X);
+            else if (EPI == SEPI_APROD_ACC) epi.apply(a, (int64_t)ts.wb + lane, s, ts.win.O, true, ts.win.W);
             else epi.apply(a, (int64_t)ts.wb + lane, s, ts.win.O);
         }
         ts.woff += (uint32_t)__popc(__ballot_sync(0xffffffffu, ends));
@@ -215,6 +232,7 @@ __device__ __forceinline__ void warp_chunk(const StreamArgs &a, RowEpilogue<EPI,
     const double x2 = ldg_keep_f64(a.x + cur.c[2], pol_keep);
     const double x3 = ldg_keep_f64(a.x + cur.c[3], pol_keep);
     load_chunk(a.A, base + kChunk, lane, e0, e1, pol_stream, nxt);
+    prefetch_chunk(a.A, base + (1u + LSQRB_L2_PREFETCH_CHUNKS) * kChunk, e1, lane);
     warp_chunk_core<EPI>(a, epi, su, ts, cur.v, x0, x1, x2, x3, base, r1, e1, lane);
 }
 
@@ -318,6 +336,8 @@ __device__ __forceinline__ void warp_tile(const StreamArgs &a, RowEpilogue<EPI, 
     ts.win.load(a, epi, r0, r1, lane);
     ChunkRegs ra, rb;
     load_chunk(a.A, a0, lane, e0, e1, pol_stream, ra);
+#pragma unroll
+    for (uint32_t d = 1; d <= LSQRB_L2_PREFETCH_CHUNKS; ++d) prefetch_chunk(a.A, a0 + d * kChunk, e1, lane);
     // two chunks per trip so that the register double buffer needs no copies; at least one chunk is processed
     // even for a tile without entries, so that its (empty) rows still get their epilogue
     for (uint32_t base = a0;;) {
@@ -336,7 +356,7 @@ template <int EPI>
 __global__ void __launch_bounds__(kWThreads, kWMinBlocks)
 spmv_warp_kernel(StreamArgs a)
 {
-    constexpr bool kFused = (EPI == SEPI_APROD || EPI == SEPI_ATPROD || EPI == SEPI_INIT_ATPROD || EPI == SEPI_ATPROD_UPD);
+    constexpr bool kFused = (sepi_is_aprod(EPI) || EPI == SEPI_ATPROD || EPI == SEPI_INIT_ATPROD || EPI == SEPI_ATPROD_UPD);
     __shared__ double s_red[kWWarps];
     __shared__ __align__(16) double s_u[kWWarps][kChunk];
 
@@ -347,7 +367,7 @@ spmv_warp_kernel(StreamArgs a)
     bool tracing = false;
     if (kFused) {
         if (st->done) return;
-        if (EPI == SEPI_APROD && st->istop != 0) return;   // stop already decided: only the deferred update is left
+        if (sepi_is_aprod(EPI) && st->istop != 0) return;   // stop already decided: only the deferred update is left
         if (EPI == SEPI_ATPROD && st->beta == 0.0) {
             // beta = 0: the reference skips the A' half and keeps alpha (src/lsqr.f90:691-699)
             if (blockIdx.x == 0 && threadIdx.x == 0) step_after_atprod(*st, 0.0, false);
@@ -417,7 +437,7 @@ spmv_warp_kernel(StreamArgs a)
             }
         } else if (finish_reduction<kWThreads>(st, 0, epi.sq, s_red, &total)) {
             if (tracing) st->trace[1][st->tr_n & (kTraceSlots - 1)] = globaltimer_ns();
-            if (EPI == SEPI_APROD) {
+            if (sepi_is_aprod(EPI)) {
                 if (a.aux) *a.aux = total; else step_after_aprod(*st, total);
             }
             else if (EPI == SEPI_ATPROD) step_after_atprod(*st, total, true);
