@@ -231,7 +231,7 @@ def main():
         "iters_per_s": res["iters_per_s"], "itn_per_step": res["itn_per_step"], "ms_per_iteration": res["ms_per_iteration"],
         "frac_of_hbm_roofline": res["frac_of_hbm_roofline"],
         "config": res["config"], "e2e": res["e2e"], "gpu_launches": res["gpu_launches"],
-        "roofline": res["roofline"], "clocks": res["clocks"],
+        "roofline": res["roofline"], "clocks": res["clocks"], "check": res["check"],
     }
     if secondary:
         line["secondary"] = secondary
@@ -331,6 +331,24 @@ def run_workload(name, args, steps, world, rank, dev, with_roofline=True):
         solver.solve(b_host, cfg["damp"], x=x_host)
     ms_e2e, wall_e2e, itn_e2e, _, last_e2e = timed(b_host, x_host, steps)
 
+    # ---- self-check (outside the timed regions): the residual of the returned x, recomputed with the engine's own
+    # Aprod from the device copy of x, must equal the rnorm the recurrence reported (the reference's xcheck idea,
+    # src/lsqr.f90:1073-1101); host and device runs must agree on x
+    ax = torch.zeros(m_loc, dtype=torch.float64, device=dev)
+    solver.aprod(1, m_loc, n, x_dev, ax)
+    rr = torch.sum((b_dev - ax) ** 2)
+    if world > 1:
+        import torch.distributed as td
+        td.all_reduce(rr)
+    rnorm_true = float(torch.sqrt(rr).item())
+    dx = float((x_host.to(dev) - x_dev).abs().max().item())
+    check = {"rnorm_reported": last.rnorm, "rnorm_recomputed": rnorm_true,
+             "rel_diff": abs(rnorm_true - last.rnorm) / max(last.rnorm, 1e-300), "max_abs_dx_host_vs_device_run": dx}
+    check["ok"] = bool(check["rel_diff"] <= 1e-8 and dx == 0.0 and last.istop in (1, 2, 3) and last_e2e.itn == last.itn)
+    del ax
+    if not check["ok"]:
+        raise AssertionError(f"bench self-check failed: {check}")
+
     # ---- roofline of the dominant kernel: CUDA-event pairs around every launch inside the real loop
     solver.set_tolerances(profile=True)
     solver.solve(b_dev, cfg["damp"], x=x_dev)
@@ -385,7 +403,7 @@ def run_workload(name, args, steps, world, rank, dev, with_roofline=True):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * m_loc, "d2h_bytes_per_step": 8 * n,
                 "iters_per_s": itn_e2e / (ms_e2e * 1e-3), "ms_per_step": ms_e2e / steps, "wall_s": wall_e2e,
                 "api": "lsqr_b200_ez_solve with pinned host b and x (C ABI, via LsqrSolverEz.solve)"},
-        "gpu_launches": launches, "roofline": roofline, "clocks": clocks,
+        "gpu_launches": launches, "roofline": roofline, "clocks": clocks, "check": check,
     }
 
 

@@ -4,7 +4,7 @@ N=${1:-2}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=index,name --format=csv,noheader | head -8
 if [ "$N" == "2" ]; then
-  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29633 tests/mgpu_worker.py 2>&1 | grep -E "MGPU_OK|Error|error|assert" | head
+  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29633 tests/mgpu_worker.py 2>&1 | grep -E "MGPU_OK|Error|error|assert" | head -20
 fi
 for chunks in ${CHUNKS:-4}; do
 LSQR_B200_COMM_CHUNKS=$chunks LSQR_B200_VERBOSE=1 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29701 \

@@ -25,9 +25,17 @@ def main():
     from lsqr_b200 import dist, synth, synth_device
     from oracle import oracle as O      # the checker
 
-    # (workload, scale, tolerance, se wanted, column chunks of the pipelined all-reduce)
-    for name, scale, tol, want_se, chunks in (("C2", 20, 1e-10, False, 1), ("C3", 100, 1e-8, True, 3), ("C4", 200, 1e-10, False, 4)):
+        # (workload, scale, tolerance, se wanted, column chunks of the pipelined all-reduce, forced blocked layouts)
+    for name, scale, tol, want_se, chunks, blocked in (("C2", 20, 1e-10, False, 1, False), ("C3", 100, 1e-8, True, 3, False),
+                                                       ("C4", 200, 1e-10, False, 4, False), ("C5", 200, 1e-10, False, 1, True),
+                                                       ("C5", 200, 1e-10, False, 2, True)):
         os.environ["LSQR_B200_COMM_CHUNKS"] = str(chunks)
+        # the layouts of the full-size multi-GPU runs: column-blocked A (fused last block) and row-blocked A'
+        for key, val in (("LSQR_B200_VBLOCK_COLS", "20000"), ("LSQR_B200_UBLOCK_ROWS", "90000")):
+            if blocked:
+                os.environ[key] = val
+            else:
+                os.environ.pop(key, None)
         cfg = synth.scaled(name, scale)
         m, n = cfg["m"], cfg["n"]
         row0, row1 = dist.row_block(m, world, rank)
@@ -54,7 +62,7 @@ def main():
             if want_se:
                 rse = np.linalg.norm(np.asarray(r.se) - ref.se) / np.linalg.norm(ref.se)
                 assert rse <= 1e-8, (name, rse)
-            print(f"MGPU_OK {name}/{scale} chunks={chunks} world={world} istop={r.istop} itn={r.itn} (oracle {ref.itn}) rel_x={rel:.2e}", flush=True)
+            print(f"MGPU_OK {name}/{scale} chunks={chunks} blocked={blocked} world={world} istop={r.istop} itn={r.itn} (oracle {ref.itn}) rel_x={rel:.2e}", flush=True)
         del s
         td.barrier()
     td.destroy_process_group()

@@ -562,7 +562,7 @@ def test_two_gpu_row_partition_matches_oracle(lb):
                         "--master-addr", "127.0.0.1", "--master-port", "29633", os.path.join(root, "tests", "mgpu_worker.py")],
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-5000:]
-    assert r.stdout.count("MGPU_OK") == 3
+    assert r.stdout.count("MGPU_OK") == 5
 
 
 # ------------------------------------------------------------------ row-blocked transpose (u larger than L2)
