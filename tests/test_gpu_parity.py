@@ -490,6 +490,89 @@ def test_one_by_one(lb):
     assert abs(r.x[0] - 0.5) < 1e-15
 
 
+# ------------------------------------------------------------------ behavioural quirks of the reference
+@pytest.mark.parametrize("engine", [0, 1], ids=["fused", "refstruct"])
+def test_negative_damp_skips_the_rotation_but_enters_anorm(lb, engine):
+    """damped = damp > 0 (src/lsqr.f90:597): a negative damp leaves the damping rotation out (:703-710) yet still
+    goes into anorm through d2norm(temp, damp) (:688); istop 2 is not promoted to 3 (:871)."""
+    from lsqr_b200 import synth
+    cfg = synth.scaled("C2", 50)
+    data, r, ref = _solve_both(lb, cfg, 1e-10, 1e-10, 1e8, 500, damp=-0.05, engine=engine)
+    _, r0, _ = _solve_both(lb, cfg, 1e-10, 1e-10, 1e8, 500, damp=0.0, engine=engine)
+    assert r.istop == ref.istop and r.istop != 3 and abs(r.itn - ref.itn) <= 2
+    assert relerr(r.x, ref.x) <= RTOL
+    assert abs(r.anorm - ref.anorm) <= 1e-9 * ref.anorm
+    if r.itn == r0.itn:
+        assert r.anorm > r0.anorm                      # the only trace a negative damp leaves
+    assert relerr(r.x, r0.x) <= 1e-7                   # same iterates as the undamped problem (stop test differs)
+
+
+def test_duplicate_triplets_are_summed_in_coo_order(lb):
+    """Nothing merges or sorts duplicates (src/lsqr.f90:168-172): the product adds every copy."""
+    m, n = 3, 2
+    irow = np.array([1, 1, 1, 2, 3, 3, 1], np.int32)
+    icol = np.array([1, 1, 2, 2, 1, 1, 1], np.int32)
+    a = np.array([1.0, 2.0, 3.0, 4.0, 5.0, -5.0, 0.5])
+    s = lb.LsqrSolverEz().initialize(m, n, a, irow, icol)
+    y = np.zeros(m)
+    s.aprod(1, m, n, np.array([1.0, 10.0]), y)
+    assert np.array_equal(y, np.array([33.5, 40.0, 0.0]))
+    x = np.zeros(n)
+    s.aprod(2, m, n, x, np.array([1.0, 1.0, 1.0]))
+    assert np.array_equal(x, np.array([3.5, 7.0]))
+    ptr, idx, val, perm = s.get_csr()
+    assert list(ptr) == [0, 4, 5, 7] and list(perm[:4]) == [0, 1, 2, 6]      # COO order kept inside row 1
+    b = np.array([1.0, 2.0, 3.0])
+    r, ref = s.solve(b), O.SolverEz(m, n, a, irow, icol).solve(b)
+    assert r.istop == ref.istop and r.itn == ref.itn and relerr(r.x, ref.x) <= 1e-12
+
+
+def test_initialize_twice_resets_the_object(lb):
+    """`me` is intent(out) in initialize_ez (src/lsqr.f90:95): a second initialize starts from a clean object,
+    including the optional tolerances falling back to their defaults (:46-51)."""
+    rng = np.random.default_rng(5)
+    m, n, nnz = 400, 60, 3000
+    irow, icol, a = _random_coo(rng, m, n, nnz)
+    b = rng.standard_normal(m)
+    s = lb.LsqrSolverEz().initialize(m, n, a, irow, icol, atol=1e-3, btol=1e-3, itnlim=7)
+    first = s.solve(b)
+    m2, n2 = 50, 40
+    irow2, icol2, a2 = _random_coo(rng, m2, n2, 900)
+    b2 = rng.standard_normal(m2)
+    s.initialize(m2, n2, a2, irow2, icol2)                       # defaults again: atol = btol = 0, itnlim = 100
+    again = s.solve(b2)
+    fresh = lb.LsqrSolverEz().initialize(m2, n2, a2, irow2, icol2).solve(b2)
+    ref = O.SolverEz(m2, n2, a2, irow2, icol2).solve(b2)
+    assert len(again.x) == n2 and again.itn == fresh.itn and np.array_equal(np.asarray(again.x), np.asarray(fresh.x))
+    assert again.istop == ref.istop and abs(again.itn - ref.itn) <= 6 and relerr(again.x, ref.x) <= 1e-8   # zero tolerances
+    assert first.itn <= 7
+
+
+@pytest.mark.parametrize("shape", [(1, 7), (9, 1), (2, 2)])
+def test_single_row_and_single_column(lb, shape):
+    """dnrm2's n == 1 branch (src/lsqrblas.f90:131-133) and the degenerate bidiagonalisations."""
+    m, n = shape
+    rng = np.random.default_rng(m * 10 + n)
+    irow = np.repeat(np.arange(1, m + 1), n).astype(np.int32)
+    icol = np.tile(np.arange(1, n + 1), m).astype(np.int32)
+    a = rng.standard_normal(m * n)
+    b = rng.standard_normal(m)
+    r = lb.LsqrSolverEz().initialize(m, n, a, irow, icol, itnlim=50).solve(b)
+    ref = O.SolverEz(m, n, a, irow, icol, itnlim=50).solve(b)
+    assert r.istop == ref.istop and abs(r.itn - ref.itn) <= 2
+    assert relerr(r.x, ref.x) <= 1e-10
+
+
+def test_se_is_only_produced_when_wanted(lb):
+    """wantse = .false. leaves se alone (src/lsqr.f90:478-480, 626-630)."""
+    from lsqr_b200 import synth
+    cfg = synth.scaled("C2", 100)
+    data, r, ref = _solve_both(lb, cfg, 1e-10, 1e-10, 1e8, 500, want_se=False)
+    assert r.se is None
+    data, r, ref = _solve_both(lb, cfg, 1e-10, 1e-10, 1e8, 500, want_se=True)
+    assert r.se is not None and relerr(r.se, ref.se) <= 1e-8
+
+
 def test_device_resident_vectors(lb):
     import torch
     from lsqr_b200 import synth
