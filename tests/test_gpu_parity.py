@@ -819,3 +819,48 @@ def test_full_size_properties(lb, name):
     r3 = s.solve(2.0 * b, cfg["damp"])
     assert r3.istop == r1.istop and abs(r3.itn - r1.itn) <= 1
     assert float((r3.x - 2.0 * x1).norm() / x1.norm()) <= 1e-8
+
+
+def test_c5_full_size_on_one_gpu(lb):
+    """C5 (100M x 10M, 2.0e9 entries: the north-star problem) on ONE B200: both blocked layouts at full size (A in 2
+    column blocks, A' in 16 row blocks), adjointness of the products (acheck), the solution checked by xcheck's true
+    residuals, bitwise reproducibility.  The complete CSR verification of the blocked layouts is done at C3 / C4
+    full size and in test_row_blocked_transpose / test_column_blocked_matrix (its int64 temporaries would not fit
+    next to a 2e9-entry problem)."""
+    import torch
+    from lsqr_b200 import synth, synth_device
+    dev = torch.device("cuda", 0)
+    torch.cuda.empty_cache()
+    free, _total = torch.cuda.mem_get_info(dev)
+    if free < 150e9:
+        pytest.skip("needs ~130 GB of free HBM")
+    cfg = synth.CONFIGS["C5"]
+    m, n = cfg["m"], cfg["n"]
+    irow, icol, a = synth_device.coo_block(cfg["kind"], cfg["seed"], m, n, cfg["k"], 0, m, dev)
+    assert a.numel() == 2_000_000_000
+    s = lb.LsqrSolverEz().initialize(m, n, a, irow, icol, atol=1e-10, btol=1e-10, conlim=1e8, itnlim=500)
+    del irow, icol, a
+    torch.cuda.empty_cache()
+    assert s.blocks(False)[0] == 2 and s.blocks(True)[0] == 16
+    for tr in (False, True):
+        for blk in range(s.blocks(tr)[0]):
+            assert s.schedule(tr, blk)["imbalance"] <= 1.06
+    op = lb.EzAsOperator(s)
+    v, x = torch.empty(n, dtype=torch.float64, device=dev), torch.empty(n, dtype=torch.float64, device=dev)
+    w, y = torch.empty(m, dtype=torch.float64, device=dev), torch.empty(m, dtype=torch.float64, device=dev)
+    inform, rel = op.acheck(m, n, v, w, x, y)
+    assert inform == 0 and rel <= 1e-12
+    del y
+    xt = synth_device.x_true(cfg["seed"], n, dev)
+    b = synth_device.noise(cfg["seed"], 0, m, dev)
+    s.aprod(1, m, n, xt, b)                                    # b = A x_true + 1e-3 noise
+    r1 = s.solve(b, cfg["damp"])
+    assert r1.istop in (1, 2) and 5 <= r1.itn < 100
+    assert float((r1.x - xt).norm() / xt.norm()) <= 1e-3       # the noise level
+    chk = op.xcheck(m, n, r1.anorm, cfg["damp"], b, w, v, x, r1.x)
+    assert chk["inform"] in (1, 2, 3)
+    assert abs(chk["rho2"] - r1.rnorm) <= 1e-6 * r1.rnorm
+    x1 = r1.x.clone()
+    r2 = s.solve(b, cfg["damp"])
+    assert r2.itn == r1.itn and torch.equal(r2.x.view(torch.int64), x1.view(torch.int64))
+    s.destroy()
