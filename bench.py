@@ -340,7 +340,8 @@ def run_workload(name, args, steps, world, rank, dev, with_roofline=True):
     if world > 1:
         import torch.distributed as td
         td.all_reduce(rr)
-    rnorm_true = float(torch.sqrt(rr).item())
+    # damped problems: the recurrence's rnorm is that of the augmented system, sqrt(||b - A x||^2 + damp^2 ||x||^2)
+    rnorm_true = float(torch.sqrt(rr + cfg["damp"] ** 2 * torch.sum(x_dev ** 2)).item())
     dx = float((x_host.to(dev) - x_dev).abs().max().item())
     check = {"rnorm_reported": last.rnorm, "rnorm_recomputed": rnorm_true,
              "rel_diff": abs(rnorm_true - last.rnorm) / max(last.rnorm, 1e-300), "max_abs_dx_host_vs_device_run": dx}

@@ -248,7 +248,8 @@ static int launch_spmv(Work &wk, const CsrView &V, int lanes, const double *x, d
 struct TileMapOwner {
     uint2 *tiles = nullptr;
     int ntiles = 0;
-    uint32_t tile = kTile;   // nominal stored entries per tile
+    uint32_t tile = kTile;   // nominal work units per tile (stored entries + row_w per row)
+    uint32_t row_w = 0;      // kind 3: weight of a row in the tile cut, so that long runs of empty rows are split too
     int kind = 2;            // 2 = CTA tiles of the TMA-streamed kernel, 3 = warp tiles of the segmented kernel
     // kind 3, very uneven rows only: balanced tile schedule (see TileMap::order); the grid is then the full persistent grid
     uint32_t *order = nullptr;
@@ -277,14 +278,16 @@ static uint32_t warp_tile_size(int ctas, int64_t nnz)
     return (uint32_t)std::max<int64_t>(512, (t + 3) & ~(int64_t)3);
 }
 
+static inline int64_t tile_work(const TileMapOwner &mp, const CsrView &V, int64_t nnz) { return nnz + (int64_t)mp.row_w * V.nrows; }
+
 static int build_tiles(Work &wk, const CsrView &V, int64_t nnz, uint32_t tile, TileMapOwner *out)
 {
     if (out->tiles) { cudaFree(out->tiles); out->tiles = nullptr; }
     out->tile = tile;
-    const int64_t nt = std::max<int64_t>(1, (nnz + tile - 1) / tile);
+    const int64_t nt = std::max<int64_t>(1, (tile_work(*out, V, nnz) + tile - 1) / tile);
     out->ntiles = (int)nt;
     LSQRB_CUDA(cudaMalloc(&out->tiles, sizeof(uint2) * (size_t)(nt + 1)));
-    build_tiles_kernel<<<(int)((nt + 1 + 255) / 256), 256, 0, wk.stream>>>(V.ptr, V.nrows, (int)nt, tile, out->tiles);
+    build_tiles_kernel<<<(int)((nt + 1 + 255) / 256), 256, 0, wk.stream>>>(V.ptr, V.nrows, (int)nt, tile, out->row_w, out->tiles);
     LSQRB_CUDA(cudaGetLastError());
     return LSQR_B200_OK;
 }
@@ -322,7 +325,7 @@ static int balance_tile_map(Work &wk, const CsrView &V, int64_t nnz, TileMapOwne
         for (int i = 0; i < out->ntiles; ++i) load[(size_t)(i % gw)] += cost[(size_t)i];
         out->imbalance = total > 0 ? *std::max_element(load.begin(), load.end()) / (total / nw) : 1.0;
     }
-    if (env_int("LSQR_B200_BALANCE", 1) == 0 || nnz <= (int64_t)nw * 512) return LSQR_B200_OK;   // nothing to deal out
+    if (env_int("LSQR_B200_BALANCE", 1) == 0 || tile_work(*out, V, nnz) <= (int64_t)nw * 512) return LSQR_B200_OK;   // nothing to deal out
     if (out->imbalance <= 1.0 + 1e-3 * env_int("LSQR_B200_BALANCE_PERMILLE", 60)) return LSQR_B200_OK;
 
     // finer tiles pack better (the long rows stay as long as they are)
@@ -364,7 +367,11 @@ static int build_tile_map(Work &wk, const CsrView &V, int64_t nnz, int kind, Til
 {
     out->kind = kind;
     out->ctas = std::max(1, wk.sms - reserve_sms) * kWMinBlocks;
-    LSQRB_TRY(build_tiles(wk, V, nnz, kind == 3 ? warp_tile_size(out->ctas, nnz) : (uint32_t)kTile, out));
+    // A row costs about as much as 4 stored entries (its share of a window reload and its epilogue).  Without the row
+    // term a block of a row-blocked banded A' -- half of whose rows are empty -- puts a million empty rows into ONE
+    // tile, i.e. one warp (measured: C3 full size, Atprod 55 ms instead of 1.4 ms).
+    out->row_w = kind == 3 ? (uint32_t)std::max(0, env_int("LSQR_B200_TILE_ROW_WEIGHT", 4)) : 0u;
+    LSQRB_TRY(build_tiles(wk, V, nnz, kind == 3 ? warp_tile_size(out->ctas, tile_work(*out, V, nnz)) : (uint32_t)kTile, out));
     if (kind == 3) LSQRB_TRY(balance_tile_map(wk, V, nnz, out));
     return LSQR_B200_OK;
 }

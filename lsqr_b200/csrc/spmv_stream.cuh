@@ -91,19 +91,23 @@ __device__ __forceinline__ void fence_proxy_async_smem()
 }
 
 // ---------------------------------------------------------------------------------------------
-// Tile map construction: tile t starts at the first row whose first entry is at or after t*tile.
+// Tile map construction: tile t starts at the first row whose work coordinate is at or after t*tile.
 // ---------------------------------------------------------------------------------------------
 // ptr may be the pointer array of one block of a row-blocked transpose: its entries then start at ptr[0] != 0.
-__global__ void build_tiles_kernel(const uint32_t *__restrict__ ptr, int64_t nrows, int ntiles, uint32_t tile, uint2 *tiles)
+// Work coordinate of row r: W(r) = (ptr[r] - ptr[0]) + row_w * r  (stored entries before the row, plus row_w units
+// per row: a run of EMPTY rows is work too -- every row gets its epilogue -- and must not land in one tile).
+__global__ void build_tiles_kernel(const uint32_t *__restrict__ ptr, int64_t nrows, int ntiles, uint32_t tile, uint32_t row_w,
+                                   uint2 *tiles)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t > ntiles) return;
     if (t == ntiles) { tiles[t] = make_uint2((uint32_t)nrows, ptr[nrows]); return; }
-    const uint64_t target = (uint64_t)ptr[0] + (uint64_t)t * tile;
-    int64_t lo = 0, hi = nrows;   // first r in [0, nrows] with ptr[r] >= target
+    const uint64_t base = ptr[0];
+    const uint64_t target = (uint64_t)t * tile;
+    int64_t lo = 0, hi = nrows;   // first r in [0, nrows] with W(r) >= target
     while (lo < hi) {
         const int64_t mid = (lo + hi) >> 1;
-        if ((uint64_t)ptr[mid] >= target) hi = mid; else lo = mid + 1;
+        if (((uint64_t)ptr[mid] - base) + (uint64_t)row_w * (uint64_t)mid >= target) hi = mid; else lo = mid + 1;
     }
     tiles[t] = make_uint2((uint32_t)lo, ptr[lo]);
 }

@@ -864,3 +864,45 @@ def test_c5_full_size_on_one_gpu(lb):
     r2 = s.solve(b, cfg["damp"])
     assert r2.itn == r1.itn and torch.equal(r2.x.view(torch.int64), x1.view(torch.int64))
     s.destroy()
+
+
+def test_row_blocked_banded_transpose_has_no_giant_tile(lb, monkeypatch):
+    """C3 family (banded) with a row-blocked A': inside one block half of the rows of A' are EMPTY (their entries
+    live in the other row blocks).  Tiles are cut by work (entries + a weight per row), so the empty half is split
+    over many warps instead of landing in one tile (regression: full-size C3 Atprod took 55 ms instead of 1.4 ms);
+    the blocked product must cost about as much as the unblocked one and give the same result to rounding."""
+    import torch
+    from lsqr_b200 import synth, synth_device
+    cfg = synth.scaled("C3", 10)                       # 1M x 200k, 5e7 entries
+    m, n = cfg["m"], cfg["n"]
+    dev = torch.device("cuda", 0)
+    irow, icol, a = synth_device.coo_block(cfg["kind"], cfg["seed"], m, n, cfg["k"], 0, m, dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    y = synth_device.noise(cfg["seed"], 0, m, dev, scale=1.0)
+    res, times = [], []
+    for rows in ("0", str(m // 4)):
+        if rows == "0":
+            monkeypatch.delenv("LSQR_B200_UBLOCK_ROWS", raising=False)
+        else:
+            monkeypatch.setenv("LSQR_B200_UBLOCK_ROWS", rows)
+        s = lb.LsqrSolverEz().initialize(m, n, a, irow, icol, stream=stream)
+        nb = s.blocks(True)[0]
+        assert nb == (1 if rows == "0" else 4)
+        for blk in range(nb):
+            assert s.schedule(True, blk)["imbalance"] <= 1.5, (blk, s.schedule(True, blk))
+        x = torch.zeros(n, dtype=torch.float64, device=dev)
+        for _ in range(3):
+            s.aprod_device(2, m, n, x, y, stream)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            s.aprod_device(2, m, n, x, y, stream)
+        e1.record()
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1) / 10)
+        x.zero_()
+        s.aprod(2, m, n, x, y)
+        res.append(x.clone())
+        s.destroy()
+    assert float((res[0] - res[1]).abs().max() / res[0].abs().max()) <= 1e-13
+    assert times[1] <= 3.0 * times[0], times
