@@ -47,8 +47,11 @@ def parse_args():
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--workload", default="auto", choices=["auto", "C2", "C3", "C4", "C5"])
     p.add_argument("--scale", type=float, default=1.0, help="divide m and n by this factor")
-    p.add_argument("--secondary", default="C2", choices=["none", "C2", "C3", "C4"],
-                   help="N = 1 only: a second workload measured the same way and reported under `secondary`")
+    p.add_argument("--secondary", default="C2,C3",
+                   help="N = 1 only: comma-separated workloads measured the same way and reported under `secondary` (or none)")
+    p.add_argument("--via-hook", action="store_true",
+                   help="drive the ez matrix through the low-level lsqr_solver%%lsqr operator-hook path (engine = 1)")
+    p.add_argument("--no-oracle-check", action="store_true")
     p.add_argument("--cpu-scale", type=float, default=0.0, help="scale of the CPU-baseline sample (0 = auto)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-graph", action="store_true")
@@ -70,6 +73,32 @@ def measured_peak():
         return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def host_synth():
+    """lsqr_b200/synth.py (numpy only) loaded BY PATH: the reference arm and the CPU baseline must not import the
+    lsqr_b200 package, whose __init__ maps the CUDA engine into the process."""
+    import importlib.util
+    name = "_lsqr_b200_host_synth"
+    if name in sys.modules:
+        return sys.modules[name]
+    spec = importlib.util.spec_from_file_location(name, os.path.join(ROOT, "lsqr_b200", "synth.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def cpu_info() -> dict:
+    model, present = "unknown", os.cpu_count() or 0
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.lower().startswith("model name"):
+                model = line.split(":", 1)[1].strip()
+                break
+    except OSError:
+        pass
+    return {"cpu_model": model, "cores_present": present}
 
 
 class ClockSampler:
@@ -127,23 +156,32 @@ class ClockSampler:
 # reference arm / CPU baseline: the oracle port of the reference algorithm on the host CPU
 # ------------------------------------------------------------------------------------------------
 def cpu_sample_config(name: str, cpu_scale: float):
-    from lsqr_b200 import synth
-    auto = {"C2": 1.0, "C3": 25.0, "C4": 40.0, "C5": 100.0}[name]
+    synth = host_synth()
+    # C3/C4/C5 at 1/10 scale: the gathered vectors (x: 1.6 - 8 MB, u: 8 - 80 MB) no longer sit in the CPU's caches,
+    # and one full solve takes 10 - 30 s on one core
+    auto = {"C2": 1.0, "C3": 10.0, "C4": 10.0, "C5": 10.0}[name]
     scale = cpu_scale if cpu_scale > 0 else auto
     return synth.scaled(name, scale), scale
 
 
 def run_cpu_reference(name: str, cpu_scale: float, steps: int, warmup: int, budget_s: float = 25.0):
-    """Times oracle solve_ez (serial, like the reference) on a bounded sample of the workload."""
-    from lsqr_b200 import synth
+    """Times oracle solve_ez (serial, like the reference) on a bounded sample of the workload: at least one full
+    solve, more while the time budget lasts."""
+    synth = host_synth()
     from oracle import oracle as O
+    flags = O.use_native_build()          # gcc -O3 -march=native -ffp-contract=off on THIS box (BASELINE.md 4)
     cfg, scale = cpu_sample_config(name, cpu_scale)
     m, n = cfg["m"], cfg["n"]
     irow, icol, a = synth.coo_block(cfg["kind"], cfg["seed"], m, n, cfg["k"])
     b = synth.rhs_block(irow, icol, a, m, synth.x_true(cfg["seed"], n), cfg["seed"])
     s = O.SolverEz(m, n, a, irow, icol, SOLVE_OPTS["atol"], SOLVE_OPTS["btol"], SOLVE_OPTS["conlim"], SOLVE_OPTS["itnlim"])
-    for _ in range(max(0, min(warmup, 1))):
+    t0 = time.perf_counter()
+    warm = 0
+    for _ in range(max(0, warmup)):
         s.solve(b, cfg["damp"])
+        warm += 1
+        if time.perf_counter() - t0 > 0.4 * budget_s:
+            break
     t0 = time.perf_counter()
     itn = 0
     done = 0
@@ -155,12 +193,15 @@ def run_cpu_reference(name: str, cpu_scale: float, steps: int, warmup: int, budg
             break
     dt = time.perf_counter() - t0
     bytes_iter = synth.b_iter_bytes(a.size, m, n)
-    return {
+    out = {
         "value": bytes_iter * itn / dt / 1e9, "unit": UNIT, "cores": 1, "kind": "port",
-        "iters_per_s": itn / dt, "ms_per_step": 1e3 * dt / done, "steps_done": done, "itn_per_step": itn / done,
-        "sample": f"{name} at 1/{scale:g} scale: {m}x{n}, nnz={a.size}; {done} full solves, serial C port of "
-                  f"src/lsqr.f90 (no Fortran compiler in this image), gcc -O2 -ffp-contract=off",
+        "iters_per_s": itn / dt, "ms_per_step": 1e3 * dt / done, "steps_done": done, "warmup_done": warm,
+        "itn_per_step": itn / done, "sample_scale": scale,
+        "sample": f"{name} at 1/{scale:g} scale: {m}x{n}, nnz={a.size}; {done} full solve(s) after {warm} warm-up, serial C "
+                  f"port of src/lsqr.f90 (no Fortran compiler in this image), gcc {flags}",
     }
+    out.update(cpu_info())
+    return out
 
 
 def reference_main(args):
@@ -168,14 +209,17 @@ def reference_main(args):
     if rank != 0:
         return
     name = pick_workload(args)
-    res = run_cpu_reference(name, args.cpu_scale, args.steps, args.warmup, budget_s=120.0)
+    res = run_cpu_reference(name, args.cpu_scale, args.steps, args.warmup, budget_s=150.0)
     line = {
         "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
-        "steps": res["steps_done"], "warmup": min(args.warmup, 1), "ms_per_step": res["ms_per_step"],
+        "steps": res["steps_done"], "warmup": res["warmup_done"], "ms_per_step": res["ms_per_step"],
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "iters_per_s": res["iters_per_s"],
-        "config": {"workload": name, "sample": res["sample"]},
-        "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "config": {"workload": name, "sample": res["sample"], "sample_scale": res["sample_scale"],
+                   "note": "GB/s is throughput normalised by the problem's own algorithmic bytes; the CPU sample is a "
+                           "scaled-down instance of the GPU arm's workload (a cross-size ratio: the full problem needs "
+                           "64 GB of COO on the host and ~30 min per solve on one core)"},
+        "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample", "cpu_model", "cores_present", "sample_scale")},
         "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -209,14 +253,21 @@ def main():
     name = pick_workload(args)
     res = run_workload(name, args, args.steps, world, rank, dev, with_roofline=True)
 
-    # N = 1 only: BASELINE.json's 1 x B200 configuration (configs[1], C2) rides along as a secondary record
-    secondary = None
-    if world == 1 and args.secondary != "none" and args.secondary != name and args.scale == 1.0:
-        sec = run_workload(args.secondary, args, max(args.steps, 20), world, rank, dev, with_roofline=True)
-        secondary = {k: sec[k] for k in ("workload", "value", "iters_per_s", "ms_per_iteration", "frac_of_hbm_roofline",
-                                         "itn_per_step", "istop")}
-        secondary["e2e_value"] = sec["e2e"]["value"]
-        secondary["roofline"] = {k: sec["roofline"][k] for k in ("kernel", "achieved", "frac", "traffic", "avg_launch_ms")}
+    # oracle parity of the very code path that was timed (same blocked layouts, same exchange), on a reduced-scale
+    # instance the serial oracle solves in seconds; every N, outside the timed region, failing loudly
+    oracle_check = None if args.no_oracle_check else oracle_parity_check(name, world, rank, dev, res["layout"])
+
+    # N = 1 only: BASELINE.json's other single-GPU configurations ride along as secondary records
+    secondary = []
+    if world == 1 and args.secondary != "none" and args.scale == 1.0:
+        for sec_name in [t for t in args.secondary.split(",") if t and t != name]:
+            sec = run_workload(sec_name, args, max(args.steps, 20) if sec_name == "C2" else 5, world, rank, dev, with_roofline=True)
+            rec = {k: sec[k] for k in ("workload", "value", "iters_per_s", "ms_per_iteration", "frac_of_hbm_roofline",
+                                       "itn_per_step", "istop")}
+            rec["e2e_value"] = sec["e2e"]["value"]
+            rec["roofline"] = {k: sec["roofline"][k] for k in ("kernel", "achieved", "frac", "traffic", "avg_launch_ms", "per_kernel", "loop_frac")}
+            rec["plan"] = sec["layout"]["plan"]
+            secondary.append(rec)
 
     if world > 1:
         import torch.distributed as td
@@ -232,13 +283,78 @@ def main():
         "frac_of_hbm_roofline": res["frac_of_hbm_roofline"],
         "config": res["config"], "e2e": res["e2e"], "gpu_launches": res["gpu_launches"],
         "roofline": res["roofline"], "clocks": res["clocks"], "check": res["check"],
+        "e2e_cold": res["e2e_cold"], "launches_per_iteration": res["launches_per_iteration"],
     }
+    if oracle_check is not None:
+        line["check"]["oracle"] = oracle_check
+    if world > 1:
+        line["collective_ms"] = res["collective_ms"]
     if secondary:
         line["secondary"] = secondary
     if world == 1 and not args.no_cpu_baseline:
-        cb = run_cpu_reference(name, args.cpu_scale, 3, 1, budget_s=20.0)
-        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "iters_per_s")}
+        cb = run_cpu_reference(name, args.cpu_scale, 1, 0, budget_s=20.0)
+        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "iters_per_s", "cpu_model",
+                                                   "cores_present", "sample_scale")}
     print(json.dumps(line), file=_JSON_OUT, flush=True)
+
+
+def oracle_parity_check(name, world, rank, dev, layout):
+    """Engine vs the serial oracle on a reduced-scale instance of `name`, through the same code path as the timed
+    run: the same number of column blocks of A / row blocks of A' per rank (forced through the block-size switches)
+    and the same multi-GPU exchange.  Every rank solves its row block; rank 0 runs oracle.SolverEz on the whole
+    problem and compares x, istop, itn, rnorm (north_star: rel <= 1e-10, |d itn| <= 2, istop equal)."""
+    import torch
+    import lsqr_b200
+    from lsqr_b200 import synth, dist as ldist, synth_device
+    scale = {"C2": 10.0, "C3": 100.0, "C4": 100.0, "C5": 500.0}[name]
+    cfg = synth.scaled(name, scale)
+    m, n = cfg["m"], cfg["n"]
+    row0, row1 = ldist.row_block(m, world, rank)
+    m_loc = row1 - row0
+    env = {}
+    if layout["blocks_a"] > 1:
+        env["LSQR_B200_VBLOCK_COLS"] = str(-(-n // layout["blocks_a"]))
+    if layout["blocks_at"] > 1:
+        env["LSQR_B200_UBLOCK_ROWS"] = str(max(1, -(-m_loc // layout["blocks_at"])))
+    saved = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        irow, icol, a = synth_device.coo_block(cfg["kind"], cfg["seed"], m, n, cfg["k"], row0, m_loc, dev)
+        uid = ldist.exchange_unique_id(world, rank) if world > 1 else None
+        s = lsqr_b200.LsqrSolverEz().initialize(m_loc, n, a, irow, icol, stream=torch.cuda.current_stream().cuda_stream,
+                                                world_size=world, rank=rank, nccl_unique_id=uid, m_global=m,
+                                                atol=1e-10, btol=1e-10, conlim=1e8, itnlim=4000)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    hs = host_synth()
+    I, J, A = hs.coo_block(cfg["kind"], cfg["seed"], m, n, cfg["k"])
+    b = hs.rhs_block(I, J, A, m, hs.x_true(cfg["seed"], n), cfg["seed"])
+    r = s.solve(np.ascontiguousarray(b[row0:row1]), cfg["damp"])
+    blocks = (s.blocks(False)[0], s.blocks(True)[0])
+    peer = s.plan(False)["peer_exchange"]
+    s.destroy()
+    out = None
+    if rank == 0:
+        from oracle import oracle as O
+        ref = O.SolverEz(m, n, A, I, J, atol=1e-10, btol=1e-10, conlim=1e8, itnlim=4000).solve(b, cfg["damp"])
+        rel_x = float(np.linalg.norm(np.asarray(r.x) - ref.x) / np.linalg.norm(ref.x))
+        out = {"problem": f"{name} at 1/{scale:g} scale: {m}x{n}", "n_gpus": world, "blocks_a": blocks[0], "blocks_at": blocks[1],
+               "peer_exchange": peer, "rel_x": rel_x, "rel_rnorm": abs(r.rnorm - ref.rnorm) / ref.rnorm,
+               "istop": r.istop, "istop_oracle": ref.istop, "itn": r.itn, "itn_oracle": ref.itn}
+        out["ok"] = bool(rel_x <= 1e-10 and out["rel_rnorm"] <= 1e-10 and r.istop == ref.istop and abs(r.itn - ref.itn) <= 2)
+    if world > 1:
+        import torch.distributed as td
+        flag = torch.tensor([1 if (out is None or out["ok"]) else 0], dtype=torch.int32, device=dev)
+        td.broadcast(flag, src=0)
+        if int(flag.item()) == 0 and rank != 0:
+            raise AssertionError("oracle parity check failed on rank 0")
+    if out is not None and not out["ok"]:
+        raise AssertionError(f"bench oracle parity check failed: {out}")
+    return out
 
 
 def run_workload(name, args, steps, world, rank, dev, with_roofline=True):
@@ -265,10 +381,11 @@ def run_workload(name, args, steps, world, rank, dev, with_roofline=True):
     torch.cuda.synchronize()
     t_init = time.perf_counter()
     solver = lsqr_b200.LsqrSolverEz().initialize(
-        m_loc, n, a, irow, icol, stream=stream, use_graph=not args.no_graph,
+        m_loc, n, a, irow, icol, stream=stream, use_graph=not args.no_graph, engine=1 if args.via_hook else 0,
         world_size=world, rank=rank, nccl_unique_id=nccl_id, m_global=m, **SOLVE_OPTS)
     torch.cuda.synchronize()
     t_init = time.perf_counter() - t_init
+    plan_a, plan_at = solver.plan(False), solver.plan(True)
     del irow, icol, a
     torch.cuda.empty_cache()
 
@@ -319,7 +436,11 @@ def run_workload(name, args, steps, world, rank, dev, with_roofline=True):
             ms = float(t.item())
         return ms, wall, itn, launches, last
 
-    # ---- warm-up, then the timed regions
+    # ---- warm-up (the first solve is the cold one: graph capture, first touches), then the timed regions
+    torch.cuda.synchronize()
+    t_cold = time.perf_counter()
+    solver.solve(b_host, cfg["damp"], x=x_host)
+    t_cold = time.perf_counter() - t_cold
     for _ in range(max(args.warmup, 3)):
         solver.solve(b_dev, cfg["damp"], x=x_dev)
     sampler = ClockSampler(local_rank)
@@ -365,23 +486,37 @@ def run_workload(name, args, steps, world, rank, dev, with_roofline=True):
     kms = {"aprod": kt["aprod_ms"], "atprod": kt["atprod_ms"], "update": kt["update_ms"]}
     dom = max(kms, key=lambda k: kms[k])
     achieved = kb[dom] / (kms[dom] * 1e-3) / 1e9 if kms[dom] > 0 else 0.0
-    traffic = None
-    try:   # per-launch DRAM bytes from the committed ncu capture, if it was summarised for this workload
+    traffic, traffic_src = None, None
+    try:   # per-launch DRAM bytes: NOT measured in this run -- read from the committed ncu capture of this workload
         prof = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic.json")))
         traffic = prof.get(name, {}).get(dom)
+        if traffic is not None:
+            traffic_src = prof.get("_source", "committed ncu capture (profiles/dram_traffic.json)")
     except Exception:
         pass
     roofline = {
         "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-        "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+        "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
         "algorithmic_bytes_per_launch": kb[dom], "avg_launch_ms": kms[dom],
-        "launch_note": "one product = %d (Aprod) / %d (Atprod) block launches timed as a group between one CUDA-event pair "
-                       "(A column-blocked / A' row-blocked when the gathered vector exceeds the L2 budget)" % (nblk_a, nblk_at),
+        "launch_note": "one product = ONE persistent launch that walks %d column blocks of A (Aprod) / %d row blocks of A' "
+                       "(Atprod); blocked when the gathered vector exceeds the L2 budget%s" % (
+                           nblk_a, nblk_at, "" if plan_a["single_launch"] else " [single launch OFF: one launch per block]"),
         "per_kernel": {k: {"ms": kms[k], "GBps": (kb[k] / (kms[k] * 1e-3) / 1e9 if kms[k] > 0 else 0.0),
                            "frac": (kb[k] / (kms[k] * 1e-3) / 1e9 / peak if kms[k] > 0 else 0.0)} for k in kms},
         "loop_frac": (bytes_iter * last.itn / (kt["loop_ms"] * 1e-3) / 1e9) / (peak * world) if kt["loop_ms"] > 0 else None,
     }
 
+    layout = {
+        "blocks_a": nblk_a, "blocks_at": nblk_at, "block_cols": solver.blocks(False)[1], "block_rows": solver.blocks(True)[1],
+        "m_loc": m_loc, "n": n,
+        "plan": {"A": {k: plan_a[k] for k in ("window_doubles", "windowed_fraction", "ctas_per_sm", "grid_ctas", "balanced")},
+                 "At": {k: plan_at[k] for k in ("window_doubles", "windowed_fraction", "ctas_per_sm", "grid_ctas", "balanced")},
+                 "single_launch": plan_a["single_launch"], "peer_exchange": plan_a["peer_exchange"]},
+    }
+    launches_per_iteration = kt["iteration_launches"]
+    # multi-GPU: device time per iteration of the kernels that are not products or the update, i.e. the owner-side
+    # reduction + all-gather + scalar step of the peer exchange (or vfinish after the all-reduce): the exposed part
+    collective_ms = kt["other_ms"]
     solver.destroy()
     del b_dev, x_dev, b_host, x_host, xt
     torch.cuda.empty_cache()
@@ -405,6 +540,10 @@ def run_workload(name, args, steps, world, rank, dev, with_roofline=True):
                 "iters_per_s": itn_e2e / (ms_e2e * 1e-3), "ms_per_step": ms_e2e / steps, "wall_s": wall_e2e,
                 "api": "lsqr_b200_ez_solve with pinned host b and x (C ABI, via LsqrSolverEz.solve)"},
         "gpu_launches": launches, "roofline": roofline, "clocks": clocks, "check": check,
+        "layout": layout, "launches_per_iteration": launches_per_iteration, "collective_ms": collective_ms,
+        "e2e_cold": {"initialize_s": t_init, "first_solve_s": t_cold, "total_s": t_init + t_cold,
+                     "note": "COO -> CSR/CSR' build + plans (initialize) and the first solve from pinned host b "
+                             "(graph capture included); excluded from `value` and `e2e`, which time warm solves"},
     }
 
 

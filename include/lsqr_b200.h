@@ -19,7 +19,16 @@
  *    with LSQR_B200_ERR_NO_DEVICE.
  *  - One handle = one solve at a time (the reference object is not re-entrant either:
  *    aprod_ez mutates me%Ax / me%Aty, src/lsqr.f90:166-167,186-187).  Different handles
- *    may be driven from different host threads.
+ *    may be driven from different host threads; the library keeps no global mutable state
+ *    (the error detail of lsqr_b200_last_error() is per thread).
+ *  - Stream ordering.  options.stream == NULL: the handle works on a library-owned BLOCKING
+ *    stream, which CUDA orders against the legacy default stream (stream 0, the one PyTorch
+ *    uses by default): device data the caller produced on stream 0 is complete before the
+ *    library reads it, and the library's results are complete before the caller's later
+ *    stream-0 work.  A caller working on any other stream passes that stream.  Where a
+ *    function takes a `stream` ARGUMENT (lsqr_b200_ez_aprod_device, the BLAS-1 functions, the
+ *    aprod callback), NULL means the legacy default stream itself, as everywhere in CUDA;
+ *    cudaStreamLegacy / cudaStreamPerThread handles are accepted too.
  */
 #ifndef LSQR_B200_H
 #define LSQR_B200_H
@@ -30,7 +39,7 @@
 extern "C" {
 #endif
 
-#define LSQR_B200_VERSION 100
+#define LSQR_B200_VERSION 200
 
 /* The shared library is built with -fvisibility=hidden; only these entry points are exported. */
 #if defined(__GNUC__)
@@ -99,8 +108,9 @@ typedef struct lsqr_b200_options {
                                 (dscal / aprod / dnrm2 as separate kernels; for A/B parity) */
     int32_t use_graph;       /* 1 (default) = CUDA-graph the iteration, 0 = plain launches */
     int32_t profile;         /* 1 = time every kernel class with CUDA events (slower)  */
-    int32_t spmv_variant;    /* 0 = default (3), 1 = sub-warp per row, 2 = CTA tiles streamed by TMA,
-                                3 = warp-autonomous segmented kernel */
+    int32_t spmv_variant;    /* 0 or 3: the warp-autonomous segmented kernel (round 1's variants 1 and 2
+                                measured slower on every workload and were removed; other values are
+                                rejected with LSQR_B200_ERR_ARG) */
     /* --- multi-GPU: A is row-partitioned, one process per GPU ----------- */
     int32_t world_size;      /* 1 (default) = single GPU                         */
     int32_t rank;
@@ -177,6 +187,23 @@ LSQR_B200_API int lsqr_b200_ez_blocks(const lsqr_b200_ez *me, int32_t which, int
 LSQR_B200_API int lsqr_b200_ez_schedule(const lsqr_b200_ez *me, int32_t which, int64_t block, int64_t *ntiles,
                           int64_t *tile_entries, int32_t *balanced, double *imbalance);
 
+/* The work plan of the SpMV kernel over the stored A (which = 0) or A' (which = 1): one plan covers every block of
+ * the matrix.  Diagnostic; no reference counterpart. */
+typedef struct lsqr_b200_plan_info {
+    int64_t nblocks;            /* blocks along the gathered coordinate (1 = plain CSR)                         */
+    int64_t ntiles;             /* row-aligned tiles; the same row cuts in every block                          */
+    int32_t grid_ctas;          /* persistent grid                                                              */
+    int32_t ctas_per_sm;        /* kernel flavour: 4 (32 warps per SM) or 2 (16 warps, wide gather windows)     */
+    int32_t window_doubles;     /* shared-memory gather window per warp, in doubles (0 = gathers stay global)   */
+    int32_t balanced;           /* largest-first tile schedule in use (very uneven row lengths)                 */
+    double  windowed_fraction;  /* fraction of the stored entries whose gathers are served from shared memory   */
+    double  imbalance;          /* most loaded warp / mean load                                                 */
+    int64_t span_median, span_max;  /* gather span of the pieces (entries of the dense vector)                  */
+    int32_t single_launch;      /* one persistent launch walks every block of a product                         */
+    int32_t peer_exchange;      /* multi-GPU: exchange over NVLink peer memory instead of one NCCL all-reduce   */
+} lsqr_b200_plan_info;
+LSQR_B200_API int lsqr_b200_ez_plan(const lsqr_b200_ez *me, int32_t which, lsqr_b200_plan_info *out);
+
 /* Kernel timing of the most recent solve.  loop_ms / init_ms / total_launches are always
  * filled; the per-kernel averages only when options.profile = 1 (CUDA-event pairs around every
  * launch inside the real iteration loop, so L2 contents are those of the real loop). */
@@ -186,6 +213,7 @@ typedef struct lsqr_b200_kernel_times {
     int64_t total_launches;    /* every kernel of this library launched by the last solve */
     double  loop_ms;           /* device time of the iteration loop of the last solve     */
     double  init_ms;           /* device time before the first iteration (b -> u, v, w)   */
+    int64_t iteration_launches;/* kernels of this library per LSQR iteration              */
 } lsqr_b200_kernel_times;
 LSQR_B200_API int lsqr_b200_ez_get_kernel_times(const lsqr_b200_ez *me, lsqr_b200_kernel_times *out);
 
@@ -200,7 +228,11 @@ typedef int (*lsqr_b200_aprod_fn)(void *user, int32_t mode, int32_t m, int32_t n
 /* Replaces  lsqr_solver%lsqr  (LSQR, src/lsqr.f90:432-882) with a caller-supplied operator and
  * caller-supplied DEVICE storage u(m) [in: b, overwritten], v(n), w(n), x(n) [out],
  * se(n) [touched only if wantse].  Scalar outputs are host pointers (NULL to omit).
- * opts supplies stream/device/log/iter; its atol..itnlim fields are ignored here. */
+ * opts supplies stream/device/log/iter; its atol..itnlim fields are ignored here.
+ * Iterations are enqueued in batches without host synchronisation (the device stops itself), so
+ * the callback may be invoked a few times after the stopping iteration: x, se and every scalar are
+ * those of the stopping iteration, u and v are work space on return (the reference leaves the last
+ * Lanczos vectors there). */
 LSQR_B200_API int lsqr_b200_lsqr(lsqr_b200_aprod_fn aprod, void *aprod_user,
                    int32_t m, int32_t n, double damp, int32_t wantse,
                    double *u_dev, double *v_dev, double *w_dev, double *x_dev, double *se_dev,

@@ -42,7 +42,18 @@ class KernelTimes(C.Structure):
         ("aprod_ms", C.c_double), ("atprod_ms", C.c_double), ("update_ms", C.c_double), ("other_ms", C.c_double),
         ("aprod_launches", C.c_int64), ("atprod_launches", C.c_int64), ("update_launches", C.c_int64),
         ("other_launches", C.c_int64), ("total_launches", C.c_int64),
-        ("loop_ms", C.c_double), ("init_ms", C.c_double),
+        ("loop_ms", C.c_double), ("init_ms", C.c_double), ("iteration_launches", C.c_int64),
+    ]
+
+
+class PlanInfo(C.Structure):
+    """struct lsqr_b200_plan_info"""
+    _fields_ = [
+        ("nblocks", C.c_int64), ("ntiles", C.c_int64),
+        ("grid_ctas", C.c_int32), ("ctas_per_sm", C.c_int32), ("window_doubles", C.c_int32), ("balanced", C.c_int32),
+        ("windowed_fraction", C.c_double), ("imbalance", C.c_double),
+        ("span_median", C.c_int64), ("span_max", C.c_int64),
+        ("single_launch", C.c_int32), ("peer_exchange", C.c_int32),
     ]
 
 
@@ -104,6 +115,8 @@ def load() -> C.CDLL:
     L.lsqr_b200_ez_schedule.restype = C.c_int
     L.lsqr_b200_ez_schedule.argtypes = [vp, C.c_int32, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                                         C.POINTER(C.c_int32), C.POINTER(C.c_double)]
+    L.lsqr_b200_ez_plan.restype = C.c_int
+    L.lsqr_b200_ez_plan.argtypes = [vp, C.c_int32, C.POINTER(PlanInfo)]
     L.lsqr_b200_ez_get_csr_device.restype = C.c_int
     L.lsqr_b200_ez_get_csr_device.argtypes = [vp, C.c_int32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     L.lsqr_b200_ez_nnz.restype = C.c_int64

@@ -22,7 +22,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
          "-Xptxas", "-v", "--expt-relaxed-constexpr"]
-SOURCES = ["engine.cu", "build_csr.cu", "synth.cu", "spmv_stream.cu"]
+SOURCES = ["engine.cu", "build_csr.cu", "synth.cu"]
 
 
 def _deps(src: str) -> list[str]:

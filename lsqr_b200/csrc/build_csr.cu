@@ -98,6 +98,29 @@ copy_kernel(int64_t nnz, const int32_t *__restrict__ other, const double *__rest
     }
 }
 
+// Temporaries of the build: freed on every exit path (after the stream has drained, so that no kernel still
+// reads them); an early LSQRB_CUDA return therefore leaks nothing.
+struct TempPool {
+    cudaStream_t stream;
+    void *ptrs[8];
+    int n = 0;
+    explicit TempPool(cudaStream_t s) : stream(s) {}
+    template <typename T> cudaError_t alloc(T **out, size_t bytes)
+    {
+        void *p = nullptr;
+        cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
+        if (e == cudaSuccess) ptrs[n++] = p;
+        *out = static_cast<T *>(p);
+        return e;
+    }
+    ~TempPool()
+    {
+        if (n == 0) return;
+        cudaStreamSynchronize(stream);
+        for (int i = 0; i < n; ++i) cudaFree(ptrs[i]);
+    }
+};
+
 int bits_for(int64_t nkeys)
 {
     int b = 1;
@@ -111,8 +134,9 @@ int coo_validate(cudaStream_t stream, int32_t m, int32_t n, int64_t nnz,
                  const int32_t *d_irow, const int32_t *d_icol)
 {
     if (nnz == 0) return LSQR_B200_OK;
+    TempPool tmp(stream);
     int32_t *d_mm = nullptr;
-    LSQRB_CUDA(cudaMalloc(&d_mm, 4 * sizeof(int32_t)));
+    LSQRB_CUDA(tmp.alloc(&d_mm, 4 * sizeof(int32_t)));
     const int32_t init[4] = {INT32_MAX, INT32_MIN, INT32_MAX, INT32_MIN};
     LSQRB_CUDA(cudaMemcpyAsync(d_mm, init, sizeof init, cudaMemcpyHostToDevice, stream));
     minmax_kernel<<<grid_for(nnz), kT, 0, stream>>>(nnz, d_irow, d_mm);
@@ -120,7 +144,6 @@ int coo_validate(cudaStream_t stream, int32_t m, int32_t n, int64_t nnz,
     int32_t h[4];
     LSQRB_CUDA(cudaMemcpyAsync(h, d_mm, sizeof h, cudaMemcpyDeviceToHost, stream));
     LSQRB_CUDA(cudaStreamSynchronize(stream));
-    cudaFree(d_mm);
     // same order as the reference: irow first (:110), then icol (:111)
     if (h[1] > m) return LSQR_B200_ERR_IROW;
     if (h[3] > n) return LSQR_B200_ERR_ICOL;
@@ -140,6 +163,7 @@ int coo_to_csr_device(cudaStream_t stream, int64_t nkeys_one, int64_t nnz,
     out->block_rows = 0;
     int64_t nkeys = nkeys_one;
     const int32_t *d_key = d_key_in;
+    TempPool tmp(stream);
     int32_t *d_comp = nullptr;
     if (block_rows > 0 && nother > block_rows && nnz > 0) {
         const int64_t nb = (nother + block_rows - 1) / block_rows;
@@ -150,12 +174,11 @@ int coo_to_csr_device(cudaStream_t stream, int64_t nkeys_one, int64_t nnz,
         out->nblocks = nb;
         out->block_rows = block_rows;
         nkeys = nb * nkeys_one;
-        LSQRB_CUDA(cudaMalloc(&d_comp, sizeof(int32_t) * (size_t)nnz));
+        LSQRB_CUDA(tmp.alloc(&d_comp, sizeof(int32_t) * (size_t)nnz));
         composite_key_kernel<<<grid_for(nnz), kT, 0, stream>>>(nnz, d_key_in, d_other, (uint32_t)block_rows, (uint32_t)nkeys_one, d_comp);
         LSQRB_CUDA(cudaGetLastError());
         d_key = d_comp;
     }
-    struct CompGuard { int32_t *p; cudaStream_t s; ~CompGuard() { if (p) { cudaStreamSynchronize(s); cudaFree(p); } } } comp_guard{d_comp, stream};
     out->nrows = nkeys;
     out->nnz = nnz;
     out->was_sorted = 1;
@@ -176,20 +199,17 @@ int coo_to_csr_device(cudaStream_t stream, int64_t nkeys_one, int64_t nnz,
         void *d_tmp = nullptr;
         size_t tmp_bytes = 0;
         LSQRB_CUDA(cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, out->ptr, out->ptr, nkeys + 1, stream));
-        LSQRB_CUDA(cudaMalloc(&d_tmp, tmp_bytes ? tmp_bytes : 1));
+        LSQRB_CUDA(tmp.alloc(&d_tmp, tmp_bytes));
         LSQRB_CUDA(cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, out->ptr, out->ptr, nkeys + 1, stream));
-        LSQRB_CUDA(cudaStreamSynchronize(stream));
-        cudaFree(d_tmp);
     }
 
     // already grouped by key?  then the stable sort is the identity
     int *d_flag = nullptr, h_flag = 0;
-    LSQRB_CUDA(cudaMalloc(&d_flag, sizeof(int)));
+    LSQRB_CUDA(tmp.alloc(&d_flag, sizeof(int)));
     LSQRB_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), stream));
     unsorted_flag_kernel<<<grid_for(nnz), kT, 0, stream>>>(nnz, d_key, d_flag);
     LSQRB_CUDA(cudaMemcpyAsync(&h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, stream));
     LSQRB_CUDA(cudaStreamSynchronize(stream));
-    cudaFree(d_flag);
 
     iota_kernel<<<grid_for(nnz), kT, 0, stream>>>(nnz, out->perm);
     if (!h_flag) {
@@ -201,24 +221,20 @@ int coo_to_csr_device(cudaStream_t stream, int64_t nkeys_one, int64_t nnz,
 
     // stable LSD radix sort of (key, COO position); only the low bits_for(nkeys) bits are sorted
     uint32_t *d_keys_out = nullptr, *d_iota = nullptr;
-    LSQRB_CUDA(cudaMalloc(&d_keys_out, sizeof(uint32_t) * nz));
-    LSQRB_CUDA(cudaMalloc(&d_iota, sizeof(uint32_t) * nz));
+    LSQRB_CUDA(tmp.alloc(&d_keys_out, sizeof(uint32_t) * nz));
+    LSQRB_CUDA(tmp.alloc(&d_iota, sizeof(uint32_t) * nz));
     LSQRB_CUDA(cudaMemcpyAsync(d_iota, out->perm, sizeof(uint32_t) * nz, cudaMemcpyDeviceToDevice, stream));
     void *d_tmp = nullptr;
     size_t tmp_bytes = 0;
     const uint32_t *keys_in = reinterpret_cast<const uint32_t *>(d_key);
     LSQRB_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, keys_in, d_keys_out, d_iota, out->perm,
                                                nnz, 0, bits_for(nkeys), stream));
-    LSQRB_CUDA(cudaMalloc(&d_tmp, tmp_bytes ? tmp_bytes : 1));
+    LSQRB_CUDA(tmp.alloc(&d_tmp, tmp_bytes));
     LSQRB_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, keys_in, d_keys_out, d_iota, out->perm,
                                                nnz, 0, bits_for(nkeys), stream));
     gather_kernel<<<grid_for(nnz), kT, 0, stream>>>(nnz, out->perm, d_other, d_a, out->idx, out->val);
     LSQRB_CUDA(cudaGetLastError());
-    LSQRB_CUDA(cudaStreamSynchronize(stream));
-    cudaFree(d_tmp);
-    cudaFree(d_keys_out);
-    cudaFree(d_iota);
-    return LSQR_B200_OK;
+    return LSQR_B200_OK;   // (the pool drains the stream and frees the temporaries)
 }
 
 void csr_free(Csr *c)

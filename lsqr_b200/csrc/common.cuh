@@ -41,6 +41,18 @@ constexpr int kTraceSlots = 1024;
 // lives here, is advanced by the last block of the kernel that produces its inputs, and never
 // visits the host inside the loop.
 // ---------------------------------------------------------------------------------------------
+// Scaled sum of squares (J. L. Blue's three-accumulator scheme, the algorithm of LAPACK 3.10's dnrm2): values in
+// the mid range are squared directly, very large ones are scaled down and very small ones scaled up before
+// squaring, so sqrt(sum x^2) neither overflows nor underflows -- the single-pass, order-independent (hence
+// parallel and deterministic) counterpart of the reference's serial scaled recurrence src/lsqrblas.f90:136-154.
+struct Ssq {
+    double med, big, sml;
+};
+constexpr double kBlueSsml = 4.4989137945431964e+161;   // 2^537 : scale of the small accumulator
+constexpr double kBlueSbig = 1.1113793747425387e-162;   // 2^-538: scale of the big accumulator
+constexpr unsigned kBlueExpLo = 512u;                   // biased exponent of 2^-511 (tsml)
+constexpr unsigned kBlueExpSpan = 996u;                 // mid range: 2^-511 <= |x| < 2^486 (tbig)
+
 struct DevState {
     // configuration (set by the host before the solve)
     double damp, atol, btol, ctol;
@@ -54,8 +66,8 @@ struct DevState {
     double ca_mat, ca_vec;   // Aprod : u' = ca_mat * (A v)  + ca_vec * u
     double ct_mat, ct_vec;   // Atprod: v' = ct_mat * (A'u') + ct_vec * v
     double t1, t2, t3;       // update: x += t1 w ; w' = inv_alpha * v' + t2 w ; se += (t3 w)^2
-    double wnorm2;           // sum(w^2) of the current w (gives dknorm = |t3| sqrt(wnorm2))
-    // coefficients of the operator-hook path, which keeps u and v normalised like the reference:
+    double wnorm;            // ||w|| of the current w (gives dknorm = |t3| wnorm)
+    // coefficients of the reference-structure path, which keeps u and v normalised like the reference:
     // dscal(u,-alpha) | dscal(u,1/beta) | dscal(v,-beta) | dscal(v,1/alpha)  (src/lsqr.f90:681,692,693,697)
     double g_c0, g_c1, g_c2, g_c3;
 
@@ -67,21 +79,30 @@ struct DevState {
 
     int itn, istop, nstop, maxdx;
     int done;                // set after the x/w update of the stopping iteration
-    int upd_pending;         // the x/w update of iteration rec.itn has not been applied yet (deferred-update engine)
+    int hook_lazy;           // operator-hook path: u, v are kept unnormalised (fused hook loop)
+
+    // multi-GPU exchange (peer-memory path): iteration epoch the flags are compared with, error latch of a timed-out wait
+    unsigned int epoch;
+    int comm_error;
+    Ssq usq_local, vsq_local, wsq_local;   // this rank's partial sums of squares of u', v' (slice), w' (slice)
 
     // scalars of the iteration whose x/w update is still outstanding; published to the host ring
     // (with x(1)) by step_after_update
     lsqr_b200_iter_record rec;
 
-    // completion counters of the "last block finishes the reduction" pattern
+    // completion counters of the "last block finishes the reduction" pattern, and "an exceptional (scaled) value was
+    // seen" flags of the same slots
     unsigned int counter[4];
+    unsigned int exc_flag[4];
+    // multi-block SpMV launches: warps that have finished block b (bounds the drift between the warps of one launch)
+    unsigned int blk_done[64];
 
-    // partial sums of the reducing kernels (fixed slot per block => deterministic final sum)
-    double partial[kMaxPartials];
-    double partial2[kMaxPartials];   // second simultaneous reduction (fused Atprod + deferred update)
+    // partial sums of the reducing kernels (fixed slot per block => deterministic final sum): [0] mid-range squares,
+    // [1] scaled big, [2] scaled small
+    double partial[3][kMaxPartials];
+    double partial2[3][kMaxPartials];   // the x/w update runs next to the following Aprod: its own slots
 
-    // trace[0]: first instruction of block 0, trace[1]: last block has the final sums, trace[2]: scalar step done,
-    // trace[3]: (fused Atprod + update only) between step_after_update and step_after_atprod
+    // trace[0]: first instruction of block 0, trace[1]: last block has the final sums, trace[2]: scalar step done
     unsigned long long trace[4][kTraceSlots];
 };
 
@@ -97,6 +118,43 @@ __device__ __forceinline__ double d2norm(double a, double b)
     double p = a / scale, q = b / scale;
     return scale * sqrt(p * p + q * q);
 }
+
+// ---- Blue's scaled sum of squares -----------------------------------------------------------------------------
+// Rare path of ssq_add: r is zero, subnormal / tiny, huge, Inf or NaN.  exc[0] / exc[stride] are the calling thread's
+// private big / small accumulators (shared memory: they cost no registers in the kernels' hot loops).
+static __device__ __noinline__ void ssq_add_rare(double &med, double *exc, int stride, double r, unsigned e)
+{
+    if (e == 0x7ffu) { med += r * r; return; }               // Inf / NaN propagate
+    if (e > kBlueExpLo + kBlueExpSpan) { const double t = r * kBlueSbig; exc[0] += t * t; return; }
+    if (r != 0.0) { const double t = r * kBlueSsml; exc[stride] += t * t; }
+}
+__device__ __forceinline__ void ssq_add(double &med, double *exc, int stride, double r)
+{
+    const unsigned e = ((unsigned)__double2hiint(r) >> 20) & 0x7ffu;
+    if (e - kBlueExpLo <= kBlueExpSpan) med += r * r;        // the common case: one subtract + compare
+    else ssq_add_rare(med, exc, stride, r, e);
+}
+// sqrt(sum x^2) from the three accumulators (the combination step of LAPACK 3.10 dnrm2)
+__device__ __host__ inline double ssq_norm(const Ssq &a)
+{
+    double med = a.med;
+    if (a.big > 0.0) {
+        double big = a.big;
+        if (med > 0.0 || med != med) big += (med * kBlueSbig) * kBlueSbig;
+        return sqrt(big) / kBlueSbig;
+    }
+    if (a.sml > 0.0) {
+        if (med > 0.0 || med != med) {
+            med = sqrt(med);
+            const double sm = sqrt(a.sml) / kBlueSsml;
+            const double ymin = med < sm ? med : sm, ymax = med < sm ? sm : med;
+            return ymax * sqrt(1.0 + (ymin / ymax) * (ymin / ymax));
+        }
+        return sqrt(a.sml) / kBlueSsml;
+    }
+    return sqrt(med);
+}
+__device__ __host__ inline Ssq ssq_sum(const Ssq &a, const Ssq &b) { return Ssq{a.med + b.med, a.big + b.big, a.sml + b.sml}; }
 
 __device__ __forceinline__ unsigned long long globaltimer_ns()
 {

@@ -1,570 +1,10 @@
 // engine.cu -- host driver + C ABI of the B200 LSQR engine (include/lsqr_b200.h).
 //
-// One handle owns: CSR(A) and CSR(A') in HBM, the work vectors u(m), v,w,x,(se)(n), a
+// One handle owns: CSR(A) and CSR(A') in HBM with their work plans, the work vectors u(m), v,w,x,(se)(n), a
 // device-resident scalar state (DevState), and a ring of per-iteration records in pinned mapped
 // host memory.  The host never computes a scalar of the recurrence: it enqueues batches of
 // iterations (CUDA graph), and reads the records to learn when the device decided to stop.
-#include <dlfcn.h>
-#include <nccl.h>   // types only; the library is dlopen'ed so single-GPU use has no NCCL dependency
-
-#include <algorithm>
-#include <cfloat>
-#include <cmath>
-#include <cstdlib>
-#include <cstring>
-#include <mutex>
-#include <queue>
-#include <vector>
-
-#include "build_csr.h"
-#include "kernels.cuh"
-#include "spmv_stream.cuh"
-#include "spmv_warp.cuh"
-
-namespace lsqrb {
-
-// ---------------------------------------------------------------------------------------------
-// errors
-// ---------------------------------------------------------------------------------------------
-static thread_local std::string g_last_error;
-void set_last_error(const std::string &msg) { g_last_error = msg; }
-
-static bool is_device_ptr(const void *p)
-{
-    if (!p) return false;
-    cudaPointerAttributes at;
-    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
-        cudaGetLastError();
-        return false;
-    }
-    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
-}
-
-static int env_int(const char *name, int dflt)
-{
-    const char *v = getenv(name);
-    return (v && *v) ? atoi(v) : dflt;
-}
-
-// ---------------------------------------------------------------------------------------------
-// NCCL, loaded at run time
-// ---------------------------------------------------------------------------------------------
-struct NcclApi {
-    void *lib = nullptr;
-    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
-    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
-    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
-    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
-    const char *(*GetErrorString)(ncclResult_t) = nullptr;
-};
-
-static NcclApi *nccl_api()
-{
-    static NcclApi api;
-    static std::once_flag once;
-    std::call_once(once, [] {
-        // Prefer a copy that is already in the process (torch loads its bundled libnccl.so.2).
-        void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
-        if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
-        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
-        if (!h) return;
-        api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(h, "ncclGetUniqueId");
-        api.CommInitRank = (decltype(api.CommInitRank))dlsym(h, "ncclCommInitRank");
-        api.AllReduce = (decltype(api.AllReduce))dlsym(h, "ncclAllReduce");
-        api.CommDestroy = (decltype(api.CommDestroy))dlsym(h, "ncclCommDestroy");
-        api.GetErrorString = (decltype(api.GetErrorString))dlsym(h, "ncclGetErrorString");
-        if (api.GetUniqueId && api.CommInitRank && api.AllReduce && api.CommDestroy) api.lib = h;
-    });
-    return api.lib ? &api : nullptr;
-}
-
-#define LSQRB_NCCL(call)                                                                          \
-    do {                                                                                          \
-        ncclResult_t r__ = (call);                                                                \
-        if (r__ != ncclSuccess) {                                                                 \
-            NcclApi *a__ = nccl_api();                                                            \
-            set_last_error(std::string(#call) + ": " +                                            \
-                           ((a__ && a__->GetErrorString) ? a__->GetErrorString(r__) : "nccl error")); \
-            return LSQR_B200_ERR_NCCL;                                                            \
-        }                                                                                         \
-    } while (0)
-
-// ---------------------------------------------------------------------------------------------
-// Fortran-style number formatting for the nout log (1PEw.d)
-// ---------------------------------------------------------------------------------------------
-static std::string fe(int w, int d, double v)
-{
-    char tmp[64];
-    snprintf(tmp, sizeof tmp, "%.*E", d, v);
-    std::string s(tmp);
-    size_t e = s.find('E');
-    if (e != std::string::npos && s.size() - (e + 2) >= 3) s.erase(e, 1);   // E+100 -> +100
-    if ((int)s.size() > w) return std::string((size_t)w, '*');
-    return std::string((size_t)w - s.size(), ' ') + s;
-}
-
-// ---------------------------------------------------------------------------------------------
-// Work: stream + device state + record ring, shared by the ez path and the operator-hook path
-// ---------------------------------------------------------------------------------------------
-struct Work {
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    bool own_stream = false;
-    DevState *st = nullptr;                       // device
-    DevState h;                                   // host mirror (header part only is copied)
-    lsqr_b200_iter_record *ring_h = nullptr;      // pinned, mapped
-    lsqr_b200_iter_record *ring_d = nullptr;      // device alias of ring_h
-    int max_grid = kNumSMs * 8;
-    int stream_grid = kNumSMs * 3;   // cap on the persistent CTAs of the tile-streamed kernels
-    int sms = kNumSMs;
-    int64_t launches = 0;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-
-    int init(int dev, void *user_stream)
-    {
-        int count = 0;
-        if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
-            cudaGetLastError();
-            set_last_error("no CUDA device is visible; this engine has no CPU path");
-            return LSQR_B200_ERR_NO_DEVICE;
-        }
-        if (dev < 0) LSQRB_CUDA(cudaGetDevice(&dev));
-        if (dev >= count) { set_last_error("device ordinal out of range"); return LSQR_B200_ERR_ARG; }
-        device = dev;
-        LSQRB_CUDA(cudaSetDevice(device));
-        if (user_stream) {
-            stream = (cudaStream_t)user_stream;
-        } else {
-            LSQRB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-            own_stream = true;
-        }
-        LSQRB_CUDA(cudaMalloc(&st, sizeof(DevState)));
-        LSQRB_CUDA(cudaMemsetAsync(st, 0, sizeof(DevState), stream));
-        LSQRB_CUDA(cudaHostAlloc(&ring_h, sizeof(lsqr_b200_iter_record) * kRingSize, cudaHostAllocMapped));
-        LSQRB_CUDA(cudaHostGetDevicePointer(&ring_d, ring_h, 0));
-        for (auto &e : ev) LSQRB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDefault));
-        LSQRB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
-        sms = std::max(1, sms);
-        max_grid = std::min(kMaxPartials, std::max(1, sms) * env_int("LSQR_B200_BLOCKS_PER_SM", 8));
-        stream_grid = std::min(kMaxPartials, std::max(1, sms) * env_int("LSQR_B200_STREAM_CTAS_PER_SM", 3));
-        return LSQR_B200_OK;
-    }
-
-    void destroy()
-    {
-        if (st) cudaFree(st);
-        if (ring_h) cudaFreeHost(ring_h);
-        for (auto &e : ev) if (e) cudaEventDestroy(e);
-        if (own_stream && stream) cudaStreamDestroy(stream);
-        st = nullptr; ring_h = nullptr; stream = nullptr;
-    }
-
-    int grid_for(int64_t items, int per_block) const
-    {
-        int64_t b = (items + per_block - 1) / per_block;
-        if (b < 1) b = 1;
-        return (int)std::min<int64_t>(b, max_grid);
-    }
-
-    // reset the scalar state for a new solve (src/lsqr.f90:597-617)
-    int reset_state(double damp, double atol, double btol, double conlim, int itnlim, int wantse, int dist)
-    {
-        memset(&h, 0, offsetof(DevState, partial));
-        h.damp = damp; h.atol = atol; h.btol = btol;
-        h.ctol = conlim > 0.0 ? 1.0 / conlim : 0.0;
-        h.itnlim = itnlim; h.wantse = wantse; h.damped = damp > 0.0; h.dist = dist;
-        h.tr_on = env_int("LSQR_B200_TRACE", 0); h.tr_n = 0;
-        h.cs2 = -1.0;
-        h.inv_alpha = h.inv_beta = 1.0;
-        h.g_c0 = h.g_c1 = h.g_c2 = h.g_c3 = 1.0;
-        LSQRB_CUDA(cudaMemcpyAsync(st, &h, offsetof(DevState, partial), cudaMemcpyHostToDevice, stream));
-        for (int i = 0; i < kRingSize; ++i) ring_h[i].itn = -1.0;
-        return LSQR_B200_OK;
-    }
-
-    int fetch_state()
-    {
-        LSQRB_CUDA(cudaMemcpyAsync(&h, st, offsetof(DevState, partial), cudaMemcpyDeviceToHost, stream));
-        LSQRB_CUDA(cudaStreamSynchronize(stream));
-        if (h.tr_on) dump_trace();
-        return LSQR_B200_OK;
-    }
-
-    // LSQR_B200_TRACE=1: timeline of the fused kernels of the last solve, to stderr (microseconds)
-    void dump_trace()
-    {
-        const int n = std::min(h.tr_n, kTraceSlots);
-        std::vector<unsigned long long> t((size_t)4 * kTraceSlots);
-        if (cudaMemcpy(t.data(), (const char *)st + offsetof(DevState, trace), sizeof(unsigned long long) * t.size(),
-                       cudaMemcpyDeviceToHost) != cudaSuccess) return;
-        fprintf(stderr, "[lsqr_b200 trace] %d fused kernels: idx start_us busy_us step_us gap_to_next_us upd_step_us\n", n);
-        for (int k = 0; k < n; ++k) {
-            const double t0 = (double)(t[k] - t[0]) * 1e-3;
-            const double busy = (double)(t[kTraceSlots + k] - t[k]) * 1e-3;
-            const double step = (double)(t[2 * kTraceSlots + k] - t[kTraceSlots + k]) * 1e-3;
-            const double gap = k + 1 < n ? (double)(t[k + 1] - t[2 * kTraceSlots + k]) * 1e-3 : 0.0;
-            const unsigned long long tm = t[3 * kTraceSlots + k];
-            const double ustep = tm > t[kTraceSlots + k] && tm <= t[2 * kTraceSlots + k] ? (double)(tm - t[kTraceSlots + k]) * 1e-3 : 0.0;
-            if (k < 40 || k >= n - 4) fprintf(stderr, "[lsqr_b200 trace] %4d %10.2f %8.2f %6.2f %6.2f %6.2f\n", k, t0, busy, step, gap, ustep);
-        }
-    }
-};
-
-// ---------------------------------------------------------------------------------------------
-// SpMV launch dispatch
-// ---------------------------------------------------------------------------------------------
-static int pick_lanes(const Csr &M, const char *env_name)
-{
-    int forced = env_int(env_name, 0);
-    if (forced == 1 || forced == 2 || forced == 4 || forced == 8 || forced == 16 || forced == 32) return forced;
-    const double mean = M.nrows > 0 ? (double)M.nnz / (double)M.nrows : 1.0;
-    int lanes = 2;
-    while (lanes < 32 && lanes * 3 < mean) lanes <<= 1;   // about three passes over a mean row
-    return lanes;
-}
-
-static inline CsrView view_of(const Csr &M) { return CsrView{M.ptr, M.idx, M.val, M.nrows}; }
-// block b of a row-blocked transpose (an ordinary CSR over nkeys rows whose entries start at ptr[b*nkeys])
-static inline CsrView view_of_block(const Csr &M, int64_t b) { return CsrView{M.ptr + b * M.nkeys, M.idx, M.val, M.nkeys}; }
-
-template <int EPI>
-static int launch_spmv(Work &wk, const CsrView &V, int lanes, const double *x, double *out, double *aux, int check_done = 0)
-{
-    const int grid = wk.grid_for(V.nrows, kThreads / lanes);
-    switch (lanes) {
-    case 1:  spmv_rowgroup_kernel<1, EPI><<<grid, kThreads, 0, wk.stream>>>(V, x, out, wk.st, aux, check_done); break;
-    case 2:  spmv_rowgroup_kernel<2, EPI><<<grid, kThreads, 0, wk.stream>>>(V, x, out, wk.st, aux, check_done); break;
-    case 4:  spmv_rowgroup_kernel<4, EPI><<<grid, kThreads, 0, wk.stream>>>(V, x, out, wk.st, aux, check_done); break;
-    case 8:  spmv_rowgroup_kernel<8, EPI><<<grid, kThreads, 0, wk.stream>>>(V, x, out, wk.st, aux, check_done); break;
-    case 16: spmv_rowgroup_kernel<16, EPI><<<grid, kThreads, 0, wk.stream>>>(V, x, out, wk.st, aux, check_done); break;
-    default: spmv_rowgroup_kernel<32, EPI><<<grid, kThreads, 0, wk.stream>>>(V, x, out, wk.st, aux, check_done); break;
-    }
-    wk.launches++;
-    LSQRB_CUDA(cudaGetLastError());
-    return LSQR_B200_OK;
-}
-
-// ---- variant 2: tile-streamed kernels (spmv_stream.cuh) -----------------------------------------
-struct TileMapOwner {
-    uint2 *tiles = nullptr;
-    int ntiles = 0;
-    uint32_t tile = kTile;   // nominal work units per tile (stored entries + row_w per row)
-    uint32_t row_w = 0;      // kind 3: weight of a row in the tile cut, so that long runs of empty rows are split too
-    int kind = 2;            // 2 = CTA tiles of the TMA-streamed kernel, 3 = warp tiles of the segmented kernel
-    // kind 3, very uneven rows only: balanced tile schedule (see TileMap::order); the grid is then the full persistent grid
-    uint32_t *order = nullptr;
-    int nslots = 0;
-    int ctas = 0;            // kind 3: persistent grid this map was cut for (0 = sms * CTAs per SM); the chunk launches
-                             // that overlap an all-reduce leave a few SMs to the collective's own kernels
-    double imbalance = 1.0;  // most loaded warp / mean load under the schedule in use (diagnostic)
-};
-
-static void tile_map_free(TileMapOwner &mp)
-{
-    if (mp.tiles) cudaFree(mp.tiles);
-    if (mp.order) cudaFree(mp.order);
-    mp.tiles = nullptr; mp.order = nullptr;
-}
-
-// Variant 3 sizes its tiles so that every warp of the persistent grid gets the same number of them
-// (k tiles of ~8K entries or less each): a small matrix is cut into exactly one tile per warp.
-static uint32_t warp_tile_size(int ctas, int64_t nnz)
-{
-    const int forced = env_int("LSQR_B200_WARP_TILE", 0);
-    if (forced >= 128) return (uint32_t)forced;
-    const int64_t nwarps = (int64_t)ctas * kWWarps;
-    const int64_t k = std::max<int64_t>(1, (nnz + nwarps * 8192 - 1) / (nwarps * 8192));
-    const int64_t t = (nnz + nwarps * k - 1) / (nwarps * k);
-    return (uint32_t)std::max<int64_t>(512, (t + 3) & ~(int64_t)3);
-}
-
-static inline int64_t tile_work(const TileMapOwner &mp, const CsrView &V, int64_t nnz) { return nnz + (int64_t)mp.row_w * V.nrows; }
-
-static int build_tiles(Work &wk, const CsrView &V, int64_t nnz, uint32_t tile, TileMapOwner *out)
-{
-    if (out->tiles) { cudaFree(out->tiles); out->tiles = nullptr; }
-    out->tile = tile;
-    const int64_t nt = std::max<int64_t>(1, (tile_work(*out, V, nnz) + tile - 1) / tile);
-    out->ntiles = (int)nt;
-    LSQRB_CUDA(cudaMalloc(&out->tiles, sizeof(uint2) * (size_t)(nt + 1)));
-    build_tiles_kernel<<<(int)((nt + 1 + 255) / 256), 256, 0, wk.stream>>>(V.ptr, V.nrows, (int)nt, tile, out->row_w, out->tiles);
-    LSQRB_CUDA(cudaGetLastError());
-    return LSQR_B200_OK;
-}
-
-// Cost of a warp tile in units of one 128-entry chunk: its chunks plus its row-window reloads.
-static inline double tile_cost(const uint2 &a, const uint2 &b)
-{
-    if (a.x == b.x) return 0.0;   // no row starts here: skipped by the kernel
-    return std::ceil((double)(b.y - a.y + 3u) / 128.0) + 0.25 * std::ceil((double)(b.x - a.x) / 32.0) + 1.0;
-}
-
-// Tiles are row-aligned, so a row of 10 000 entries makes a tile of more than 10 000: with round-robin assignment the
-// most loaded warp of a power-law matrix (C4) carries ~1.5x the mean and the whole grid waits for it.  When that
-// happens the matrix is re-cut into smaller tiles and the tiles are dealt to the warps by LPT (largest first, to the
-// least loaded warp).  The schedule is a pure function of ptr[], so results stay reproducible run to run.
-static int balance_tile_map(Work &wk, const CsrView &V, int64_t nnz, TileMapOwner *out)
-{
-    const int nw = out->ctas * kWWarps;
-    std::vector<uint2> t;
-    std::vector<double> cost;
-    double total = 0.0;
-    auto fetch = [&]() -> int {   // tile bounds and costs of the current cut
-        t.resize((size_t)out->ntiles + 1);
-        LSQRB_CUDA(cudaMemcpyAsync(t.data(), out->tiles, sizeof(uint2) * t.size(), cudaMemcpyDeviceToHost, wk.stream));
-        LSQRB_CUDA(cudaStreamSynchronize(wk.stream));
-        cost.resize((size_t)out->ntiles);
-        total = 0.0;
-        for (int i = 0; i < out->ntiles; ++i) total += (cost[(size_t)i] = tile_cost(t[(size_t)i], t[(size_t)i + 1]));
-        return LSQR_B200_OK;
-    };
-    LSQRB_TRY(fetch());
-    {   // round robin: tile i belongs to warp i mod (warps of the grid)
-        const int gw = std::max(1, std::min((out->ntiles + kWWarps - 1) / kWWarps, out->ctas)) * kWWarps;
-        std::vector<double> load((size_t)gw, 0.0);
-        for (int i = 0; i < out->ntiles; ++i) load[(size_t)(i % gw)] += cost[(size_t)i];
-        out->imbalance = total > 0 ? *std::max_element(load.begin(), load.end()) / (total / nw) : 1.0;
-    }
-    if (env_int("LSQR_B200_BALANCE", 1) == 0 || tile_work(*out, V, nnz) <= (int64_t)nw * 512) return LSQR_B200_OK;   // nothing to deal out
-    if (out->imbalance <= 1.0 + 1e-3 * env_int("LSQR_B200_BALANCE_PERMILLE", 60)) return LSQR_B200_OK;
-
-    // finer tiles pack better (the long rows stay as long as they are)
-    const uint32_t fine = (uint32_t)std::max(512, std::min<int>((int)out->tile / 4, env_int("LSQR_B200_BALANCE_TILE", 2048))) & ~3u;
-    if (fine < out->tile) { LSQRB_TRY(build_tiles(wk, V, nnz, fine, out)); LSQRB_TRY(fetch()); }
-    const int nt = out->ntiles;
-    if (nt <= nw) return LSQR_B200_OK;
-    std::vector<int> ids;
-    ids.reserve((size_t)nt);
-    for (int i = 0; i < nt; ++i) if (cost[(size_t)i] > 0.0) ids.push_back(i);
-    std::stable_sort(ids.begin(), ids.end(), [&](int a, int b) { return cost[(size_t)a] > cost[(size_t)b]; });
-    typedef std::pair<double, int> Slot;   // (load, warp): the least loaded warp first, ties by warp number
-    std::priority_queue<Slot, std::vector<Slot>, std::greater<Slot>> heap;
-    for (int w = 0; w < nw; ++w) heap.push(Slot(0.0, w));
-    std::vector<std::vector<uint32_t>> lists((size_t)nw);
-    for (int id : ids) {
-        Slot sl = heap.top(); heap.pop();
-        lists[(size_t)sl.second].push_back((uint32_t)id);
-        sl.first += cost[(size_t)id];
-        heap.push(sl);
-    }
-    size_t depth = 0;
-    double worst = 0.0;
-    while (!heap.empty()) { worst = std::max(worst, heap.top().first); heap.pop(); }
-    for (auto &l : lists) { std::sort(l.begin(), l.end()); depth = std::max(depth, l.size()); }   // each warp walks its tiles in matrix order
-    std::vector<uint32_t> order(depth * (size_t)nw, kNoTile);
-    for (int w = 0; w < nw; ++w)
-        for (size_t k = 0; k < lists[(size_t)w].size(); ++k) order[k * (size_t)nw + (size_t)w] = lists[(size_t)w][k];
-    out->nslots = (int)order.size();
-    out->imbalance = total > 0 ? worst / (total / nw) : 1.0;
-    LSQRB_CUDA(cudaMalloc(&out->order, sizeof(uint32_t) * std::max<size_t>(order.size(), 1)));
-    LSQRB_CUDA(cudaMemcpyAsync(out->order, order.data(), sizeof(uint32_t) * order.size(), cudaMemcpyHostToDevice, wk.stream));
-    LSQRB_CUDA(cudaStreamSynchronize(wk.stream));
-    return LSQR_B200_OK;
-}
-
-// V: a whole CSR, or one block of a row-blocked transpose (nnz = its number of stored entries)
-static int build_tile_map(Work &wk, const CsrView &V, int64_t nnz, int kind, TileMapOwner *out, int reserve_sms = 0)
-{
-    out->kind = kind;
-    out->ctas = std::max(1, wk.sms - reserve_sms) * kWMinBlocks;
-    // A row costs about as much as 4 stored entries (its share of a window reload and its epilogue).  Without the row
-    // term a block of a row-blocked banded A' -- half of whose rows are empty -- puts a million empty rows into ONE
-    // tile, i.e. one warp (measured: C3 full size, Atprod 55 ms instead of 1.4 ms).
-    out->row_w = kind == 3 ? (uint32_t)std::max(0, env_int("LSQR_B200_TILE_ROW_WEIGHT", 4)) : 0u;
-    LSQRB_TRY(build_tiles(wk, V, nnz, kind == 3 ? warp_tile_size(out->ctas, tile_work(*out, V, nnz)) : (uint32_t)kTile, out));
-    if (kind == 3) LSQRB_TRY(balance_tile_map(wk, V, nnz, out));
-    return LSQR_B200_OK;
-}
-
-// Opt in to the large dynamic shared memory window and the maximum carve-out, and measure how many
-// CTAs of this instantiation are co-resident per SM: the persistent grid is sized to exactly that.
-template <int EPI>
-static int stream_kernel_prepare(int *ctas_per_sm)
-{
-    static int occ = 0;
-    if (occ == 0) {
-        LSQRB_CUDA(cudaFuncSetAttribute(spmv_stream_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStreamSmem));
-        LSQRB_CUDA(cudaFuncSetAttribute(spmv_stream_kernel<EPI>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        int n = 0;
-        LSQRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, spmv_stream_kernel<EPI>, kStreamThreads, kStreamSmem));
-        occ = std::max(1, n);
-        if (env_int("LSQR_B200_VERBOSE", 0))
-            fprintf(stderr, "[lsqr_b200] spmv_stream_kernel<%d>: %d CTAs/SM, %zu B dynamic smem\n", EPI, occ, kStreamSmem);
-    }
-    *ctas_per_sm = occ;
-    return LSQR_B200_OK;
-}
-
-struct StreamExtra {   // operands of the fused deferred update
-    double *ux = nullptr, *uw = nullptr, *use = nullptr;
-    int check_done = 0;
-};
-
-template <int EPI>
-static int launch_stream(Work &wk, const CsrView &V, const TileMapOwner &map, const double *x, double *out, double *aux,
-                         const StreamExtra &ex = StreamExtra())
-{
-    StreamArgs a;
-    a.A = V;
-    a.map = TileMap{map.tiles, map.ntiles, map.order, map.nslots};
-    a.x = x; a.out = out; a.st = wk.st; a.aux = aux;
-    a.ux = ex.ux; a.uw = ex.uw; a.use = ex.use;
-    a.ring = wk.ring_d;
-    a.out_aligned16 = ((uintptr_t)out & 15u) == 0;
-    a.check_done = ex.check_done;
-    if (map.kind == 3) {
-        const int ctas = map.ctas > 0 ? map.ctas : wk.sms * kWMinBlocks;
-        const int grid = map.order ? ctas : std::max(1, std::min((map.ntiles + kWWarps - 1) / kWWarps, ctas));
-        spmv_warp_kernel<EPI><<<grid, kWThreads, 0, wk.stream>>>(a);
-    } else {
-        int occ = 1;
-        LSQRB_TRY(stream_kernel_prepare<EPI>(&occ));
-        const int grid = std::max(1, std::min(map.ntiles, std::min(wk.stream_grid, wk.sms * occ)));
-        spmv_stream_kernel<EPI><<<grid, kStreamThreads, kStreamSmem, wk.stream>>>(a);
-    }
-    wk.launches++;
-    LSQRB_CUDA(cudaGetLastError());
-    return LSQR_B200_OK;
-}
-
-static inline int vec_ok(const void *a, const void *b, const void *c, const void *d)
-{
-    auto al = [](const void *p) { return p == nullptr || ((uintptr_t)p & 15u) == 0; };
-    return al(a) && al(b) && al(c) && al(d);
-}
-
-template <bool LAZY>
-static int launch_update(Work &wk, int64_t n, double *x, double *w, const double *v, double *se, bool wantse)
-{
-    const int grid = wk.grid_for((n + 1) / 2, kThreads);
-    const int vok = vec_ok(x, w, v, wantse ? se : nullptr);
-    if (wantse) xw_update_kernel<true, LAZY><<<grid, kThreads, 0, wk.stream>>>(n, x, w, v, se, wk.st, wk.ring_d, vok);
-    else        xw_update_kernel<false, LAZY><<<grid, kThreads, 0, wk.stream>>>(n, x, w, v, se, wk.st, wk.ring_d, vok);
-    wk.launches++;
-    LSQRB_CUDA(cudaGetLastError());
-    return LSQR_B200_OK;
-}
-
-// record 0 of the log (src/lsqr.f90:666-671): written once the first alpha, beta are known
-__global__ void record0_kernel(DevState *st, volatile lsqr_b200_iter_record *ring)
-{
-    volatile lsqr_b200_iter_record *r = ring;
-    r->istop = (double)st->istop;
-    r->x1 = 0.0;
-    r->rnorm = st->rnorm;
-    r->test1 = 1.0;
-    r->test2 = st->beta > 0.0 ? st->alpha / st->beta : 0.0;
-    r->anorm = 0.0; r->acond = 0.0; r->phi = 0.0; r->dknorm = 0.0; r->dxk = 0.0; r->alfopt = 0.0;
-    r->alpha = st->alpha; r->beta = st->beta; r->xnorm = 0.0; r->arnorm = st->arnorm;
-    __threadfence_system();
-    r->itn = 0.0;
-}
-
-// ---------------------------------------------------------------------------------------------
-// nout log reconstruction on the host (formats of src/lsqr.f90:589-595,655-671,827-829,872-880)
-// ---------------------------------------------------------------------------------------------
-struct LogCtx {
-    lsqr_b200_log_fn log = nullptr;  void *log_user = nullptr;
-    lsqr_b200_iter_fn iter = nullptr; void *iter_user = nullptr;
-    int64_t m = 0, n = 0;
-    double damp = 0, atol = 0, btol = 0, conlim = 0, ctol = 0;
-    int itnlim = 0, wantse = 0;
-    double bnorm = 0;
-
-    void line(const std::string &s) const { if (log) log(log_user, s.c_str()); }
-
-    void header() const
-    {
-        if (!log) return;
-        char buf[160];
-        line(""); line("");
-        line(" Enter LSQR.       Least-squares solution of  Ax = b");
-        snprintf(buf, sizeof buf, " The matrix  A  has%7lld rows   and%7lld columns", (long long)m, (long long)n);
-        line(buf);
-        line(" damp   =" + fe(22, 14, damp) + "   wantse =" + std::string(9, ' ') + (wantse ? "T" : "F"));
-        line(" atol   =" + fe(10, 2, atol) + std::string(15, ' ') + "conlim =" + fe(10, 2, conlim));
-        snprintf(buf, sizeof buf, "%10d", itnlim);
-        line(" btol   =" + fe(10, 2, btol) + std::string(15, ' ') + "itnlim =" + buf);
-    }
-
-    void iter_line(const lsqr_b200_iter_record &r, int nvals) const
-    {
-        static const int w[10] = {17, 17, 10, 10, 10, 10, 9, 8, 8, 8};
-        static const int d[10] = {9, 9, 2, 2, 2, 2, 1, 1, 1, 1};
-        const double vals[10] = {r.x1, r.rnorm, r.test1, r.test2, r.anorm, r.acond, r.phi, r.dknorm, r.dxk, r.alfopt};
-        char buf[16];
-        snprintf(buf, sizeof buf, "%6d", (int)r.itn);
-        std::string s(buf);
-        for (int k = 0; k < nvals; ++k) s += fe(w[k], d[k], vals[k]);
-        line(s);
-    }
-
-    void record(const lsqr_b200_iter_record &r)
-    {
-        if (iter) iter(iter_user, &r);
-        if (!log) return;
-        const int itn = (int)r.itn;
-        if (itn == 0) {
-            bnorm = r.beta;
-            line(""); line("");
-            if (damp > 0.0) line("   Itn       x(1)           Function     Compatible   LS     Norm Abar Cond Abar");
-            else            line("   Itn       x(1)           Function     Compatible   LS        Norm A    Cond A");
-            line(std::string(80, ' ') + "    phi    dknorm   dxk  alfa_opt");
-            iter_line(r, 4);
-            line("");
-            return;
-        }
-        const double test3 = 1.0 / r.acond;
-        const double rtol = btol + atol * r.anorm * r.xnorm / bnorm;
-        const bool print_iter = (n <= 40) || (itn <= 10) || (itn >= itnlim - 10) || (itn % 10 == 0) ||
-                                (test3 <= 2.0 * ctol) || (r.test2 <= 10.0 * atol) ||
-                                (r.test1 <= 10.0 * rtol) || (r.istop != 0.0);
-        if (print_iter) iter_line(r, 10);
-    }
-
-    void footer(int istop, const DevState &h) const
-    {
-        if (!log) return;
-        static const char *const msg[6] = {
-            "The exact solution is x = 0                          ",
-            "A solution to Ax = b was found, given atol, btol     ",
-            "A least-squares solution was found, given atol       ",
-            "A damped least-squares solution was found, given atol",
-            "Cond(Abar) seems to be too large, given conlim       ",
-            "The iteration limit was reached                      "};
-        char buf[160];
-        const std::string ex = " Exit  LSQR.  ";
-        line(""); line("");
-        snprintf(buf, sizeof buf, "     istop  =%2d               itn    =%8d", istop, h.itn);
-        line(ex + buf);
-        line(ex + "     anorm  =" + fe(12, 5, h.anorm) + "     acond  =" + fe(12, 5, h.acond));
-        line(ex + "     bnorm  =" + fe(12, 5, h.bnorm) + "     xnorm  =" + fe(12, 5, h.xnorm));
-        line(ex + "     rnorm  =" + fe(12, 5, h.rnorm) + "     arnorm =" + fe(12, 5, h.arnorm));
-        snprintf(buf, sizeof buf, " occurred at itn %8d", h.maxdx);
-        line(ex + "     max dx =" + fe(8, 1, h.dxmax) + buf);
-        line(ex + "            =" + fe(8, 1, h.dxmax / (h.xnorm + 1.0e-20)) + "*xnorm");
-        line(ex + "     " + msg[istop]);
-    }
-};
-
-// Consume finished records in order; returns true once a record carries istop != 0.
-static bool drain_ring(Work &wk, LogCtx &lc, int &seen, int upto)
-{
-    bool stop = false;
-    while (seen < upto) {
-        const int k = seen + 1;
-        volatile lsqr_b200_iter_record *r = wk.ring_h + (k % kRingSize);
-        if (r->itn != (double)k) break;
-        lsqr_b200_iter_record rec;
-        memcpy(&rec, (const void *)r, sizeof rec);
-        lc.record(rec);
-        seen = k;
-        if (rec.istop != 0.0) { stop = true; break; }
-    }
-    return stop;
-}
-
-}  // namespace lsqrb
+#include "plan.cuh"
 
 using namespace lsqrb;
 
@@ -576,38 +16,36 @@ struct lsqr_b200_ez {
     int32_t m = 0, n = 0;
     int64_t nnz = 0;
     Csr A, AT;
-    int lanes_a = 4, lanes_at = 32;
-    std::vector<TileMapOwner> mapA;    // one per block of the column-blocked A
-    std::vector<TileMapOwner> mapAT;   // one per block of the row-blocked transpose
-    std::vector<int64_t> a_off;        // first stored entry of every block of A (nblocks + 1 values)
-    // multi-GPU: the LAST row block of A' is cut into comm_chunks column ranges; the all-reduce of range c runs on
-    // comm_stream while the SpMV launch of range c+1 computes (mapATc[c], chunk c = columns [cc[c], cc[c+1]))
-    int comm_chunks = 1;
-    std::vector<int64_t> cc;
-    std::vector<TileMapOwner> mapATc;
-    cudaStream_t comm_stream = nullptr;
-    cudaEvent_t ev_chunk[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    cudaEvent_t ev_comm = nullptr;
-    bool fuse_last = false;            // column-blocked A, tiled kernels: the last block's launch finishes the Aprod step
-    bool a_blocked = false;            // A is column-blocked (v does not fit in L2): Aprod = one launch per block into gu
-    double *gu = nullptr;              // [m] A v of the column-blocked Aprod
-    std::vector<int64_t> at_off;       // first stored entry of every block of A' (nblocks + 1 values)
-    bool stream = true;           // tiled kernels (variants 2, 3) vs sub-warp-per-row (variant 1)
-    bool blocked = false;         // A' is row-blocked (u does not fit in L2): Atprod = one launch per block into g
-    bool deferred = false;        // single GPU, tiled, unblocked: x/w update fused into the next Atprod (2 kernels / iteration)
-    bool overlap_update = true;   // fused engine, 3 kernels / iteration: the x/w update of iteration k runs on a side
-                                  // stream next to the Aprod of iteration k+1 (they touch disjoint vectors)
+    TilePlan planA, planAT;       // one plan per stored matrix (all its blocks)
+    bool single_launch = true;    // one persistent launch per product walks every block (else one launch per block)
+    bool guard = true;            // soft drift guard between the warps of a multi-block launch
+    bool a_blocked = false;       // A is column-blocked (v does not fit in L2)
+    bool at_blocked = false;      // A' is row-blocked (u does not fit in L2)
+    double *gu = nullptr;         // [m] partial A v across the column blocks
+    bool overlap_update = true;   // the x/w update of iteration k runs on a side stream next to the Aprod of iteration
+                                  // k+1 (they touch disjoint vectors)
     cudaStream_t side = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool side_pending = false;    // an update is in flight on the side stream that the main stream has not joined
     lsqr_b200_options opt;
     double *u = nullptr, *v = nullptr, *w = nullptr, *x = nullptr, *se = nullptr;
-    double *g = nullptr;          // multi-GPU: [ A_p'u_p (n) | sum(u_p^2) ]
+    double *g = nullptr;          // [n + 3] partial A'u across the row blocks; multi-GPU (NCCL path): [ A_p'u_p | Ssq(u_p) ]
     double *tmp_m = nullptr, *tmp_n = nullptr;   // staging for lsqr_b200_ez_aprod with host vectors
+    // ---- multi-GPU
     ncclComm_t comm = nullptr;
+    bool peer = false;            // exchange over NVLink peer memory (peer.cuh) instead of one NCCL all-reduce per iteration
+    void *sym_local = nullptr;    // this rank's symmetric exchange block (cudaMalloc'ed, IPC-exported)
+    std::vector<void *> sym_peer; // every rank's block mapped into this process ([rank] = sym_local)
+    PeerView pv;                  // host copy of the device view
+    PeerView *pv_dev = nullptr;
+    double **push_dev = nullptr;  // [world] where this rank's contributions to rank q's columns go
+    int64_t slice0 = 0, slice_len = 0;   // owned columns [slice0, slice0 + slice_len)
+    double *xs = nullptr, *ws = nullptr, *ses = nullptr;   // owned slices of x, w, se (peer path); xs is [world * cols] for the final gather
+    // ---- batches
     int batch = 8;                // iterations per enqueue (per CUDA-graph launch)
     cudaGraphExec_t graph_exec = nullptr;
     int graph_wantse = -1;
+    int64_t graph_launches = 0;   // kernels of this library inside one graph launch
     lsqr_b200_kernel_times times;
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_t2 = nullptr;
     std::vector<cudaEvent_t> prof_ev;   // profile mode: start/stop pairs
@@ -620,22 +58,128 @@ static void ez_free(lsqr_b200_ez *me)
     cudaSetDevice(me->wk.device);
     if (me->wk.stream) cudaStreamSynchronize(me->wk.stream);
     if (me->graph_exec) cudaGraphExecDestroy(me->graph_exec);
+    for (size_t q = 0; q < me->sym_peer.size(); ++q)
+        if (me->sym_peer[q] && me->sym_peer[q] != me->sym_local) cudaIpcCloseMemHandle(me->sym_peer[q]);
     if (me->comm) { NcclApi *a = nccl_api(); if (a) a->CommDestroy(me->comm); }
+    if (me->sym_local) cudaFree(me->sym_local);
+    else if (me->v) cudaFree(me->v);              // (peer path: v lives inside the symmetric block)
+    if (me->pv_dev) cudaFree(me->pv_dev);
+    if (me->push_dev) cudaFree(me->push_dev);
     csr_free(&me->A);
     csr_free(&me->AT);
-    for (auto &mp : me->mapA) tile_map_free(mp);
-    for (auto &mp : me->mapAT) tile_map_free(mp);
-    for (auto &mp : me->mapATc) tile_map_free(mp);
-    for (auto e : me->ev_chunk) if (e) cudaEventDestroy(e);
-    if (me->ev_comm) cudaEventDestroy(me->ev_comm);
-    if (me->comm_stream) cudaStreamDestroy(me->comm_stream);
-    if (me->gu) cudaFree(me->gu);
-    for (double *p : {me->u, me->v, me->w, me->x, me->se, me->g, me->tmp_m, me->tmp_n}) if (p) cudaFree(p);
+    plan_free(me->planA);
+    plan_free(me->planAT);
+    for (double *p : {me->u, me->w, me->x, me->se, me->g, me->gu, me->tmp_m, me->tmp_n, me->xs, me->ws, me->ses}) if (p) cudaFree(p);
     for (auto e : {me->ev_t0, me->ev_t1, me->ev_t2, me->ev_fork, me->ev_join}) if (e) cudaEventDestroy(e);
     if (me->side) cudaStreamDestroy(me->side);
     for (auto e : me->prof_ev) cudaEventDestroy(e);
     me->wk.destroy();
     delete me;
+}
+
+// ---------------------------------------------------------------------------------------------
+// multi-GPU peer path: the symmetric exchange block and its IPC mapping
+// ---------------------------------------------------------------------------------------------
+// Layout of every rank's block (byte offsets are the same on all ranks):
+//   [ recv: world * cols doubles ][ v: n doubles (+ pad) ][ sc: world * kScDoubles doubles ][ flag1: world ][ flag2: world ]
+struct SymLayout {
+    size_t off_recv, off_v, off_sc, off_f1, off_f2, bytes;
+};
+static SymLayout sym_layout(int world, int64_t cols, int64_t n)
+{
+    auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    SymLayout L;
+    L.off_recv = 0;
+    L.off_v = up(sizeof(double) * (size_t)world * (size_t)cols);
+    L.off_sc = L.off_v + up(sizeof(double) * (size_t)(n + 2));
+    L.off_f1 = L.off_sc + up(sizeof(double) * (size_t)world * kScDoubles);
+    L.off_f2 = L.off_f1 + up(sizeof(unsigned int) * (size_t)world);
+    L.bytes = L.off_f2 + up(sizeof(unsigned int) * (size_t)world);
+    return L;
+}
+
+// Every rank allocates its block, the IPC handles travel through one NCCL all-gather, and every rank maps the
+// blocks of its peers.  Returns false (on every rank alike) if any rank could not set the mapping up: the caller
+// then keeps the NCCL all-reduce path.
+static int peer_setup(lsqr_b200_ez *me, bool *ok_out)
+{
+    *ok_out = false;
+    NcclApi *api = nccl_api();
+    Work &wk = me->wk;
+    const int world = me->opt.world_size, rank = me->opt.rank;
+    if (!api || !api->AllGather || world > kMaxRanks) return LSQR_B200_OK;
+    const int64_t n = me->n;
+    const int64_t cols = (((n + world - 1) / world) + 1) & ~(int64_t)1;     // even: 16-byte aligned slices
+    const SymLayout L = sym_layout(world, cols, n);
+    int good = 1;
+    void *block = nullptr;
+    if (cudaMalloc(&block, L.bytes) != cudaSuccess) { cudaGetLastError(); good = 0; }
+    cudaIpcMemHandle_t mine;
+    memset(&mine, 0, sizeof mine);
+    if (good && cudaIpcGetMemHandle(&mine, block) != cudaSuccess) { cudaGetLastError(); good = 0; }
+    if (good) cudaMemsetAsync(block, 0, L.bytes, wk.stream);
+    // exchange: [ handle (64 bytes) | good (8 bytes) ] per rank
+    constexpr size_t kRec = sizeof(cudaIpcMemHandle_t) + 8;
+    unsigned char *d_all = nullptr;
+    LSQRB_CUDA(cudaMalloc(&d_all, kRec * (size_t)world));
+    std::vector<unsigned char> h_all(kRec * (size_t)world, 0);
+    memcpy(h_all.data() + kRec * (size_t)rank, &mine, sizeof mine);
+    h_all[kRec * (size_t)rank + sizeof mine] = (unsigned char)good;
+    LSQRB_CUDA(cudaMemcpyAsync(d_all + kRec * (size_t)rank, h_all.data() + kRec * (size_t)rank, kRec, cudaMemcpyHostToDevice, wk.stream));
+    LSQRB_NCCL(api->AllGather(d_all + kRec * (size_t)rank, d_all, kRec, ncclChar, me->comm, wk.stream));
+    LSQRB_CUDA(cudaMemcpyAsync(h_all.data(), d_all, h_all.size(), cudaMemcpyDeviceToHost, wk.stream));
+    LSQRB_CUDA(cudaStreamSynchronize(wk.stream));
+    for (int q = 0; q < world; ++q) good = good && h_all[kRec * (size_t)q + sizeof mine];
+    me->sym_peer.assign((size_t)world, nullptr);
+    if (good) {
+        for (int q = 0; q < world && good; ++q) {
+            if (q == rank) { me->sym_peer[(size_t)q] = block; continue; }
+            cudaIpcMemHandle_t h;
+            memcpy(&h, h_all.data() + kRec * (size_t)q, sizeof h);
+            void *p = nullptr;
+            if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); good = 0; }
+            me->sym_peer[(size_t)q] = p;
+        }
+    }
+    // second round: did every rank map every peer?
+    h_all[0] = (unsigned char)good;
+    LSQRB_CUDA(cudaMemcpyAsync(d_all + rank, h_all.data(), 1, cudaMemcpyHostToDevice, wk.stream));
+    LSQRB_NCCL(api->AllGather(d_all + rank, d_all, 1, ncclChar, me->comm, wk.stream));
+    LSQRB_CUDA(cudaMemcpyAsync(h_all.data(), d_all, (size_t)world, cudaMemcpyDeviceToHost, wk.stream));
+    LSQRB_CUDA(cudaStreamSynchronize(wk.stream));
+    cudaFree(d_all);
+    for (int q = 0; q < world; ++q) good = good && h_all[(size_t)q];
+    if (!good) {
+        for (int q = 0; q < world; ++q)
+            if (me->sym_peer[(size_t)q] && q != rank) cudaIpcCloseMemHandle(me->sym_peer[(size_t)q]);
+        me->sym_peer.clear();
+        if (block) cudaFree(block);
+        return LSQR_B200_OK;
+    }
+    me->sym_local = block;
+    PeerView &pv = me->pv;
+    memset(&pv, 0, sizeof pv);
+    pv.world = world; pv.rank = rank; pv.cols = cols; pv.n = n;
+    std::vector<double *> push((size_t)world);
+    for (int q = 0; q < world; ++q) {
+        char *base = (char *)me->sym_peer[(size_t)q];
+        pv.recv[q] = (double *)(base + L.off_recv);
+        pv.v[q] = (double *)(base + L.off_v);
+        pv.sc[q] = (double *)(base + L.off_sc);
+        pv.flag1[q] = (unsigned int *)(base + L.off_f1);
+        pv.flag2[q] = (unsigned int *)(base + L.off_f2);
+        push[(size_t)q] = pv.recv[q] + (size_t)rank * (size_t)cols;
+    }
+    LSQRB_CUDA(cudaMalloc(&me->pv_dev, sizeof(PeerView)));
+    LSQRB_CUDA(cudaMemcpyAsync(me->pv_dev, &pv, sizeof pv, cudaMemcpyHostToDevice, wk.stream));
+    LSQRB_CUDA(cudaMalloc(&me->push_dev, sizeof(double *) * (size_t)world));
+    LSQRB_CUDA(cudaMemcpyAsync(me->push_dev, push.data(), sizeof(double *) * (size_t)world, cudaMemcpyHostToDevice, wk.stream));
+    LSQRB_CUDA(cudaStreamSynchronize(wk.stream));
+    me->v = pv.v[rank];
+    me->slice0 = std::min<int64_t>(n, (int64_t)rank * cols);
+    me->slice_len = std::max<int64_t>(0, std::min<int64_t>(cols, n - me->slice0));
+    *ok_out = true;
+    return LSQR_B200_OK;
 }
 
 extern "C" {
@@ -695,6 +239,8 @@ int lsqr_b200_nccl_unique_id(void *out128)
     return LSQR_B200_OK;
 }
 
+
+
 // ---------------------------------------------------------------------------------------------
 // initialize_ez  (src/lsqr.f90:91-127)
 // ---------------------------------------------------------------------------------------------
@@ -725,7 +271,8 @@ static int ez_initialize_impl(lsqr_b200_ez *me, int64_t nnz, const double *a, co
     };
     int rc = coo_validate(wk.stream, me->m, me->n, nnz, d_irow, d_icol);
     if (rc == LSQR_B200_OK) {
-        // Column-blocked A: the mirror image of the row-blocked transpose below, for a v (8 n bytes) beyond the L2 budget
+        // Column-blocked A: when v (8 n bytes) cannot stay in L2 while A streams past it, A is stored as one CSR per
+        // block of COLUMNS, so that every block gathers from a slice of v that does fit.
         int64_t block_cols = env_int("LSQR_B200_VBLOCK_COLS", 0);
         if (block_cols <= 0) {
             const int64_t budget = (int64_t)env_int("LSQR_B200_VBLOCK_MB", 48) * (1 << 20) / 8;
@@ -737,8 +284,7 @@ static int ez_initialize_impl(lsqr_b200_ez *me, int64_t nnz, const double *a, co
         rc = coo_to_csr_device(wk.stream, me->m, nnz, d_irow, d_icol, d_a, &me->A, block_cols, me->n);
     }
     if (rc == LSQR_B200_OK) {
-        // Row-blocked transpose: when u (8 m bytes) cannot stay in L2 while A' streams past it, A' is stored as one
-        // CSR per block of rows of A, so that every Atprod launch gathers from a slice of u that does fit.
+        // Row-blocked transpose: the mirror image for u (8 m bytes) and A'.
         int64_t block_rows = env_int("LSQR_B200_UBLOCK_ROWS", 0);
         if (block_rows <= 0) {
             const int64_t budget_rows = (int64_t)env_int("LSQR_B200_UBLOCK_MB", 48) * (1 << 20) / 8;
@@ -753,97 +299,57 @@ static int ez_initialize_impl(lsqr_b200_ez *me, int64_t nnz, const double *a, co
     release();
     LSQRB_TRY(rc);
 
-    me->lanes_a = pick_lanes(me->A, "LSQR_B200_LANES_A");
-    me->lanes_at = pick_lanes(me->AT, "LSQR_B200_LANES_AT");
-    const int variant = me->opt.spmv_variant ? me->opt.spmv_variant : env_int("LSQR_B200_SPMV_VARIANT", 3);
-    me->stream = variant != 1;
-    me->blocked = me->AT.nblocks > 1;
+    if (me->opt.spmv_variant != 0 && me->opt.spmv_variant != 3) {
+        set_last_error("spmv_variant: only the warp-autonomous segmented kernel (0 / 3) exists");
+        return LSQR_B200_ERR_ARG;
+    }
     me->a_blocked = me->A.nblocks > 1;
-    me->fuse_last = me->a_blocked && me->stream && env_int("LSQR_B200_FUSE_LAST_BLOCK", 1) != 0;
-    me->deferred = me->stream && !me->blocked && !me->a_blocked && me->opt.world_size == 1 && env_int("LSQR_B200_DEFERRED_UPDATE", 0) != 0;
-    me->overlap_update = !me->deferred && !me->blocked && !me->a_blocked && me->opt.world_size == 1 && env_int("LSQR_B200_OVERLAP_UPDATE", 1) != 0;
+    me->at_blocked = me->AT.nblocks > 1;
+    me->single_launch = env_int("LSQR_B200_SINGLE_LAUNCH", 1) != 0;
+    me->guard = env_int("LSQR_B200_DRIFT_GUARD", 1) != 0;
+    me->overlap_update = me->opt.world_size == 1 && env_int("LSQR_B200_OVERLAP_UPDATE", 1) != 0;
     if (me->overlap_update) {
         LSQRB_CUDA(cudaStreamCreateWithFlags(&me->side, cudaStreamNonBlocking));
         LSQRB_CUDA(cudaEventCreateWithFlags(&me->ev_fork, cudaEventDisableTiming));
         LSQRB_CUDA(cudaEventCreateWithFlags(&me->ev_join, cudaEventDisableTiming));
     }
-    // first stored entry of every block of A and of A'
-    auto block_offsets = [&](const Csr &M, std::vector<int64_t> *out) -> int {
-        const int64_t nb = M.nblocks;
-        out->assign((size_t)nb + 1, 0);
-        std::vector<uint32_t> off((size_t)nb + 1);
-        for (int64_t b = 0; b <= nb; ++b)
-            LSQRB_CUDA(cudaMemcpyAsync(&off[(size_t)b], M.ptr + b * M.nkeys, sizeof(uint32_t), cudaMemcpyDeviceToHost, wk.stream));
-        LSQRB_CUDA(cudaStreamSynchronize(wk.stream));
-        for (int64_t b = 0; b <= nb; ++b) (*out)[(size_t)b] = off[(size_t)b];
-        return LSQR_B200_OK;
-    };
-    LSQRB_TRY(block_offsets(me->A, &me->a_off));
-    LSQRB_TRY(block_offsets(me->AT, &me->at_off));
-    if (me->stream) {
-        me->mapA.resize((size_t)me->A.nblocks);
-        for (int64_t b = 0; b < me->A.nblocks; ++b)
-            LSQRB_TRY(build_tile_map(wk, view_of_block(me->A, b), me->a_off[(size_t)b + 1] - me->a_off[(size_t)b],
-                                     variant == 2 ? 2 : 3, &me->mapA[(size_t)b]));
-        me->mapAT.resize((size_t)me->AT.nblocks);
-        for (int64_t b = 0; b < me->AT.nblocks; ++b)
-            LSQRB_TRY(build_tile_map(wk, view_of_block(me->AT, b), me->at_off[(size_t)b + 1] - me->at_off[(size_t)b],
-                                     variant == 2 ? 2 : 3, &me->mapAT[(size_t)b]));
-        LSQRB_CUDA(cudaStreamSynchronize(wk.stream));
+    // work plans: row cuts shared by all blocks, gather windows, kernel flavour, balanced schedule
+    LSQRB_TRY(build_plan(wk, me->A, &me->planA));
+    LSQRB_TRY(build_plan(wk, me->AT, &me->planAT));
+    if (env_int("LSQR_B200_VERBOSE", 0)) {
+        auto say = [&](const char *name, const Csr &M, const TilePlan &P) {
+            fprintf(stderr, "[lsqr_b200] %s: blocks=%lld (block size %lld) tiles=%d (%llu work units) grid=%d CTAs x %d/SM  window=%d doubles "
+                            "(%.1f%% of the entries staged; piece span median %u, max %u)%s imbalance %.3f\n",
+                    name, (long long)M.nblocks, (long long)M.block_rows, P.ntiles, (unsigned long long)P.tile, P.ctas, P.minb, P.win_cap,
+                    100.0 * P.windowed, P.span_p50, P.span_max, P.order ? " LPT" : "", P.imbalance);
+        };
+        fprintf(stderr, "[lsqr_b200] m=%d n=%d nnz=%lld single_launch=%d guard=%d\n", me->m, me->n, (long long)me->nnz, (int)me->single_launch, (int)me->guard);
+        say("A ", me->A, me->planA);
+        say("A'", me->AT, me->planAT);
     }
-    if (me->a_blocked) LSQRB_CUDA(cudaMalloc(&me->gu, sizeof(double) * (size_t)std::max<int32_t>(me->m, 1)));
-    if (me->opt.world_size > 1 && me->stream) {
-        // Column chunks for the pipelined all-reduce.  Off by default: measured on 8 x B200 (C5, n = 1e7, 80 MB per
-        // all-reduce) 1 / 4 / 8 chunks give 3.05 / 3.14 / 3.26 ms per iteration -- the persistent SpMV grids hold every
-        // SM's registers, so NCCL's CTAs only start when a launch drains and the smaller launches pay more in tails
-        // than the overlap returns (profiles/r01/run2/n8_allreduce_pipelining_ab.txt).
-        int k = env_int("LSQR_B200_COMM_CHUNKS", 1);
-        k = std::max(1, std::min(k, 8));
-        me->comm_chunks = k;
-        if (k > 1) {
-            me->cc.assign((size_t)k + 1, 0);
-            for (int c = 0; c <= k; ++c) me->cc[(size_t)c] = c == k ? (int64_t)me->n : (((int64_t)me->n * c / k) & ~(int64_t)1);
-            const int64_t bl = me->AT.nblocks - 1;          // only the last block is pipelined (no extra passes over u)
-            std::vector<uint32_t> off((size_t)k + 1);
-            for (int c = 0; c <= k; ++c)
-                LSQRB_CUDA(cudaMemcpyAsync(&off[(size_t)c], me->AT.ptr + bl * me->AT.nkeys + me->cc[(size_t)c],
-                                           sizeof(uint32_t), cudaMemcpyDeviceToHost, wk.stream));
-            LSQRB_CUDA(cudaStreamSynchronize(wk.stream));
-            me->mapATc.resize((size_t)k);
-            for (int c = 0; c < k; ++c) {
-                CsrView V = view_of_block(me->AT, bl);
-                V.ptr += me->cc[(size_t)c];
-                V.nrows = me->cc[(size_t)c + 1] - me->cc[(size_t)c];
-                // every range but the first runs next to the all-reduce of the previous one: leave NCCL some SMs
-                LSQRB_TRY(build_tile_map(wk, V, (int64_t)off[(size_t)c + 1] - (int64_t)off[(size_t)c], variant == 2 ? 2 : 3,
-                                         &me->mapATc[(size_t)c], c > 0 ? env_int("LSQR_B200_COMM_RESERVE_SMS", 0) : 0));
-            }
-            LSQRB_CUDA(cudaStreamSynchronize(wk.stream));
-            // highest priority: the SpMV grids are persistent and fill every SM, so the collective's CTAs can only
-            // start on resources freed by a finishing SpMV launch -- they must win those against the next launch
-            int prio_lo = 0, prio_hi = 0;
-            LSQRB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-            LSQRB_CUDA(cudaStreamCreateWithPriority(&me->comm_stream, cudaStreamNonBlocking,
-                                                    env_int("LSQR_B200_COMM_PRIORITY", 1) ? prio_hi : prio_lo));
-            for (int c = 0; c < k; ++c) LSQRB_CUDA(cudaEventCreateWithFlags(&me->ev_chunk[c], cudaEventDisableTiming));
-            LSQRB_CUDA(cudaEventCreateWithFlags(&me->ev_comm, cudaEventDisableTiming));
-        }
-    }
-    if (env_int("LSQR_B200_VERBOSE", 0))
-        fprintf(stderr, "[lsqr_b200] m=%d n=%d nnz=%lld variant=%d A blocks=%lld (block_cols=%lld) A' blocks=%lld (block_rows=%lld) "
-                        "warp tile A=%u%s (imbalance %.3f) A'=%u%s (imbalance %.3f)\n", me->m, me->n, (long long)me->nnz, variant,
-                (long long)me->A.nblocks, (long long)me->A.block_rows, (long long)me->AT.nblocks, (long long)me->AT.block_rows,
-                me->mapA.empty() ? 0u : me->mapA[0].tile, !me->mapA.empty() && me->mapA[0].order ? " LPT" : "",
-                me->mapA.empty() ? 1.0 : me->mapA[0].imbalance,
-                me->mapAT.empty() ? 0u : me->mapAT[0].tile, !me->mapAT.empty() && me->mapAT[0].order ? " LPT" : "",
-                me->mapAT.empty() ? 1.0 : me->mapAT[0].imbalance);
 
     const size_t mm = (size_t)std::max<int32_t>(me->m, 1), nn = (size_t)std::max<int32_t>(me->n, 1);
-    LSQRB_CUDA(cudaMalloc(&me->u, sizeof(double) * mm));
-    LSQRB_CUDA(cudaMalloc(&me->v, sizeof(double) * nn));
-    LSQRB_CUDA(cudaMalloc(&me->w, sizeof(double) * nn));
-    LSQRB_CUDA(cudaMalloc(&me->x, sizeof(double) * nn));
-    if (me->opt.world_size > 1 || me->blocked) LSQRB_CUDA(cudaMalloc(&me->g, sizeof(double) * (nn + 1)));
+    LSQRB_CUDA(cudaMalloc(&me->u, sizeof(double) * (mm + 2)));
+    if (me->a_blocked) LSQRB_CUDA(cudaMalloc(&me->gu, sizeof(double) * (mm + 2)));
+    if (me->opt.world_size > 1 || me->at_blocked) LSQRB_CUDA(cudaMalloc(&me->g, sizeof(double) * (nn + 4)));
+    if (me->opt.world_size > 1) {
+        const int want = env_int("LSQR_B200_PEER_EXCHANGE", 1);
+        bool ok = false;
+        if (want) LSQRB_TRY(peer_setup(me, &ok));
+        me->peer = ok;
+        if (env_int("LSQR_B200_VERBOSE", 0))
+            fprintf(stderr, "[lsqr_b200] rank %d/%d: exchange over %s\n", me->opt.rank, me->opt.world_size,
+                    me->peer ? "NVLink peer memory (IPC-mapped symmetric blocks)" : "one NCCL all-reduce per iteration");
+    }
+    if (!me->peer) {
+        LSQRB_CUDA(cudaMalloc(&me->v, sizeof(double) * (nn + 2)));
+        LSQRB_CUDA(cudaMalloc(&me->w, sizeof(double) * (nn + 2)));
+        LSQRB_CUDA(cudaMalloc(&me->x, sizeof(double) * (nn + 2)));
+    } else {
+        const size_t sl = (size_t)std::max<int64_t>(me->pv.cols, 1);
+        LSQRB_CUDA(cudaMalloc(&me->ws, sizeof(double) * sl));
+        LSQRB_CUDA(cudaMalloc(&me->xs, sizeof(double) * sl * (size_t)me->opt.world_size));   // gathered in place at the end
+    }
     LSQRB_CUDA(cudaEventCreate(&me->ev_t0));
     LSQRB_CUDA(cudaEventCreate(&me->ev_t1));
     LSQRB_CUDA(cudaEventCreate(&me->ev_t2));
@@ -934,13 +440,35 @@ int lsqr_b200_ez_schedule(const lsqr_b200_ez *me, int32_t which, int64_t block, 
                           int64_t *tile_entries, int32_t *balanced, double *imbalance)
 {
     if (!me) return LSQR_B200_ERR_ARG;
-    const std::vector<TileMapOwner> &maps = which ? me->mapAT : me->mapA;
-    if (block < 0 || (size_t)block >= maps.size()) { set_last_error("no such block / no tiled schedule"); return LSQR_B200_ERR_ARG; }
-    const TileMapOwner &mp = maps[(size_t)block];
-    if (ntiles) *ntiles = mp.ntiles;
-    if (tile_entries) *tile_entries = mp.tile;
-    if (balanced) *balanced = mp.order != nullptr;
-    if (imbalance) *imbalance = mp.imbalance;
+    const Csr &M = which ? me->AT : me->A;
+    const TilePlan &P = which ? me->planAT : me->planA;
+    if (block < 0 || block >= M.nblocks) { set_last_error("no such block"); return LSQR_B200_ERR_ARG; }
+    // one plan covers every block of the matrix: the same row cuts, the same warp for a tile in every block
+    if (ntiles) *ntiles = P.ntiles;
+    if (tile_entries) *tile_entries = (int64_t)(P.tile / (uint64_t)std::max<int64_t>(M.nblocks, 1));
+    if (balanced) *balanced = P.order != nullptr;
+    if (imbalance) *imbalance = P.imbalance;
+    return LSQR_B200_OK;
+}
+
+int lsqr_b200_ez_plan(const lsqr_b200_ez *me, int32_t which, lsqr_b200_plan_info *out)
+{
+    if (!me || !out || (which != 0 && which != 1)) return LSQR_B200_ERR_ARG;
+    const Csr &M = which ? me->AT : me->A;
+    const TilePlan &P = which ? me->planAT : me->planA;
+    memset(out, 0, sizeof *out);
+    out->nblocks = M.nblocks;
+    out->ntiles = P.ntiles;
+    out->grid_ctas = P.ctas;
+    out->ctas_per_sm = P.minb;
+    out->window_doubles = P.win_cap;
+    out->windowed_fraction = P.windowed;
+    out->span_median = P.span_p50;
+    out->span_max = P.span_max;
+    out->balanced = P.order != nullptr;
+    out->imbalance = P.imbalance;
+    out->single_launch = me->single_launch && M.nblocks <= kMaxSpmvBlocks;
+    out->peer_exchange = me->peer;
     return LSQR_B200_OK;
 }
 
@@ -966,6 +494,8 @@ int lsqr_b200_ez_get_csr(lsqr_b200_ez *me, int32_t which, int64_t *ptr, int32_t 
     return LSQR_B200_OK;
 }
 
+
+
 // ---------------------------------------------------------------------------------------------
 // aprod_ez  (src/lsqr.f90:134-200)
 // ---------------------------------------------------------------------------------------------
@@ -975,23 +505,24 @@ int lsqr_b200_ez_aprod_device(void *handle, int32_t mode, int32_t m, int32_t n,
     lsqr_b200_ez *me = (lsqr_b200_ez *)handle;
     if (!me) return LSQR_B200_ERR_ARG;
     if (m != me->m || n != me->n) return LSQR_B200_ERR_NOINIT;   // :152
+    if (mode != 1 && mode != 2) return LSQR_B200_ERR_MODE;       // :197
     Work &wk = me->wk;
+    // `stream` is an ordinary cudaStream_t argument: NULL is the legacy default stream (as everywhere in CUDA), not
+    // the handle's own stream -- the caller's work on that stream is ordered before and after these launches
     cudaStream_t saved = wk.stream;
-    if (stream) wk.stream = (cudaStream_t)stream;
-    int rc;
-    if (mode == 1) {                                                                                                       // y += A x
-        rc = LSQR_B200_OK;
-        for (int64_t b = 0; b < me->A.nblocks && rc == LSQR_B200_OK; ++b)
-            rc = me->stream ? launch_stream<SEPI_ACC>(wk, view_of_block(me->A, b), me->mapA[(size_t)b], x_dev, y_dev, nullptr)
-                            : launch_spmv<EPI_ACC>(wk, view_of_block(me->A, b), me->lanes_a, x_dev, y_dev, nullptr);
+    wk.stream = stream ? (cudaStream_t)stream : cudaStreamLegacy;
+    int rc = cudaSetDevice(wk.device) == cudaSuccess ? LSQR_B200_OK : LSQR_B200_ERR_CUDA;
+    ProductIo io;
+    io.first_mode = BM_ACC;   // every block accumulates straight into the caller's vector
+    if (rc == LSQR_B200_OK) {
+        if (mode == 1) {                                                                                                   // y += A x
+            io.x = x_dev; io.out = y_dev; io.part = y_dev;
+            rc = launch_product<FIN_NONE>(wk, me->A, me->planA, io, me->single_launch, me->guard);
+        } else {                                                                                                           // x += A'y
+            io.x = y_dev; io.out = x_dev; io.part = x_dev;
+            rc = launch_product<FIN_NONE>(wk, me->AT, me->planAT, io, me->single_launch, me->guard);
+        }
     }
-    else if (mode == 2) {                                                                                                  // x += A'y
-        rc = LSQR_B200_OK;
-        for (int64_t b = 0; b < me->AT.nblocks && rc == LSQR_B200_OK; ++b)
-            rc = me->stream ? launch_stream<SEPI_ACC>(wk, view_of_block(me->AT, b), me->mapAT[(size_t)b], y_dev, x_dev, nullptr)
-                            : launch_spmv<EPI_ACC>(wk, view_of_block(me->AT, b), me->lanes_at, y_dev, x_dev, nullptr);
-    }
-    else                rc = LSQR_B200_ERR_MODE;                                                     // :197
     wk.stream = saved;
     return rc;
 }
@@ -1016,12 +547,14 @@ int lsqr_b200_ez_aprod(lsqr_b200_ez *me, int32_t mode, int32_t m, int32_t n, dou
         dy = me->tmp_m;
         LSQRB_CUDA(cudaMemcpyAsync(dy, y, sizeof(double) * (size_t)m, cudaMemcpyHostToDevice, wk.stream));
     }
-    LSQRB_TRY(lsqr_b200_ez_aprod_device(me, mode, m, n, dx, dy, nullptr));
+    LSQRB_TRY(lsqr_b200_ez_aprod_device(me, mode, m, n, dx, dy, (void *)wk.stream));
     if (mode == 1 && !ydev) LSQRB_CUDA(cudaMemcpyAsync(y, dy, sizeof(double) * (size_t)m, cudaMemcpyDeviceToHost, wk.stream));
     if (mode == 2 && !xdev) LSQRB_CUDA(cudaMemcpyAsync(x, dx, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, wk.stream));
     LSQRB_CUDA(cudaStreamSynchronize(wk.stream));
     return LSQR_B200_OK;
 }
+
+}  // extern "C"
 
 // ---------------------------------------------------------------------------------------------
 // solve_ez + LSQR  (src/lsqr.f90:207-259, 432-882) -- fused engine
@@ -1044,133 +577,74 @@ struct ProfScope {   // profile mode: one event pair around a launch
     ~ProfScope() { if (on) cudaEventRecord(me->prof_ev[slot + 1], me->wk.stream); }
 };
 
-static int allreduce_g(lsqr_b200_ez *me)
+// u' = ca_mat (A v) + ca_vec u, ||u'||: one launch; aux != NULL: the local sum of squares goes there (multi-GPU)
+static int do_aprod(lsqr_b200_ez *me, Ssq *aux)
 {
-    NcclApi *api = nccl_api();
-    LSQRB_NCCL(api->AllReduce(me->g, me->g, (size_t)me->n + 1, ncclFloat64, ncclSum, me->comm, me->wk.stream));
-    return LSQR_B200_OK;
+    ProductIo io;
+    io.x = me->v; io.out = me->u; io.part = me->gu; io.first_mode = BM_STORE; io.aux = aux;
+    return launch_product<FIN_APROD>(me->wk, me->A, me->planA, io, me->single_launch, me->guard);
 }
-
-// the SpMV flavours of one handle
-static int do_aprod_fused(lsqr_b200_ez *me, double *aux)
+template <int FIN>   // FIN_ATPROD / FIN_INIT_ATPROD: v' = ct_mat (A'u) + ct_vec v, ||v'||: one launch
+static int do_atprod(lsqr_b200_ez *me)
 {
-    if (!me->a_blocked)
-        return me->stream ? launch_stream<SEPI_APROD>(me->wk, view_of(me->A), me->mapA[0], me->v, me->u, aux)
-                          : launch_spmv<EPI_FUSED_APROD>(me->wk, view_of(me->A), me->lanes_a, me->v, me->u, aux);
-    // column-blocked A: gu = A v block by block (block 0 stores, the others accumulate), then the fused finish
-    Work &wk = me->wk;
-    StreamExtra ex;
-    ex.check_done = 1;
-    // tiled kernels: the LAST block's launch finishes the step itself (u' = ca_mat*(gu + s) + ca_vec*u, sum u'^2), which
-    // saves one write and one read of gu and a pass over u
-    const bool fuse_last = me->fuse_last;
-    for (int64_t b = 0; b < me->A.nblocks; ++b) {
-        const CsrView V = view_of_block(me->A, b);
-        if (b == 0) LSQRB_TRY(me->stream ? launch_stream<SEPI_STORE>(wk, V, me->mapA[0], me->v, me->gu, nullptr, ex)
-                                         : launch_spmv<EPI_STORE>(wk, V, me->lanes_a, me->v, me->gu, nullptr, 1));
-        else if (fuse_last && b == me->A.nblocks - 1) {
-            StreamExtra fx;
-            fx.uw = me->gu;
-            return launch_stream<SEPI_APROD_ACC>(wk, V, me->mapA[(size_t)b], me->v, me->u, aux, fx);
-        }
-        else        LSQRB_TRY(me->stream ? launch_stream<SEPI_ACC>(wk, V, me->mapA[(size_t)b], me->v, me->gu, nullptr, ex)
-                                         : launch_spmv<EPI_ACC>(wk, V, me->lanes_a, me->v, me->gu, nullptr, 1));
-    }
-    ufinish_kernel<<<wk.grid_for(me->m, kThreads), kThreads, 0, wk.stream>>>(me->m, me->gu, me->u, wk.st, aux);
-    wk.launches++;
-    LSQRB_CUDA(cudaGetLastError());
-    return LSQR_B200_OK;
+    ProductIo io;
+    io.x = me->u; io.out = me->v; io.part = me->g; io.first_mode = BM_STORE;
+    return launch_product<FIN>(me->wk, me->AT, me->planAT, io, me->single_launch, me->guard);
 }
-// g = A'u (unfused: multi-GPU partial and/or row-blocked transpose): block 0 stores, the others accumulate
-static int do_atprod_store(lsqr_b200_ez *me)
-{
-    StreamExtra ex;
-    ex.check_done = 1;   // over-enqueued iterations after the stop are no-ops
-    for (int64_t b = 0; b < me->AT.nblocks; ++b) {
-        const CsrView V = view_of_block(me->AT, b);
-        if (b == 0) LSQRB_TRY(me->stream ? launch_stream<SEPI_STORE>(me->wk, V, me->mapAT[0], me->u, me->g, nullptr, ex)
-                                         : launch_spmv<EPI_STORE>(me->wk, V, me->lanes_at, me->u, me->g, nullptr, 1));
-        else        LSQRB_TRY(me->stream ? launch_stream<SEPI_ACC>(me->wk, V, me->mapAT[(size_t)b], me->u, me->g, nullptr, ex)
-                                         : launch_spmv<EPI_ACC>(me->wk, V, me->lanes_at, me->u, me->g, nullptr, 1));
-    }
-    return LSQR_B200_OK;
-}
-// multi-GPU: g = sum over ranks of [A_p'u_p | sum u_p^2].  With comm_chunks > 1 the all-reduce of column range c
-// (on comm_stream) overlaps the SpMV launches of range c+1; the Atprod is then ordered chunk-major, block-minor.
+// multi-GPU, NCCL path: g = [ A_p'u_p | Ssq(u_p) ] summed over the ranks by one all-reduce
 static int do_atprod_allreduce(lsqr_b200_ez *me)
 {
-    Work &wk = me->wk;
+    ProductIo io;
+    io.x = me->u; io.out = me->g; io.part = me->g; io.first_mode = BM_STORE; io.check_done = 1;
+    LSQRB_TRY(launch_product<FIN_NONE>(me->wk, me->AT, me->planAT, io, me->single_launch, me->guard));
     NcclApi *api = nccl_api();
-    const int k = me->comm_chunks;
-    if (k <= 1) {
-        LSQRB_TRY(do_atprod_store(me));
-        return allreduce_g(me);
-    }
-    StreamExtra ex;
-    ex.check_done = 1;
-    const int64_t nb = me->AT.nblocks;
-    for (int64_t b = 0; b + 1 < nb; ++b) {               // all but the last block: whole-width launches
-        const CsrView V = view_of_block(me->AT, b);
-        if (b == 0) LSQRB_TRY(launch_stream<SEPI_STORE>(wk, V, me->mapAT[0], me->u, me->g, nullptr, ex));
-        else        LSQRB_TRY(launch_stream<SEPI_ACC>(wk, V, me->mapAT[(size_t)b], me->u, me->g, nullptr, ex));
-    }
-    for (int c = 0; c < k; ++c) {                        // last block, range by range, each followed by its all-reduce
-        const int64_t c0 = me->cc[(size_t)c], c1 = me->cc[(size_t)c + 1];
-        CsrView V = view_of_block(me->AT, nb - 1);
-        V.ptr += c0;
-        V.nrows = c1 - c0;
-        if (nb == 1) LSQRB_TRY(launch_stream<SEPI_STORE>(wk, V, me->mapATc[(size_t)c], me->u, me->g + c0, nullptr, ex));
-        else         LSQRB_TRY(launch_stream<SEPI_ACC>(wk, V, me->mapATc[(size_t)c], me->u, me->g + c0, nullptr, ex));
-        LSQRB_CUDA(cudaEventRecord(me->ev_chunk[c], wk.stream));
-        LSQRB_CUDA(cudaStreamWaitEvent(me->comm_stream, me->ev_chunk[c], 0));
-        const size_t count = (size_t)(c1 - c0) + (c == k - 1 ? 1 : 0);     // the last range carries sum(u_p^2) in g[n]
-        LSQRB_NCCL(api->AllReduce(me->g + c0, me->g + c0, count, ncclFloat64, ncclSum, me->comm, me->comm_stream));
-    }
-    LSQRB_CUDA(cudaEventRecord(me->ev_comm, me->comm_stream));
-    LSQRB_CUDA(cudaStreamWaitEvent(wk.stream, me->ev_comm, 0));
+    LSQRB_NCCL(api->AllReduce(me->g, me->g, (size_t)me->n + 3, ncclFloat64, ncclSum, me->comm, me->wk.stream));
     return LSQR_B200_OK;
 }
+// multi-GPU, peer path: the partial A_p'u_p goes straight to the owners of the columns (peer.cuh)
+static int do_atprod_push(lsqr_b200_ez *me)
+{
+    ProductIo io;
+    io.x = me->u; io.out = nullptr; io.part = me->g; io.first_mode = BM_STORE; io.check_done = 1;
+    io.push = me->push_dev; io.push_cols = me->pv.cols; io.peer = me->pv_dev;
+    return launch_product<FIN_PUSH>(me->wk, me->AT, me->planAT, io, me->single_launch, me->guard);
+}
 
-static int do_atprod_fused(lsqr_b200_ez *me)
-{
-    return me->stream ? launch_stream<SEPI_ATPROD>(me->wk, view_of(me->AT), me->mapAT[0], me->u, me->v, nullptr)
-                      : launch_spmv<EPI_FUSED_ATPROD>(me->wk, view_of(me->AT), me->lanes_at, me->u, me->v, nullptr);
-}
-static int do_atprod_init(lsqr_b200_ez *me)
-{
-    return me->stream ? launch_stream<SEPI_INIT_ATPROD>(me->wk, view_of(me->AT), me->mapAT[0], me->u, me->v, nullptr)
-                      : launch_spmv<EPI_INIT_ATPROD>(me->wk, view_of(me->AT), me->lanes_at, me->u, me->v, nullptr);
-}
-static int do_atprod_upd(lsqr_b200_ez *me)   // Atprod of this iteration + deferred x/w update of the previous one
-{
-    StreamExtra ex;
-    ex.ux = me->x; ex.uw = me->w; ex.use = me->se;
-    return launch_stream<SEPI_ATPROD_UPD>(me->wk, view_of(me->AT), me->mapAT[0], me->u, me->v, nullptr, ex);
-}
+static int peer_grid(const lsqr_b200_ez *me) { return me->wk.grid_for(std::max<int64_t>(me->slice_len, 1), kThreads); }
 
 // one LSQR iteration, enqueued (no host synchronisation)
 static int enqueue_iteration(lsqr_b200_ez *me, bool wantse)
 {
     Work &wk = me->wk;
-    if (me->opt.world_size > 1 || me->blocked) {
-        // unfused pipeline: u' and its partial norm, g = [A'u' | sum u'^2] (all-reduced over the ranks), then
-        // v' = g/beta - (beta/alpha) v with both scalar steps, then the x/w update
-        { ProfScope p(me, CLS_APROD);  LSQRB_TRY(do_aprod_fused(me, me->g + me->n)); }
-        if (me->opt.world_size > 1) { ProfScope p(me, CLS_ATPROD); LSQRB_TRY(do_atprod_allreduce(me)); }   // (timed together)
-        else                        { ProfScope p(me, CLS_ATPROD); LSQRB_TRY(do_atprod_store(me)); }
+    if (me->peer) {
+        { ProfScope p(me, CLS_APROD);  LSQRB_TRY(do_aprod(me, &wk.st->usq_local)); }
+        { ProfScope p(me, CLS_ATPROD); LSQRB_TRY(do_atprod_push(me)); }
+        { ProfScope p(me, CLS_OTHER);
+          peer_vfinish_kernel<false><<<peer_grid(me), kThreads, 0, wk.stream>>>(me->pv, wk.st);
+          peer_step_kernel<false><<<1, 32, 0, wk.stream>>>(me->pv, wk.st);
+          wk.launches += 2; LSQRB_CUDA(cudaGetLastError()); }
+        { ProfScope p(me, CLS_UPDATE);
+          LSQRB_TRY(launch_update<true>(wk, me->slice_len, me->xs + (size_t)me->opt.rank * (size_t)me->pv.cols, me->ws,
+                                        me->v + me->slice0, me->ses, wantse, 1)); }
+        return LSQR_B200_OK;
+    }
+    if (me->opt.world_size > 1) {
+        // NCCL path: u' and its partial norm, g = [A'u' | Ssq(u')] all-reduced over the ranks, then every rank forms
+        // v' = g/beta - (beta/alpha) v, both scalar steps and the x/w update redundantly
+        { ProfScope p(me, CLS_APROD);  LSQRB_TRY(do_aprod(me, (Ssq *)(me->g + me->n))); }
+        { ProfScope p(me, CLS_ATPROD); LSQRB_TRY(do_atprod_allreduce(me)); }   // (product and all-reduce timed together)
         { ProfScope p(me, CLS_OTHER);
           vfinish_kernel<false><<<wk.grid_for(me->n, kThreads), kThreads, 0, wk.stream>>>(me->n, me->g, me->v, wk.st);
           wk.launches++; LSQRB_CUDA(cudaGetLastError()); }
-    } else if (me->deferred) {
-        { ProfScope p(me, CLS_APROD);  LSQRB_TRY(do_aprod_fused(me, nullptr)); }
-        { ProfScope p(me, CLS_ATPROD); LSQRB_TRY(do_atprod_upd(me)); }
+        { ProfScope p(me, CLS_UPDATE); LSQRB_TRY(launch_update<true>(wk, me->n, me->x, me->w, me->v, me->se, wantse)); }
         return LSQR_B200_OK;
-    } else if (me->overlap_update) {
+    }
+    if (me->overlap_update) {
         // K3(k+1) reads v, writes u; K5(k) reads v, writes x, w: disjoint, so the update leaves the critical path.
-        // K4 overwrites v and needs ||w||^2, so it joins the side stream first.
-        { ProfScope p(me, CLS_APROD);  LSQRB_TRY(do_aprod_fused(me, nullptr)); }
+        // K4 overwrites v and needs ||w||, so it joins the side stream first.
+        { ProfScope p(me, CLS_APROD);  LSQRB_TRY(do_aprod(me, nullptr)); }
         if (me->side_pending) { LSQRB_CUDA(cudaStreamWaitEvent(wk.stream, me->ev_join, 0)); me->side_pending = false; }
-        { ProfScope p(me, CLS_ATPROD); LSQRB_TRY(do_atprod_fused(me)); }
+        { ProfScope p(me, CLS_ATPROD); LSQRB_TRY(do_atprod<FIN_ATPROD>(me)); }
         LSQRB_CUDA(cudaEventRecord(me->ev_fork, wk.stream));
         LSQRB_CUDA(cudaStreamWaitEvent(me->side, me->ev_fork, 0));
         {
@@ -1183,10 +657,9 @@ static int enqueue_iteration(lsqr_b200_ez *me, bool wantse)
         LSQRB_CUDA(cudaEventRecord(me->ev_join, me->side));
         me->side_pending = true;
         return LSQR_B200_OK;
-    } else {
-        { ProfScope p(me, CLS_APROD);  LSQRB_TRY(do_aprod_fused(me, nullptr)); }
-        { ProfScope p(me, CLS_ATPROD); LSQRB_TRY(do_atprod_fused(me)); }
     }
+    { ProfScope p(me, CLS_APROD);  LSQRB_TRY(do_aprod(me, nullptr)); }
+    { ProfScope p(me, CLS_ATPROD); LSQRB_TRY(do_atprod<FIN_ATPROD>(me)); }
     { ProfScope p(me, CLS_UPDATE); LSQRB_TRY(launch_update<true>(wk, me->n, me->x, me->w, me->v, me->se, wantse)); }
     return LSQR_B200_OK;
 }
@@ -1214,6 +687,7 @@ static int build_graph(lsqr_b200_ez *me, bool wantse)
     if (rc == LSQR_B200_OK) rc = join_side(me);   // every fork rejoins the origin stream before the capture ends
     me->side_pending = false;
     cudaError_t e = cudaStreamEndCapture(wk.stream, &graph);
+    me->graph_launches = wk.launches - saved;
     wk.launches = saved;
     if (rc != LSQR_B200_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
     LSQRB_CUDA(e);
@@ -1231,9 +705,10 @@ static int ez_solve_fused(lsqr_b200_ez *me, const double *b, double damp, double
     const int64_t m = me->m, n = me->n;
     const bool wantse = se != nullptr;
     const bool dist = me->opt.world_size > 1;
-    const bool unfused = dist || me->blocked;
+    const bool peer = me->peer;
     LSQRB_CUDA(cudaSetDevice(wk.device));
-    if (wantse && !me->se) LSQRB_CUDA(cudaMalloc(&me->se, sizeof(double) * (size_t)std::max<int64_t>(n, 1)));
+    if (wantse && !peer && !me->se) LSQRB_CUDA(cudaMalloc(&me->se, sizeof(double) * (size_t)std::max<int64_t>(n, 1)));
+    if (wantse && peer && !me->ses) LSQRB_CUDA(cudaMalloc(&me->ses, sizeof(double) * (size_t)std::max<int64_t>(me->pv.cols, 1) * (size_t)me->opt.world_size));
     wk.launches = 0;
     for (auto e : me->prof_ev) cudaEventDestroy(e);
     me->prof_ev.clear(); me->prof_cls.clear();
@@ -1250,35 +725,51 @@ static int ez_solve_fused(lsqr_b200_ez *me, const double *b, double damp, double
     LSQRB_TRY(wk.reset_state(damp, me->opt.atol, me->opt.btol, me->opt.conlim, me->opt.itnlim, wantse, dist));
 
     // u = b (:242); v = 0, x = 0, se = 0 (:621-630)
+    double *xs = peer ? me->xs + (size_t)me->opt.rank * (size_t)me->pv.cols : nullptr;      // owned slices (peer path)
+    double *ses = peer && wantse ? me->ses + (size_t)me->opt.rank * (size_t)me->pv.cols : nullptr;
     if (m > 0) LSQRB_CUDA(cudaMemcpyAsync(me->u, b, sizeof(double) * (size_t)m, cudaMemcpyDefault, wk.stream));
-    if (n > 0) {
+    if (n > 0 && !peer) {
         LSQRB_CUDA(cudaMemsetAsync(me->v, 0, sizeof(double) * (size_t)n, wk.stream));
         LSQRB_CUDA(cudaMemsetAsync(me->x, 0, sizeof(double) * (size_t)n, wk.stream));
         LSQRB_CUDA(cudaMemsetAsync(me->w, 0, sizeof(double) * (size_t)n, wk.stream));
         if (wantse) LSQRB_CUDA(cudaMemsetAsync(me->se, 0, sizeof(double) * (size_t)n, wk.stream));
+    } else if (peer) {
+        // (v is rewritten slice by slice by its owners in the first exchange; x, w, se are owned slices)
+        LSQRB_CUDA(cudaMemsetAsync(me->xs, 0, sizeof(double) * (size_t)me->pv.cols * (size_t)me->opt.world_size, wk.stream));
+        LSQRB_CUDA(cudaMemsetAsync(me->ws, 0, sizeof(double) * (size_t)me->pv.cols, wk.stream));
+        if (wantse) LSQRB_CUDA(cudaMemsetAsync(me->ses, 0, sizeof(double) * (size_t)me->pv.cols * (size_t)me->opt.world_size, wk.stream));
     }
     // beta = ||u||; v = A'(u/beta); alpha = ||v||; w = v/alpha  (:632-644), lazily normalised
-    if (unfused) {
-        sumsq_kernel<POST_NONE><<<wk.grid_for(m, kThreads), kThreads, 0, wk.stream>>>(m, me->u, wk.st, me->g + n);
+    if (peer) {
+        nrm2_kernel<POST_SSQ><<<wk.grid_for(m, kThreads), kThreads, 0, wk.stream>>>(m, me->u, wk.st, (double *)&wk.st->usq_local);
         wk.launches++;
-        if (dist) LSQRB_TRY(do_atprod_allreduce(me));
-        else      LSQRB_TRY(do_atprod_store(me));
+        LSQRB_TRY(do_atprod_push(me));
+        peer_vfinish_kernel<true><<<peer_grid(me), kThreads, 0, wk.stream>>>(me->pv, wk.st);
+        peer_step_kernel<true><<<1, 32, 0, wk.stream>>>(me->pv, wk.st);
+        init_w_kernel<<<wk.grid_for(std::max<int64_t>(me->slice_len, 1), kThreads), kThreads, 0, wk.stream>>>(me->slice_len, me->ws, me->v + me->slice0, wk.st);
+        wk.launches += 3;
+    } else if (dist) {
+        nrm2_kernel<POST_SSQ><<<wk.grid_for(m, kThreads), kThreads, 0, wk.stream>>>(m, me->u, wk.st, me->g + n);
+        wk.launches++;
+        LSQRB_TRY(do_atprod_allreduce(me));
         vfinish_kernel<true><<<wk.grid_for(n, kThreads), kThreads, 0, wk.stream>>>(n, me->g, me->v, wk.st);
-        wk.launches++;
+        init_w_kernel<<<wk.grid_for(n, kThreads), kThreads, 0, wk.stream>>>(n, me->w, me->v, wk.st);
+        wk.launches += 2;
     } else {
-        sumsq_kernel<POST_INIT_BETA><<<wk.grid_for(m, kThreads), kThreads, 0, wk.stream>>>(m, me->u, wk.st, nullptr);
+        nrm2_kernel<POST_INIT_BETA><<<wk.grid_for(m, kThreads), kThreads, 0, wk.stream>>>(m, me->u, wk.st, nullptr);
         wk.launches++;
-        LSQRB_TRY(do_atprod_init(me));
+        LSQRB_TRY(do_atprod<FIN_INIT_ATPROD>(me));
+        init_w_kernel<<<wk.grid_for(n, kThreads), kThreads, 0, wk.stream>>>(n, me->w, me->v, wk.st);
+        wk.launches++;
     }
-    init_w_kernel<<<wk.grid_for(n, kThreads), kThreads, 0, wk.stream>>>(n, me->w, me->v, wk.st);
     record0_kernel<<<1, 1, 0, wk.stream>>>(wk.st, wk.ring_d);
-    wk.launches += 2;
+    wk.launches++;
     LSQRB_CUDA(cudaGetLastError());
     LSQRB_CUDA(cudaEventRecord(me->ev_t1, wk.stream));
 
     // ---- iteration loop: enqueue batch j+1, then wait for batch j and look at its records -----
-    const bool use_graph = me->opt.use_graph && !me->opt.profile && !dist;
-    if (use_graph) LSQRB_TRY(build_graph(me, wantse));
+    const bool use_graph = me->opt.use_graph && !me->opt.profile && (!dist || env_int("LSQR_B200_DIST_GRAPH", 1) != 0);
+    if (use_graph) { LSQRB_TRY(build_graph(me, wantse)); me->times.iteration_launches = me->graph_launches / std::max(me->batch, 1); }
     const int itnlim = std::max(me->opt.itnlim, 1);   // the reference always runs one iteration (:673-676,798)
     const int B = me->batch;
     int seen = -1, enq = 0, nb = 0, done_batches = 0;   // records consumed, iterations / batches enqueued, batches finished
@@ -1286,10 +777,12 @@ static int ez_solve_fused(lsqr_b200_ez *me, const double *b, double damp, double
     auto enqueue_batch = [&]() -> int {
         if (use_graph) {
             LSQRB_CUDA(cudaGraphLaunch(me->graph_exec, wk.stream));
-            wk.launches += (int64_t)B * (me->deferred ? 2 : (me->blocked ? 2 + me->AT.nblocks : 2) + (me->a_blocked ? (me->fuse_last ? 0 : 1) + me->A.nblocks : 1));
+            wk.launches += me->graph_launches;
         } else {
+            const int64_t before = wk.launches;
             for (int i = 0; i < B; ++i) LSQRB_TRY(enqueue_iteration(me, wantse));
             LSQRB_TRY(join_side(me));
+            me->times.iteration_launches = (wk.launches - before) / B;
         }
         LSQRB_CUDA(cudaEventRecord(wk.ev[nb & 3], wk.stream));
         enq += B;
@@ -1303,7 +796,7 @@ static int ez_solve_fused(lsqr_b200_ez *me, const double *b, double damp, double
     // Keep two batches in flight.  The device stops by itself (done flag; istop = 5 at itnlim), so an
     // over-enqueued batch is a run of no-op kernels.  Launch decisions depend only on the records of
     // fully finished batches, which makes them identical on every rank of a multi-GPU run (all ranks
-    // must enqueue the same sequence of all-reduces).
+    // must enqueue the same sequence of collectives).
     while (!stop) {
         while (nb < done_batches + 2 && enq < itnlim) LSQRB_TRY(enqueue_batch());
         if (done_batches == nb) {
@@ -1315,24 +808,32 @@ static int ez_solve_fused(lsqr_b200_ez *me, const double *b, double damp, double
         done_batches += 1;
         check(std::min(done_batches * B, itnlim));
     }
-    // deferred-update engine: the x/w update of the stopping iteration may still be outstanding
-    if (me->deferred) LSQRB_TRY(do_atprod_upd(me));
     LSQRB_CUDA(cudaEventRecord(me->ev_t2, wk.stream));
 
     // se(i) = rnorm/sqrt(t) sqrt(se(i))  (:857-865)
+    const double *x_src = me->x, *se_src = me->se;
     if (wantse && n > 0) {
         const int64_t mg = dist && me->opt.m_global > 0 ? me->opt.m_global : m;
         double t = 1.0;
         if (mg > n) t = (double)(mg - n);
         if (damp > 0.0) t = (double)mg;
-        se_finish_kernel<<<wk.grid_for(n, kThreads), kThreads, 0, wk.stream>>>(n, me->se, wk.st, t);
+        if (peer) se_finish_kernel<<<wk.grid_for(std::max<int64_t>(me->slice_len, 1), kThreads), kThreads, 0, wk.stream>>>(me->slice_len, ses, wk.st, t);
+        else      se_finish_kernel<<<wk.grid_for(n, kThreads), kThreads, 0, wk.stream>>>(n, me->se, wk.st, t);
         wk.launches++;
-        LSQRB_CUDA(cudaMemcpyAsync(se, me->se, sizeof(double) * (size_t)n, cudaMemcpyDefault, wk.stream));
     }
-    if (n > 0) LSQRB_CUDA(cudaMemcpyAsync(x, me->x, sizeof(double) * (size_t)n, cudaMemcpyDefault, wk.stream));
+    if (peer) {
+        // x (and se) exist as owned slices: gather them once, in place
+        NcclApi *api = nccl_api();
+        LSQRB_NCCL(api->AllGather(xs, me->xs, (size_t)me->pv.cols, ncclFloat64, me->comm, wk.stream));
+        if (wantse) LSQRB_NCCL(api->AllGather(ses, me->ses, (size_t)me->pv.cols, ncclFloat64, me->comm, wk.stream));
+        x_src = me->xs; se_src = me->ses;
+    }
+    if (wantse && n > 0) LSQRB_CUDA(cudaMemcpyAsync(se, se_src, sizeof(double) * (size_t)n, cudaMemcpyDefault, wk.stream));
+    if (n > 0) LSQRB_CUDA(cudaMemcpyAsync(x, x_src, sizeof(double) * (size_t)n, cudaMemcpyDefault, wk.stream));
     LSQRB_TRY(wk.fetch_state());
     // any records the loop did not print yet (e.g. the stopping iteration)
     drain_ring(wk, lc, seen, wk.h.itn);
+    if (wk.h.comm_error) { set_last_error("multi-GPU peer exchange timed out (a rank did not arrive)"); return LSQR_B200_ERR_NCCL; }
 
     int is = wk.h.istop;
     if (damp > 0.0 && is == 2) is = 3;   // :871
@@ -1367,9 +868,11 @@ static int ez_solve_fused(lsqr_b200_ez *me, const double *b, double damp, double
     return LSQR_B200_OK;
 }
 
-static int ez_solve_reference_structure(lsqr_b200_ez *me, const double *b, double damp, double *x, int32_t *istop,
-                                        double *se, int32_t *itn, double *anorm, double *acond,
-                                        double *rnorm, double *arnorm, double *xnorm);
+static int ez_solve_through_hook(lsqr_b200_ez *me, const double *b, double damp, double *x, int32_t *istop,
+                                 double *se, int32_t *itn, double *anorm, double *acond,
+                                 double *rnorm, double *arnorm, double *xnorm);
+
+extern "C" {
 
 int lsqr_b200_ez_solve(lsqr_b200_ez *me, const double *b, double damp, double *x, int32_t *istop,
                        double *se, int32_t *itn, double *anorm, double *acond,
@@ -1378,7 +881,7 @@ int lsqr_b200_ez_solve(lsqr_b200_ez *me, const double *b, double damp, double *x
     if (!me) return LSQR_B200_ERR_ARG;
     if ((me->m > 0 && !b) || (me->n > 0 && !x)) { set_last_error("NULL b or x"); return LSQR_B200_ERR_ARG; }
     if (me->opt.engine == 1 && me->opt.world_size == 1)
-        return ez_solve_reference_structure(me, b, damp, x, istop, se, itn, anorm, acond, rnorm, arnorm, xnorm);
+        return ez_solve_through_hook(me, b, damp, x, istop, se, itn, anorm, acond, rnorm, arnorm, xnorm);
     return ez_solve_fused(me, b, damp, x, istop, se, itn, anorm, acond, rnorm, arnorm, xnorm);
 }
 
@@ -1392,26 +895,108 @@ int lsqr_b200_ez_get_kernel_times(const lsqr_b200_ez *me, lsqr_b200_kernel_times
 }  // extern "C"
 
 // =============================================================================================
-// Operator-hook path: LSQR with the reference's pass structure (dscal / aprod / dnrm2 as
-// separate steps, u and v kept normalised), src/lsqr.f90:432-882
+// Operator-hook path: lsqr_solver%lsqr with a caller-supplied device operator (src/lsqr.f90:16-30,67-82,432-882).
+//
+// The callback can only ACCUMULATE (y += A x, x += A'y), so the dscal passes that precede it in the reference
+// (:681, :693) stay separate kernels; everything else is folded:
+//   K_a  u <- (-alpha/beta) u            [+ the x/w update of the previous iteration and v <- v/(alpha beta), one launch]
+//   cb1  u += A v                         (v normalised)            u = A v - alpha u_true          unnormalised, ||u|| = beta'
+//   K_b  ||u||  -> step_after_aprod
+//   K_c  v <- (-beta'^2) v
+//   cb2  v += A'u                         (u unnormalised by beta') v = beta' (A'u_true - beta' v)   ||v|| = beta' alpha'
+//   K_d  ||v||  -> step_after_atprod (alpha' = ||v|| / beta')
+// i.e. 4 launches of ours per iteration instead of 7, u and v each rescaled once instead of twice, and no host
+// synchronisation inside the loop: iterations are enqueued in batches and the device stops itself (done flag);
+// the host learns of the stop from the record ring, exactly like the ez path.
 // =============================================================================================
 namespace lsqrb {
 
-static int scal_dev(Work &wk, int64_t n, double *x, const double *coef)
+// K_a.  m-part: u <- cu u.  n-part (skipped in the very first iteration: nothing to update yet):
+//   v <- cn v (normalise)  ;  x += t1 w ;  w <- v + t2 w ;  se += (t3 w)^2 ; ||w||  -> step_after_update
+// first != 0: the launch that follows the initial bidiagonalisation: w = v <- cn v, no update.
+template <bool WANTSE>
+__global__ void __launch_bounds__(kThreads)
+hook_scale_update_kernel(int64_t m, double *__restrict__ u, int64_t n, double *__restrict__ v, double *__restrict__ w,
+                         double *__restrict__ x, double *__restrict__ se, DevState *st,
+                         volatile lsqr_b200_iter_record *ring, int first)
 {
-    scal_kernel<<<wk.grid_for(n, kThreads), kThreads, 0, wk.stream>>>(n, x, coef, 1.0);
-    wk.launches++;
-    LSQRB_CUDA(cudaGetLastError());
-    return LSQR_B200_OK;
+    __shared__ double s_red[kThreads / 32];
+    __shared__ double s_exc[2 * kThreads];
+    if (st->done) return;
+    const int64_t tid = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    const int64_t nthr = (int64_t)gridDim.x * kThreads;
+    const bool stopping = st->istop != 0;          // the stop is decided: only the update of that iteration is left
+    // ---- n-part first: it closes iteration k (record, done flag)
+    s_exc[threadIdx.x] = 0.0;
+    s_exc[kThreads + threadIdx.x] = 0.0;
+    double sq = 0.0;
+    // v holds beta * alpha * v_true; beta = 0: the A' half was skipped and v is still the normalised v (:691-699)
+    const double cn = st->beta == 0.0 ? 1.0 : st->inv_alpha * st->inv_beta;
+    if (first) {
+        for (int64_t i = tid; i < n; i += nthr) { const double t = cn * v[i]; v[i] = t; w[i] = t; }
+    } else {
+        const double t1 = st->t1, t2 = st->t2, t3 = st->t3;
+        for (int64_t i = tid; i < n; i += nthr) {
+            const double vn = cn * v[i];
+            const double wo = w[i];
+            v[i] = vn;
+            x[i] = t1 * wo + x[i];
+            const double wn = t2 * wo + vn;
+            w[i] = wn;
+            ssq_add(sq, s_exc + threadIdx.x, kThreads, wn);
+            if (WANTSE) se[i] += (t3 * wo) * (t3 * wo);
+        }
+    }
+    // ---- m-part: u <- (-alpha/beta) u  (:681 with the :692 normalisation folded in)
+    if (!stopping) {
+        const double cu = st->ca_vec;
+        for (int64_t i = tid; i < m; i += nthr) u[i] = cu * u[i];
+    }
+    if (first) return;
+    Ssq total;
+    if (finish_ssq<kThreads>(st, 1, st->partial2, sq, s_exc, s_red, &total)) {
+        __threadfence();
+        step_after_update(*st, ssq_norm(total), n > 0 ? __ldcg(x) : 0.0, ring);
+    }
 }
 
-template <int POST>
-static int sumsq_dev(Work &wk, int64_t n, const double *x, double *result)
+// K_c: v <- (-beta^2) v  (:693 with the :692 normalisation of u folded into the coefficient); nothing when beta = 0
+__global__ void __launch_bounds__(kThreads)
+hook_scale_v_kernel(int64_t n, double *__restrict__ v, const DevState *st)
 {
-    sumsq_kernel<POST><<<wk.grid_for(n, kThreads), kThreads, 0, wk.stream>>>(n, x, wk.st, result);
-    wk.launches++;
-    LSQRB_CUDA(cudaGetLastError());
-    return LSQR_B200_OK;
+    if (st->done || st->istop != 0 || st->beta == 0.0) return;
+    const double c = -(st->beta * st->beta);
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) v[i] = c * v[i];
+}
+
+// K_b / K_d: the norm that follows a callback.  AFTER_AT: v holds beta * (A'u_true - beta v): alpha = ||v|| / beta.
+template <bool AFTER_AT, bool INIT>
+__global__ void __launch_bounds__(kThreads)
+hook_norm_kernel(int64_t n, const double *__restrict__ x, DevState *st)
+{
+    __shared__ double s_red[kThreads / 32];
+    __shared__ double s_exc[2 * kThreads];
+    if (st->done || (!INIT && st->istop != 0)) return;
+    if (AFTER_AT && !INIT && st->beta == 0.0) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) step_after_atprod(*st, 0.0, false);   // A' half skipped, alpha kept (:691-699)
+        return;
+    }
+    s_exc[threadIdx.x] = 0.0;
+    s_exc[kThreads + threadIdx.x] = 0.0;
+    double sq = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads)
+        ssq_add(sq, s_exc + threadIdx.x, kThreads, x[i]);
+    Ssq total;
+    if (finish_ssq<kThreads>(st, 2, st->partial, sq, s_exc, s_red, &total)) {
+        const double nrm = ssq_norm(total);
+        if (INIT) {
+            if (!AFTER_AT) step_init_beta(*st, nrm);
+            else           step_init_alpha(*st, st->beta > 0.0 ? nrm * st->inv_beta : 0.0);
+        } else {
+            if (!AFTER_AT) step_after_aprod(*st, nrm);
+            else           step_after_atprod(*st, nrm * st->inv_beta, true);
+        }
+    }
 }
 
 static int lsqr_with_operator(Work &wk, lsqr_b200_aprod_fn aprod, void *aprod_user,
@@ -1420,7 +1005,7 @@ static int lsqr_with_operator(Work &wk, lsqr_b200_aprod_fn aprod, void *aprod_us
                               double atol, double btol, double conlim, int32_t itnlim,
                               const lsqr_b200_options *opts,
                               int32_t *istop, int32_t *itn, double *anorm, double *acond,
-                              double *rnorm, double *arnorm, double *xnorm)
+                              double *rnorm, double *arnorm, double *xnorm, int64_t est_bytes_per_iter = 0)
 {
     LSQRB_CUDA(cudaSetDevice(wk.device));
     DevState *st = wk.st;
@@ -1436,40 +1021,70 @@ static int lsqr_with_operator(Work &wk, lsqr_b200_aprod_fn aprod, void *aprod_us
         if (rc != 0) { set_last_error("aprod callback returned " + std::to_string(rc)); return LSQR_B200_ERR_CALLBACK; }
         return LSQR_B200_OK;
     };
+    const int gm = wk.grid_for(m, kThreads), gn = wk.grid_for(n, kThreads), gmn = std::max(gm, gn);
+    auto scale_update = [&](int first) -> int {
+        if (wantse) hook_scale_update_kernel<true><<<gmn, kThreads, 0, wk.stream>>>(m, u, n, v, w, x, se, st, wk.ring_d, first);
+        else        hook_scale_update_kernel<false><<<gmn, kThreads, 0, wk.stream>>>(m, u, n, v, w, x, se, st, wk.ring_d, first);
+        wk.launches++;
+        LSQRB_CUDA(cudaGetLastError());
+        return LSQR_B200_OK;
+    };
 
-    // :621-644
+    // :621-653: beta = ||u||, v = A'u (u unnormalised), alpha = ||v|| / beta, v <- v/(alpha beta), w = v
     if (n > 0) {
         LSQRB_CUDA(cudaMemsetAsync(v, 0, sizeof(double) * (size_t)n, wk.stream));
         LSQRB_CUDA(cudaMemsetAsync(x, 0, sizeof(double) * (size_t)n, wk.stream));
         if (wantse) LSQRB_CUDA(cudaMemsetAsync(se, 0, sizeof(double) * (size_t)n, wk.stream));
     }
-    LSQRB_TRY(sumsq_dev<POST_INIT_BETA>(wk, m, u, nullptr));
-    LSQRB_TRY(scal_dev(wk, m, u, &st->g_c1));            // u /= beta
-    LSQRB_TRY(call_aprod(2));                            // v += A'u
-    LSQRB_TRY(sumsq_dev<POST_INIT_ALPHA>(wk, n, v, nullptr));
-    LSQRB_TRY(scal_dev(wk, n, v, &st->g_c3));            // v /= alpha
-    LSQRB_CUDA(cudaMemcpyAsync(w, v, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, wk.stream));   // dcopy
+    hook_norm_kernel<false, true><<<gm, kThreads, 0, wk.stream>>>(m, u, st);
+    LSQRB_TRY(call_aprod(2));
+    hook_norm_kernel<true, true><<<gn, kThreads, 0, wk.stream>>>(n, v, st);
+    wk.launches += 2;
+    LSQRB_TRY(scale_update(1));                          // w = v <- v/(alpha beta); u <- (-alpha/beta) u for iteration 1
     record0_kernel<<<1, 1, 0, wk.stream>>>(st, wk.ring_d);
     wk.launches++;
+    LSQRB_CUDA(cudaGetLastError());
     LSQRB_CUDA(cudaStreamSynchronize(wk.stream));
 
     int seen = -1;
     bool stop = drain_ring(wk, lc, seen, 0);
     if (wk.ring_h[0].istop != 0.0 || wk.ring_h[0].arnorm == 0.0) stop = true;   // alpha*beta = 0 (:646)
-    int k = 0;
-    while (!stop && k < itnlim) {
-        ++k;
-        LSQRB_TRY(scal_dev(wk, m, u, &st->g_c0));        // u *= -alpha            (:681)
-        LSQRB_TRY(call_aprod(1));                        // u += A v               (:682)
-        LSQRB_TRY(sumsq_dev<POST_G_BETA>(wk, m, u, nullptr));   // beta, anorm     (:683-689)
-        LSQRB_TRY(scal_dev(wk, m, u, &st->g_c1));        // u /= beta              (:692)
-        LSQRB_TRY(scal_dev(wk, n, v, &st->g_c2));        // v *= -beta             (:693)
-        LSQRB_TRY(call_aprod(2));                        // v += A'u               (:694)
-        LSQRB_TRY(sumsq_dev<POST_G_ALPHA>(wk, n, v, nullptr));  // alpha, rotations, tests (:695-810)
-        LSQRB_TRY(scal_dev(wk, n, v, &st->g_c3));        // v /= alpha             (:697)
-        LSQRB_TRY(launch_update<false>(wk, n, x, w, v, se, wantse != 0));   // (:729-745)
-        LSQRB_CUDA(cudaStreamSynchronize(wk.stream));
-        stop = drain_ring(wk, lc, seen, k);
+
+    // iterations per enqueue: ~300 us of device time (the callbacks are opaque, so no CUDA graph here)
+    int B = 1;
+    if (est_bytes_per_iter > 0) {
+        const double est_us = (double)est_bytes_per_iter / 2.5e6 + 30.0;
+        B = std::max(1, std::min((int)std::ceil(300.0 / est_us), 8));
+    }
+    B = std::max(1, std::min(env_int("LSQR_B200_HOOK_BATCH", B), kRingSize / 4));
+    const int lim = std::max(itnlim, 1);
+    int enq = 0, nb = 0, done_batches = 0;
+    auto enqueue_batch = [&]() -> int {
+        for (int i = 0; i < B; ++i) {
+            LSQRB_TRY(call_aprod(1));                                                  // u += A v           (:682)
+            hook_norm_kernel<false, false><<<gm, kThreads, 0, wk.stream>>>(m, u, st);  // beta, anorm       (:683-689)
+            hook_scale_v_kernel<<<gn, kThreads, 0, wk.stream>>>(n, v, st);             // v *= -beta        (:693)
+            LSQRB_TRY(call_aprod(2));                                                  // v += A'u           (:694)
+            hook_norm_kernel<true, false><<<gn, kThreads, 0, wk.stream>>>(n, v, st);   // alpha, rotations, tests (:695-810)
+            wk.launches += 3;
+            LSQRB_TRY(scale_update(0));                                                // x, w, se (:729-745); v, u rescaled
+        }
+        LSQRB_CUDA(cudaGetLastError());
+        LSQRB_CUDA(cudaEventRecord(wk.ev[nb & 3], wk.stream));
+        enq += B;
+        nb += 1;
+        return LSQR_B200_OK;
+    };
+    while (!stop) {
+        while (nb < done_batches + 2 && enq < lim) LSQRB_TRY(enqueue_batch());
+        if (done_batches == nb) {
+            LSQRB_CUDA(cudaStreamSynchronize(wk.stream));
+            stop = drain_ring(wk, lc, seen, lim);
+            break;
+        }
+        LSQRB_CUDA(cudaEventSynchronize(wk.ev[done_batches & 3]));
+        done_batches += 1;
+        stop = drain_ring(wk, lc, seen, std::min(done_batches * B, lim));
     }
     if (wantse && n > 0) {
         double t = 1.0;
@@ -1479,6 +1094,7 @@ static int lsqr_with_operator(Work &wk, lsqr_b200_aprod_fn aprod, void *aprod_us
         wk.launches++;
     }
     LSQRB_TRY(wk.fetch_state());
+    drain_ring(wk, lc, seen, wk.h.itn);
     int is = wk.h.istop;
     if (damp > 0.0 && is == 2) is = 3;
     lc.footer(is, wk.h);
@@ -1509,9 +1125,10 @@ __global__ void xcheck_w_kernel(int64_t n, double *w, const double *v, const dou
 
 static int reduce_to_host(Work &wk, int64_t n, const double *x, const double *y, double *out)
 {
-    double *d_res = &wk.st->partial[kMaxPartials - 1];   // last slot is never used as a block partial (grid < kMaxPartials)
+    // y != NULL: x'y ; y == NULL: ||x|| (scaled, src/lsqrblas.f90:123-159)
+    double *d_res = &wk.st->partial[0][kMaxPartials - 1];   // last slot is never used as a block partial (grid < kMaxPartials)
     if (y) dot_kernel<<<std::min(wk.grid_for(n, kThreads), kMaxPartials - 1), kThreads, 0, wk.stream>>>(n, x, y, wk.st, d_res);
-    else   sumsq_kernel<POST_NONE><<<std::min(wk.grid_for(n, kThreads), kMaxPartials - 1), kThreads, 0, wk.stream>>>(n, x, wk.st, d_res);
+    else   nrm2_kernel<POST_NONE><<<std::min(wk.grid_for(n, kThreads), kMaxPartials - 1), kThreads, 0, wk.stream>>>(n, x, wk.st, d_res);
     wk.launches++;
     LSQRB_CUDA(cudaGetLastError());
     LSQRB_CUDA(cudaMemcpyAsync(out, d_res, sizeof(double), cudaMemcpyDeviceToHost, wk.stream));
@@ -1531,9 +1148,15 @@ struct ScopedWork {   // a Work for handle-less entry points
     Work wk;
     bool ok = false;
     int rc;
-    ScopedWork(const lsqr_b200_options *o, void *stream_override = nullptr)
+    ScopedWork(const lsqr_b200_options *o)
     {
-        rc = wk.init(o ? o->device : -1, stream_override ? stream_override : (o ? o->stream : nullptr));
+        rc = wk.init(o ? o->device : -1, o ? o->stream : nullptr);
+        ok = rc == LSQR_B200_OK;
+    }
+    // BLAS-1 entry points: `stream` is a plain cudaStream_t argument, NULL = the legacy default stream
+    explicit ScopedWork(void *stream_arg)
+    {
+        rc = wk.init(-1, stream_arg, true);
         ok = rc == LSQR_B200_OK;
     }
     ~ScopedWork() { wk.destroy(); }
@@ -1541,10 +1164,12 @@ struct ScopedWork {   // a Work for handle-less entry points
 
 }  // namespace lsqrb
 
-static int ez_solve_reference_structure(lsqr_b200_ez *me, const double *b, double damp, double *x, int32_t *istop,
-                                        double *se, int32_t *itn, double *anorm, double *acond,
-                                        double *rnorm, double *arnorm, double *xnorm)
+static int ez_solve_through_hook(lsqr_b200_ez *me, const double *b, double damp, double *x, int32_t *istop,
+                                 double *se, int32_t *itn, double *anorm, double *acond,
+                                 double *rnorm, double *arnorm, double *xnorm)
 {
+    // engine = 1: the ez matrix driven through the operator-hook loop (separate dscal / aprod / dnrm2 steps), the way
+    // class(lsqr_solver_ez) is a lsqr_solver in the reference; an A/B check of the fused engine
     Work &wk = me->wk;
     const int64_t m = me->m, n = me->n;
     const bool wantse = se != nullptr;
@@ -1556,7 +1181,7 @@ static int ez_solve_reference_structure(lsqr_b200_ez *me, const double *b, doubl
     LSQRB_TRY(lsqr_with_operator(wk, lsqr_b200_ez_aprod_device, me, me->m, me->n, damp, wantse,
                                  me->u, me->v, me->w, me->x, me->se,
                                  me->opt.atol, me->opt.btol, me->opt.conlim, me->opt.itnlim, &o,
-                                 istop, itn, anorm, acond, rnorm, arnorm, xnorm));
+                                 istop, itn, anorm, acond, rnorm, arnorm, xnorm, 24 * me->nnz));
     if (n > 0) LSQRB_CUDA(cudaMemcpyAsync(x, me->x, sizeof(double) * (size_t)n, cudaMemcpyDefault, wk.stream));
     if (wantse && n > 0) LSQRB_CUDA(cudaMemcpyAsync(se, me->se, sizeof(double) * (size_t)n, cudaMemcpyDefault, wk.stream));
     LSQRB_CUDA(cudaStreamSynchronize(wk.stream));
@@ -1601,7 +1226,6 @@ int lsqr_b200_acheck(lsqr_b200_aprod_fn aprod, void *aprod_user, int32_t m, int3
     double alfa, beta;
     LSQRB_TRY(reduce_to_host(wk, n, x, nullptr, &alfa));
     LSQRB_TRY(reduce_to_host(wk, m, y, nullptr, &beta));
-    alfa = sqrt(alfa); beta = sqrt(beta);
     LSQRB_TRY(scal_imm(wk, n, x, 1.0 / alfa));
     LSQRB_TRY(scal_imm(wk, m, y, 1.0 / beta));
     LSQRB_CUDA(cudaMemcpyAsync(w, y, sizeof(double) * (size_t)m, cudaMemcpyDeviceToDevice, wk.stream));
@@ -1646,9 +1270,10 @@ int lsqr_b200_xcheck(lsqr_b200_aprod_fn aprod, void *aprod_user, int32_t m, int3
     // v = A'u (:1080-1083)
     if (rc == 0) rc = cudaMemsetAsync(v, 0, sizeof(double) * (size_t)n, wk.stream) == cudaSuccess ? 0 : LSQR_B200_ERR_CUDA;
     if (rc == 0) rc = aprod(aprod_user, 2, m, n, v, u, (void *)wk.stream);
-    cudaStreamSynchronize(wk.stream);
+    const cudaError_t sync_err = cudaStreamSynchronize(wk.stream);
     cudaFree(xtmp);
     if (rc != 0) return rc == LSQR_B200_ERR_CUDA ? rc : LSQR_B200_ERR_CALLBACK;
+    LSQRB_CUDA(sync_err);
     // w = A'u - damp^2 x (:1089-1094)
     xcheck_w_kernel<<<wk.grid_for(n, kThreads), kThreads, 0, wk.stream>>>(n, w, v, x, damp != 0.0 ? dampsq : 0.0);
     double bnorm, xnorm, rho1, sigma1, rho2, sigma2;
@@ -1656,14 +1281,12 @@ int lsqr_b200_xcheck(lsqr_b200_aprod_fn aprod, void *aprod_user, int32_t m, int3
     LSQRB_TRY(reduce_to_host(wk, n, x, nullptr, &xnorm));
     LSQRB_TRY(reduce_to_host(wk, m, u, nullptr, &rho1));
     LSQRB_TRY(reduce_to_host(wk, n, v, nullptr, &sigma1));
-    bnorm = sqrt(bnorm); xnorm = sqrt(xnorm); rho1 = sqrt(rho1); sigma1 = sqrt(sigma1);
     if (damp == 0.0) {
         rho2 = rho1;
         sigma2 = sigma1;
     } else {
         rho2 = sqrt(rho1 * rho1 + dampsq * (xnorm * xnorm));
         LSQRB_TRY(reduce_to_host(wk, n, w, nullptr, &sigma2));
-        sigma2 = sqrt(sigma2);
     }
     int inf;
     double t1 = 0, t2 = 0, t3 = 0;
@@ -1717,19 +1340,23 @@ int lsqr_b200_dnrm2(int64_t n, const double *x, double *result, void *stream)
 {
     if (!result || n < 0 || (n > 0 && !x)) return LSQR_B200_ERR_ARG;
     if (n < 1) { *result = 0.0; return LSQR_B200_OK; }   // :131
-    ScopedWork sw(nullptr, stream);
+    ScopedWork sw(stream);
     if (!sw.ok) return sw.rc;
-    double s;
-    LSQRB_TRY(reduce_to_host(sw.wk, n, x, nullptr, &s));
-    *result = sqrt(s);
-    return LSQR_B200_OK;
+    if (n == 1) {   // :132 -- abs(x(1))
+        double t;
+        LSQRB_CUDA(cudaMemcpyAsync(&t, x, sizeof(double), cudaMemcpyDeviceToHost, sw.wk.stream));
+        LSQRB_CUDA(cudaStreamSynchronize(sw.wk.stream));
+        *result = fabs(t);
+        return LSQR_B200_OK;
+    }
+    return reduce_to_host(sw.wk, n, x, nullptr, result);
 }
 
 int lsqr_b200_ddot(int64_t n, const double *x, const double *y, double *result, void *stream)
 {
     if (!result || n < 0 || (n > 0 && (!x || !y))) return LSQR_B200_ERR_ARG;
     if (n < 1) { *result = 0.0; return LSQR_B200_OK; }
-    ScopedWork sw(nullptr, stream);
+    ScopedWork sw(stream);
     if (!sw.ok) return sw.rc;
     return reduce_to_host(sw.wk, n, x, y, result);
 }
@@ -1738,7 +1365,7 @@ int lsqr_b200_dscal(int64_t n, double da, double *x, void *stream)
 {
     if (n < 0 || (n > 0 && !x)) return LSQR_B200_ERR_ARG;
     if (n == 0) return LSQR_B200_OK;
-    ScopedWork sw(nullptr, stream);
+    ScopedWork sw(stream);
     if (!sw.ok) return sw.rc;
     LSQRB_TRY(scal_imm(sw.wk, n, x, da));
     LSQRB_CUDA(cudaStreamSynchronize(sw.wk.stream));

@@ -24,7 +24,7 @@ from typing import Callable, Optional
 import numpy as np
 
 from . import _lib
-from ._lib import LsqrError, Options, KernelTimes
+from ._lib import LsqrError, Options, KernelTimes, PlanInfo
 
 
 # --------------------------------------------------------------------------------------------
@@ -244,6 +244,13 @@ class LsqrSolverEz:
         _lib.check(_lib.load().lsqr_b200_ez_schedule(self._h, int(transpose), int(block), C.byref(nt), C.byref(te),
                                                      C.byref(bal), C.byref(imb)))
         return {"ntiles": nt.value, "tile_entries": te.value, "balanced": bool(bal.value), "imbalance": imb.value}
+
+    def plan(self, transpose: bool = False) -> dict:
+        """Work plan of the SpMV kernel over the stored A (or A'): blocks, tiles, persistent grid, kernel flavour,
+        shared-memory gather window and the fraction of the entries it serves, schedule balance."""
+        p = PlanInfo()
+        _lib.check(_lib.load().lsqr_b200_ez_plan(self._h, int(transpose), C.byref(p)))
+        return {k: getattr(p, k) for k, _ in PlanInfo._fields_}
 
     def transpose_blocks(self):
         return self.blocks(True)

@@ -62,6 +62,26 @@ def build(force: bool = False) -> str:
     return _LIB_PATH
 
 
+def use_native_build() -> str:
+    """For the TIMED CPU baseline only: compile a copy of the oracle for the CPU of the box it runs on
+    (gcc -O3 -march=native -ffp-contract=off) and make lib() load it.  Call before the first
+    use of the oracle in a process.  Returns the flags in use; falls back to the portable -O2 build if the compile
+    fails or the library is already loaded."""
+    global _LIB_PATH
+    flags = "-O2 -ffp-contract=off"
+    if _lib is not None:
+        return flags
+    native = os.path.join(_HERE, "build", "liblsqr_oracle_native.so")
+    try:
+        subprocess.run(["make", "-B", "-C", _HERE, "native"], check=True, capture_output=True)   # always for THIS CPU
+        if os.path.exists(native):
+            _LIB_PATH = native
+            flags = "-O3 -march=native -ffp-contract=off"
+    except Exception:
+        pass
+    return flags
+
+
 _lib = None
 
 

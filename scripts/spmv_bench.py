@@ -1,12 +1,12 @@
 #!/usr/bin/env python
-"""Kernel-level A/B bench of the SpMV variants on the BASELINE workload families (GPU box only).
+"""Kernel-level A/B bench of the SpMV kernel modes on the BASELINE workload families (GPU box only).
 
-    python scripts/spmv_bench.py [--variants 2,3] [--workloads C2:1,C3:5,C5:20,C4:10] [--reps 20]
+    python scripts/spmv_bench.py [--modes default,perblock,nowindow] [--workloads C2:1,C3:5,C5:20,C4:10] [--reps 20]
 
-For every workload (name:scale) and variant it times y += A x (mode 1) and x += A'y (mode 2) through the
+For every workload (name:scale) and mode (environment switches read at initialize) it times y += A x (mode 1) and x += A'y (mode 2) through the
 C ABI (lsqr_b200_ez_aprod on device vectors) with CUDA events on the stream the kernels run on, reports
-algorithmic GB/s against MEASURED_PEAKS.json, cross-checks the variants against each other, and times a
-full solve.  One JSON line per (workload, variant).
+algorithmic GB/s against MEASURED_PEAKS.json, cross-checks the modes against each other, and times a
+full solve.  One JSON line per (workload, mode).
 """
 import argparse
 import json
@@ -24,9 +24,18 @@ import lsqr_b200
 from lsqr_b200 import synth, synth_device
 
 
+MODES = {
+    "default": {},
+    "perblock": {"LSQR_B200_SINGLE_LAUNCH": "0"},
+    "noguard": {"LSQR_B200_DRIFT_GUARD": "0"},
+    "nowindow": {"LSQR_B200_WINDOW": "0"},
+    "nooverlap": {"LSQR_B200_OVERLAP_UPDATE": "0"},
+}
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--variants", default="2,3")
+    ap.add_argument("--modes", default="default,perblock,nowindow")
     ap.add_argument("--workloads", default="C2:1,C3:5,C5:20,C4:10")
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--solve", type=int, default=1)
@@ -45,14 +54,22 @@ def main():
         xt = synth_device.x_true(cfg["seed"], n, dev)
         yt = synth_device.noise(cfg["seed"], 0, m, dev, scale=1.0)
         ref = {}
-        for variant in [int(v) for v in args.variants.split(",")]:
+        for mode_name in args.modes.split(","):
+            for env in MODES.values():
+                for k in env:
+                    os.environ.pop(k, None)
+            os.environ.update(MODES[mode_name])
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            s = lsqr_b200.LsqrSolverEz().initialize(m, n, a, irow, icol, stream=stream, spmv_variant=variant,
+            s = lsqr_b200.LsqrSolverEz().initialize(m, n, a, irow, icol, stream=stream,
                                                     atol=1e-10, btol=1e-10, conlim=1e8, itnlim=100000)
             torch.cuda.synchronize()
             t_init = time.perf_counter() - t0
-            out = {"workload": f"{name}/{scale}", "m": m, "n": n, "nnz": nnz, "variant": variant, "init_s": round(t_init, 3)}
+            pa, pat = s.plan(False), s.plan(True)
+            out = {"workload": f"{name}/{scale}", "m": m, "n": n, "nnz": nnz, "mode": mode_name, "init_s": round(t_init, 3),
+                   "blocks": [pa["nblocks"], pat["nblocks"]], "window": [pa["window_doubles"], pat["window_doubles"]],
+                   "windowed": [round(pa["windowed_fraction"], 3), round(pat["windowed_fraction"], 3)],
+                   "ctas_per_sm": [pa["ctas_per_sm"], pat["ctas_per_sm"]], "span_max": [pa["span_max"], pat["span_max"]]}
             for mode in (1, 2):
                 x = xt.clone()
                 y = yt.clone()

@@ -28,6 +28,21 @@ def test_reference_arm_prints_one_json_line():
     assert cb["kind"] == "port" and cb["cores"] == 1 and cb["value"] == d["value"] and "C2 at 1/20 scale" in cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["config"]["workload"] == "C2"
+    assert cb["cpu_model"] and cb["cores_present"] >= 1 and cb["sample_scale"] == 20
+    assert "-ffp-contract=off" in cb["sample"]
+
+
+def test_reference_arm_never_maps_the_engine_library():
+    """The reference arm times the oracle port only: the process must not load liblsqr_b200.so (the driver records
+    which of the repo's .so files each arm maps)."""
+    code = ("import sys, os; sys.path.insert(0, %r); sys.argv = ['bench.py', '--impl', 'reference', '--workload', 'C2', "
+            "'--cpu-scale', '50', '--steps', '1', '--warmup', '0']; import bench; bench.main()\n"
+            "maps = open('/proc/self/maps').read()\n"
+            "sys.stderr.write('ENGINE_MAPPED=%%d ORACLE_MAPPED=%%d' %% ('liblsqr_b200' in maps, 'liblsqr_oracle' in maps))\n") % ROOT
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "ENGINE_MAPPED=0 ORACLE_MAPPED=1" in r.stderr
+    assert "lsqr_b200" not in [m.split(".")[0] for m in r.stderr.split() if m.startswith("IMPORTED:")]
 
 
 def test_reference_arm_other_ranks_exit_quietly():
