@@ -250,6 +250,9 @@ def main():
         import torch.distributed as td
         td.init_process_group("nccl", device_id=dev)
 
+    if rank == 0:
+        from oracle import oracle as O      # the checker / CPU baseline: compiled for THIS box's CPU before its first use
+        O.use_native_build()
     name = pick_workload(args)
     res = run_workload(name, args, args.steps, world, rank, dev, with_roofline=True)
 

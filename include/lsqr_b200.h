@@ -257,14 +257,43 @@ LSQR_B200_API int lsqr_b200_xcheck(lsqr_b200_aprod_fn aprod, void *aprod_user, i
                      int32_t *inform, double *test1, double *test2, double *test3,
                      double *norms);
 
+/* ---- the abstract class with the reference's own signatures: HOST arrays, HOST operator -------------------- */
+/* Replaces the deferred  aprod  exactly as the reference declares it (aprod_func, src/lsqr.f90:67-82): x(n) and
+ * y(m) are HOST arrays, both intent(inout); mode 1: y = y + A*x, mode 2: x = x + A'*y.  Return 0 on success. */
+typedef int (*lsqr_b200_aprod_host_fn)(void *user, int32_t mode, int32_t m, int32_t n, double *x, double *y);
+
+/* lsqr_solver%lsqr / %acheck / %xcheck with the reference's argument lists (src/lsqr.f90:432-435, :908, :1015):
+ * every vector is a HOST (or device) array and the operator is host code, so each product makes a host round trip;
+ * all vector arithmetic and the scalar recurrence still run on the GPU.  This is the form an unmodified
+ * type,extends(lsqr_solver) of the reference binds to (fortran/lsqr_b200_shim.F90); supply a device operator through
+ * lsqr_b200_lsqr for speed.  u(m) holds b on entry and is overwritten; v, w, x (n), se (n, if wantse) are outputs. */
+LSQR_B200_API int lsqr_b200_lsqr_host(lsqr_b200_aprod_host_fn aprod, void *aprod_user,
+                        int32_t m, int32_t n, double damp, int32_t wantse,
+                        double *u, double *v, double *w, double *x, double *se,
+                        double atol, double btol, double conlim, int32_t itnlim,
+                        const lsqr_b200_options *opts,
+                        int32_t *istop, int32_t *itn, double *anorm, double *acond,
+                        double *rnorm, double *arnorm, double *xnorm);
+LSQR_B200_API int lsqr_b200_acheck_host(lsqr_b200_aprod_host_fn aprod, void *aprod_user, int32_t m, int32_t n,
+                          double eps, double *v, double *w, double *x, double *y,
+                          const lsqr_b200_options *opts, int32_t *inform, double *relerr);
+LSQR_B200_API int lsqr_b200_xcheck_host(lsqr_b200_aprod_host_fn aprod, void *aprod_user, int32_t m, int32_t n,
+                          double anorm, double damp, double eps,
+                          const double *b, double *u, double *v, double *w, const double *x,
+                          const lsqr_b200_options *opts,
+                          int32_t *inform, double *test1, double *test2, double *test3, double *norms);
+
 /* An lsqr_b200_aprod_fn backed by an ez handle (user = the lsqr_b200_ez*), so the ez matrix can
  * be driven through the low-level path exactly like  class(lsqr_solver_ez) -> lsqr_solver. */
 LSQR_B200_API int lsqr_b200_ez_aprod_device(void *ez_handle, int32_t mode, int32_t m, int32_t n,
                               double *x_dev, double *y_dev, void *stream);
 
 /* ------------------------------------------------------------------ device BLAS-1 (src/lsqrblas.f90) */
-/* Deterministic device versions of the reference's vector kernels on DEVICE arrays
- * (stride 1 only -- the only form the hot path uses).  stream may be NULL. */
+/* Deterministic device versions of the reference's vector kernels (stride 1 only -- the only form the hot path
+ * uses; the Fortran layer packs strided arguments).  The arrays may be DEVICE arrays (used in place) or HOST arrays
+ * (staged through the GPU: the arithmetic always happens on the device).  stream NULL = legacy default stream.
+ * dnrm2 is the SCALED norm of the reference (it neither overflows nor underflows, :136-154), computed with Blue's
+ * three accumulators. */
 LSQR_B200_API int lsqr_b200_dnrm2(int64_t n, const double *x_dev, double *result_host, void *stream);  /* :123-159 */
 LSQR_B200_API int lsqr_b200_ddot (int64_t n, const double *x_dev, const double *y_dev, double *result_host, void *stream); /* :74-116 */
 LSQR_B200_API int lsqr_b200_dscal(int64_t n, double da, double *x_dev, void *stream);                  /* :166-201 */

@@ -9,7 +9,7 @@ from ._lib import LsqrError, LIB_PATH
 
 _lib.load()   # fail loudly when the CUDA extension is missing
 
-from .solver import (LsqrSolverEz, LsqrSolver, EzAsOperator, SolveResult,   # noqa: E402
+from .solver import (LsqrSolverEz, LsqrSolver, LsqrSolverHost, EzAsOperator, SolveResult,   # noqa: E402
                      dnrm2, ddot, dscal, dcopy)
 
 
@@ -21,5 +21,5 @@ def version() -> int:
     return _lib.load().lsqr_b200_version()
 
 
-__all__ = ["LsqrSolverEz", "LsqrSolver", "EzAsOperator", "SolveResult", "LsqrError", "LIB_PATH",
+__all__ = ["LsqrSolverEz", "LsqrSolver", "LsqrSolverHost", "EzAsOperator", "SolveResult", "LsqrError", "LIB_PATH",
            "dnrm2", "ddot", "dscal", "dcopy", "device_count", "version"]

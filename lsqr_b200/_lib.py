@@ -19,6 +19,7 @@ class IterRecord(C.Structure):
 
 ITER_FN = C.CFUNCTYPE(None, C.c_void_p, C.POINTER(IterRecord))
 APROD_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p)
+APROD_HOST_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double))
 
 
 class Options(C.Structure):
@@ -135,6 +136,16 @@ def load() -> C.CDLL:
     L.lsqr_b200_xcheck.restype = C.c_int
     L.lsqr_b200_xcheck.argtypes = [APROD_FN, vp, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_double,
                                    vp, vp, vp, vp, vp, C.POINTER(Options), ip, dp, dp, dp, dp]
+    L.lsqr_b200_lsqr_host.restype = C.c_int
+    L.lsqr_b200_lsqr_host.argtypes = [APROD_HOST_FN, vp, C.c_int32, C.c_int32, C.c_double, C.c_int32,
+                                      vp, vp, vp, vp, vp, C.c_double, C.c_double, C.c_double, C.c_int32,
+                                      C.POINTER(Options), ip, ip, dp, dp, dp, dp, dp]
+    L.lsqr_b200_acheck_host.restype = C.c_int
+    L.lsqr_b200_acheck_host.argtypes = [APROD_HOST_FN, vp, C.c_int32, C.c_int32, C.c_double, vp, vp, vp, vp,
+                                        C.POINTER(Options), ip, dp]
+    L.lsqr_b200_xcheck_host.restype = C.c_int
+    L.lsqr_b200_xcheck_host.argtypes = [APROD_HOST_FN, vp, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_double,
+                                        vp, vp, vp, vp, vp, C.POINTER(Options), ip, dp, dp, dp, dp]
     L.lsqr_b200_dnrm2.restype = C.c_int
     L.lsqr_b200_dnrm2.argtypes = [C.c_int64, vp, dp, vp]
     L.lsqr_b200_ddot.restype = C.c_int

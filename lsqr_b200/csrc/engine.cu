@@ -18,7 +18,7 @@ struct lsqr_b200_ez {
     Csr A, AT;
     TilePlan planA, planAT;       // one plan per stored matrix (all its blocks)
     bool single_launch = true;    // one persistent launch per product walks every block (else one launch per block)
-    bool guard = true;            // soft drift guard between the warps of a multi-block launch
+    int guard = 1;                // multi-block launch: block b starts when every warp has finished block b - guard (0 = no guard)
     bool a_blocked = false;       // A is column-blocked (v does not fit in L2)
     bool at_blocked = false;      // A' is row-blocked (u does not fit in L2)
     double *gu = nullptr;         // [m] partial A v across the column blocks
@@ -306,7 +306,7 @@ static int ez_initialize_impl(lsqr_b200_ez *me, int64_t nnz, const double *a, co
     me->a_blocked = me->A.nblocks > 1;
     me->at_blocked = me->AT.nblocks > 1;
     me->single_launch = env_int("LSQR_B200_SINGLE_LAUNCH", 1) != 0;
-    me->guard = env_int("LSQR_B200_DRIFT_GUARD", 1) != 0;
+    me->guard = std::max(0, std::min(env_int("LSQR_B200_DRIFT_GUARD", 1), 8));
     me->overlap_update = me->opt.world_size == 1 && env_int("LSQR_B200_OVERLAP_UPDATE", 1) != 0;
     if (me->overlap_update) {
         LSQRB_CUDA(cudaStreamCreateWithFlags(&me->side, cudaStreamNonBlocking));
@@ -1335,21 +1335,157 @@ int lsqr_b200_xcheck(lsqr_b200_aprod_fn aprod, void *aprod_user, int32_t m, int3
     return LSQR_B200_OK;
 }
 
-// ---- device BLAS-1 (src/lsqrblas.f90), stride 1 ------------------------------------------------
+// =============================================================================================
+// The abstract class with the REFERENCE's own signatures: host arrays and a host operator
+// (aprod_func, src/lsqr.f90:67-82).  The operator is the user's CPU code, so every product makes a
+// host round trip; everything else of LSQR / acheck / xcheck runs on the GPU exactly as in the
+// device-operator entry points above.  This is what an unmodified  type,extends(lsqr_solver)  of the
+// reference (e.g. test/lsqrtest_module.f90:35-44) binds to; a device operator is the fast path.
+// =============================================================================================
+}  // extern "C"
+
+namespace lsqrb {
+
+// a device image of a vector that may live on the host
+struct DevVec {
+    double *d = nullptr;
+    double *host = nullptr;
+    size_t n = 0;
+    bool owned = false;
+    int in(cudaStream_t s, double *p, int64_t count, bool copy_in)
+    {
+        n = (size_t)std::max<int64_t>(count, 0);
+        if (!p || is_device_ptr(p)) { d = p; return LSQR_B200_OK; }
+        host = p;
+        owned = true;
+        LSQRB_CUDA(cudaMalloc(&d, sizeof(double) * std::max<size_t>(n, 1)));
+        if (copy_in && n) LSQRB_CUDA(cudaMemcpyAsync(d, p, sizeof(double) * n, cudaMemcpyHostToDevice, s));
+        return LSQR_B200_OK;
+    }
+    int out(cudaStream_t s)
+    {
+        if (owned && n) LSQRB_CUDA(cudaMemcpyAsync(host, d, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
+        return LSQR_B200_OK;
+    }
+    ~DevVec() { if (owned && d) cudaFree(d); }
+};
+
+struct HostOperator {   // adapts a host aprod to the device-operator hook
+    lsqr_b200_aprod_host_fn fn;
+    void *user;
+    std::vector<double> hx, hy;
+};
+
+static int host_operator_trampoline(void *user, int32_t mode, int32_t m, int32_t n, double *x_dev, double *y_dev, void *stream)
+{
+    HostOperator *op = (HostOperator *)user;
+    cudaStream_t s = (cudaStream_t)stream;
+    op->hx.resize((size_t)std::max(n, 1));
+    op->hy.resize((size_t)std::max(m, 1));
+    if (cudaMemcpyAsync(op->hx.data(), x_dev, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, s) != cudaSuccess) return 2;
+    if (cudaMemcpyAsync(op->hy.data(), y_dev, sizeof(double) * (size_t)m, cudaMemcpyDeviceToHost, s) != cudaSuccess) return 2;
+    if (cudaStreamSynchronize(s) != cudaSuccess) return 2;
+    const int rc = op->fn(op->user, mode, m, n, op->hx.data(), op->hy.data());
+    if (rc != 0) return rc;
+    // both arrays are intent(inout) in the reference's interface: only the accumulated one can have changed legally
+    if (mode == 1) { if (cudaMemcpyAsync(y_dev, op->hy.data(), sizeof(double) * (size_t)m, cudaMemcpyHostToDevice, s) != cudaSuccess) return 2; }
+    else           { if (cudaMemcpyAsync(x_dev, op->hx.data(), sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, s) != cudaSuccess) return 2; }
+    return cudaStreamSynchronize(s) == cudaSuccess ? 0 : 2;   // (the staging vectors are reused by the next call)
+}
+
+}  // namespace lsqrb
+
+extern "C" {
+
+int lsqr_b200_lsqr_host(lsqr_b200_aprod_host_fn aprod, void *aprod_user,
+                        int32_t m, int32_t n, double damp, int32_t wantse,
+                        double *u, double *v, double *w, double *x, double *se,
+                        double atol, double btol, double conlim, int32_t itnlim,
+                        const lsqr_b200_options *opts,
+                        int32_t *istop, int32_t *itn, double *anorm, double *acond,
+                        double *rnorm, double *arnorm, double *xnorm)
+{
+    if (!aprod || m < 0 || n < 0) return LSQR_B200_ERR_ARG;
+    if ((m > 0 && !u) || (n > 0 && (!v || !w || !x)) || (wantse && n > 0 && !se)) { set_last_error("NULL work vector"); return LSQR_B200_ERR_ARG; }
+    ScopedWork sw(opts);
+    if (!sw.ok) return sw.rc;
+    cudaStream_t s = sw.wk.stream;
+    DevVec du, dv, dw, dx, dse;
+    LSQRB_TRY(du.in(s, u, m, true));            // u holds b on entry (src/lsqr.f90:461-462)
+    LSQRB_TRY(dv.in(s, v, n, false));
+    LSQRB_TRY(dw.in(s, w, n, false));
+    LSQRB_TRY(dx.in(s, x, n, false));
+    LSQRB_TRY(dse.in(s, wantse ? se : nullptr, n, false));
+    HostOperator op{aprod, aprod_user, {}, {}};
+    LSQRB_TRY(lsqr_with_operator(sw.wk, host_operator_trampoline, &op, m, n, damp, wantse, du.d, dv.d, dw.d, dx.d, dse.d,
+                                 atol, btol, conlim, itnlim, opts, istop, itn, anorm, acond, rnorm, arnorm, xnorm));
+    LSQRB_TRY(du.out(s)); LSQRB_TRY(dv.out(s)); LSQRB_TRY(dw.out(s)); LSQRB_TRY(dx.out(s)); LSQRB_TRY(dse.out(s));
+    LSQRB_CUDA(cudaStreamSynchronize(s));
+    return LSQR_B200_OK;
+}
+
+int lsqr_b200_acheck_host(lsqr_b200_aprod_host_fn aprod, void *aprod_user, int32_t m, int32_t n, double eps,
+                          double *v, double *w, double *x, double *y,
+                          const lsqr_b200_options *opts, int32_t *inform, double *relerr)
+{
+    if (!aprod || m < 1 || n < 1 || !v || !w || !x || !y) return LSQR_B200_ERR_ARG;
+    ScopedWork sw(opts);
+    if (!sw.ok) return sw.rc;
+    cudaStream_t s = sw.wk.stream;
+    DevVec dv, dw, dx, dy;
+    LSQRB_TRY(dv.in(s, v, n, false)); LSQRB_TRY(dw.in(s, w, m, false)); LSQRB_TRY(dx.in(s, x, n, false)); LSQRB_TRY(dy.in(s, y, m, false));
+    HostOperator op{aprod, aprod_user, {}, {}};
+    lsqr_b200_options o;
+    if (opts) o = *opts; else lsqr_b200_default_options(&o);
+    o.stream = (void *)s;
+    LSQRB_TRY(lsqr_b200_acheck(host_operator_trampoline, &op, m, n, eps, dv.d, dw.d, dx.d, dy.d, &o, inform, relerr));
+    LSQRB_TRY(dv.out(s)); LSQRB_TRY(dw.out(s)); LSQRB_TRY(dx.out(s)); LSQRB_TRY(dy.out(s));
+    LSQRB_CUDA(cudaStreamSynchronize(s));
+    return LSQR_B200_OK;
+}
+
+int lsqr_b200_xcheck_host(lsqr_b200_aprod_host_fn aprod, void *aprod_user, int32_t m, int32_t n,
+                          double anorm, double damp, double eps,
+                          const double *b, double *u, double *v, double *w, const double *x,
+                          const lsqr_b200_options *opts,
+                          int32_t *inform, double *test1, double *test2, double *test3, double *norms)
+{
+    if (!aprod || m < 1 || n < 1 || !b || !u || !v || !w || !x) return LSQR_B200_ERR_ARG;
+    ScopedWork sw(opts);
+    if (!sw.ok) return sw.rc;
+    cudaStream_t s = sw.wk.stream;
+    DevVec db, du, dv, dw, dx;
+    LSQRB_TRY(db.in(s, const_cast<double *>(b), m, true)); LSQRB_TRY(dx.in(s, const_cast<double *>(x), n, true));
+    LSQRB_TRY(du.in(s, u, m, false)); LSQRB_TRY(dv.in(s, v, n, false)); LSQRB_TRY(dw.in(s, w, n, false));
+    HostOperator op{aprod, aprod_user, {}, {}};
+    lsqr_b200_options o;
+    if (opts) o = *opts; else lsqr_b200_default_options(&o);
+    o.stream = (void *)s;
+    LSQRB_TRY(lsqr_b200_xcheck(host_operator_trampoline, &op, m, n, anorm, damp, eps, db.d, du.d, dv.d, dw.d, dx.d, &o,
+                               inform, test1, test2, test3, norms));
+    LSQRB_TRY(du.out(s)); LSQRB_TRY(dv.out(s)); LSQRB_TRY(dw.out(s));      // r, A'r, A'r - damp^2 x (b and x are inputs)
+    LSQRB_CUDA(cudaStreamSynchronize(s));
+    return LSQR_B200_OK;
+}
+
+// ---- BLAS-1 (src/lsqrblas.f90), stride 1.  Arrays may be DEVICE or HOST arrays (host arrays are staged through the GPU:
+// the arithmetic always happens on the device); the result is a host scalar.
 int lsqr_b200_dnrm2(int64_t n, const double *x, double *result, void *stream)
 {
     if (!result || n < 0 || (n > 0 && !x)) return LSQR_B200_ERR_ARG;
     if (n < 1) { *result = 0.0; return LSQR_B200_OK; }   // :131
     ScopedWork sw(stream);
     if (!sw.ok) return sw.rc;
+    DevVec dx;
+    LSQRB_TRY(dx.in(sw.wk.stream, const_cast<double *>(x), n, true));
     if (n == 1) {   // :132 -- abs(x(1))
         double t;
-        LSQRB_CUDA(cudaMemcpyAsync(&t, x, sizeof(double), cudaMemcpyDeviceToHost, sw.wk.stream));
+        LSQRB_CUDA(cudaMemcpyAsync(&t, dx.d, sizeof(double), cudaMemcpyDeviceToHost, sw.wk.stream));
         LSQRB_CUDA(cudaStreamSynchronize(sw.wk.stream));
         *result = fabs(t);
         return LSQR_B200_OK;
     }
-    return reduce_to_host(sw.wk, n, x, nullptr, result);
+    return reduce_to_host(sw.wk, n, dx.d, nullptr, result);
 }
 
 int lsqr_b200_ddot(int64_t n, const double *x, const double *y, double *result, void *stream)
@@ -1358,7 +1494,10 @@ int lsqr_b200_ddot(int64_t n, const double *x, const double *y, double *result, 
     if (n < 1) { *result = 0.0; return LSQR_B200_OK; }
     ScopedWork sw(stream);
     if (!sw.ok) return sw.rc;
-    return reduce_to_host(sw.wk, n, x, y, result);
+    DevVec dx, dy;
+    LSQRB_TRY(dx.in(sw.wk.stream, const_cast<double *>(x), n, true));
+    LSQRB_TRY(dy.in(sw.wk.stream, const_cast<double *>(y), n, true));
+    return reduce_to_host(sw.wk, n, dx.d, dy.d, result);
 }
 
 int lsqr_b200_dscal(int64_t n, double da, double *x, void *stream)
@@ -1367,7 +1506,10 @@ int lsqr_b200_dscal(int64_t n, double da, double *x, void *stream)
     if (n == 0) return LSQR_B200_OK;
     ScopedWork sw(stream);
     if (!sw.ok) return sw.rc;
-    LSQRB_TRY(scal_imm(sw.wk, n, x, da));
+    DevVec dx;
+    LSQRB_TRY(dx.in(sw.wk.stream, x, n, true));
+    LSQRB_TRY(scal_imm(sw.wk, n, dx.d, da));
+    LSQRB_TRY(dx.out(sw.wk.stream));
     LSQRB_CUDA(cudaStreamSynchronize(sw.wk.stream));
     return LSQR_B200_OK;
 }
@@ -1378,7 +1520,7 @@ int lsqr_b200_dcopy(int64_t n, const double *x, double *y, void *stream)
     if (n == 0) return LSQR_B200_OK;
     int count = lsqr_b200_device_count();
     if (count == 0) return LSQR_B200_ERR_NO_DEVICE;
-    LSQRB_CUDA(cudaMemcpyAsync(y, x, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    LSQRB_CUDA(cudaMemcpyAsync(y, x, sizeof(double) * (size_t)n, cudaMemcpyDefault, (cudaStream_t)stream));
     LSQRB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
     return LSQR_B200_OK;
 }

@@ -47,11 +47,19 @@ static inline size_t plan_smem(int win_cap) { return (size_t)kWWarps * (size_t)(
 
 // Opt in to the dynamic shared memory the flavour needs and measure its co-residency (the soft drift guard of a
 // multi-block launch spins on the other warps of the grid: the grid must fit the GPU).
+// The shared-memory carve-out is set to what the resident CTAs need and no more: what is left of the 228 KB is L1,
+// and the divergent gathers of the non-windowed path live on L1 (every pending miss holds a line: with the
+// carve-out at 100 % the same kernel ran at HALF speed on every workload, profiles/r02/run1).
 template <int FIN, int MINB>
 static int spmv_prepare(size_t smem, int *ctas_per_sm)
 {
     LSQRB_CUDA(cudaFuncSetAttribute(spmv_kernel<FIN, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan_smem(MINB == 4 ? kWinCap4 : kWinCap2)));
-    LSQRB_CUDA(cudaFuncSetAttribute(spmv_kernel<FIN, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    cudaFuncAttributes fa;
+    LSQRB_CUDA(cudaFuncGetAttributes(&fa, spmv_kernel<FIN, MINB>));
+    const size_t per_cta = smem + fa.sharedSizeBytes + 1024;   // + the 1 KB the hardware reserves per CTA
+    int pct = (int)((per_cta * (size_t)MINB * 100 + 228 * 1024 - 1) / (228 * 1024)) + 1;
+    pct = std::max(0, std::min(env_int("LSQR_B200_SMEM_CARVEOUT_PCT", pct), 100));
+    LSQRB_CUDA(cudaFuncSetAttribute(spmv_kernel<FIN, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
     int n = 0;
     LSQRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, spmv_kernel<FIN, MINB>, kWThreads, smem));
     *ctas_per_sm = std::min(n, MINB);
@@ -248,10 +256,18 @@ static int build_plan(Work &wk, const Csr &M, TilePlan *p, int reserve_sms = 0)
         if (p->win_cap > 0) {
             LSQRB_TRY(prepare(&occ));
             const int ctas = std::max(1, wk.sms - reserve_sms) * occ;
-            if (ctas != p->ctas) {          // a different persistent grid: cut again for it
+            if (ctas != p->ctas) {          // a different persistent grid: cut again for it, and size the window for the new pieces
                 p->ctas = ctas;
                 LSQRB_TRY(plan_cut(wk, M, p, 0));
                 LSQRB_TRY(plan_fetch(wk, *p, &t));
+                if (forced_cap <= 0) {
+                    const uint32_t cap = p->minb == 4 ? kWinCap4 : kWinCap2;
+                    double f = 0;
+                    uint32_t need = 0;
+                    window_stats(*p, t, cap, &f, &need);
+                    p->win_cap = (int)((need + 1u) & ~1u);
+                    LSQRB_TRY(prepare(&occ));      // (occupancy cannot drop: the window only shrank or stayed under the flavour's cap)
+                }
             }
         }
     }
@@ -275,8 +291,7 @@ static int build_plan(Work &wk, const Csr &M, TilePlan *p, int reserve_sms = 0)
         for (auto &d : t) if (d.win_len > (uint32_t)p->win_cap) { d.win_len = 0; d.win_lo = 0; }
     }
     LSQRB_TRY(plan_balance(wk, M, p, &t));
-    if (p->order) {
-        // the balanced schedule re-cut the tiles: their windows have to be capped again
+    {   // the balanced schedule may have re-cut the tiles: their windows are capped (again) here, whatever path was taken
         const int64_t np = (int64_t)p->nblocks * ((int64_t)p->ntiles + 1);
         tile_window_cap_kernel<<<(int)((np + 255) / 256), 256, 0, wk.stream>>>(p->tiles, np, (uint32_t)p->win_cap);
         LSQRB_CUDA(cudaGetLastError());
@@ -315,7 +330,7 @@ static int launch_piece(Work &wk, const TilePlan &P, const SpmvArgs &a)
 // persistent launch walks every block; otherwise one launch per block (A/B switch, and the fallback for matrices
 // with more blocks than the drift counters hold).
 template <int FIN>
-static int launch_product(Work &wk, const Csr &M, const TilePlan &P, const ProductIo &io, bool single, bool guard)
+static int launch_product(Work &wk, const Csr &M, const TilePlan &P, const ProductIo &io, bool single, int guard)
 {
     SpmvArgs a;
     a.idx = M.idx; a.val = M.val;
@@ -334,7 +349,7 @@ static int launch_product(Work &wk, const Csr &M, const TilePlan &P, const Produ
         a.ptr = M.ptr; a.tiles = P.tiles; a.nblocks = nb;
         a.first_mode = io.first_mode;
         a.last_is_final = FIN != FIN_NONE;
-        a.guard = (guard && nb > 2) ? 1 : 0;
+        a.guard = nb > 1 ? guard : 0;
         return launch_piece<FIN>(wk, P, a);
     }
     a.nblocks = 1;

@@ -78,7 +78,7 @@ struct SpmvArgs {
     int last_is_final;         // the last block of this launch applies the FINAL epilogue (FIN != FIN_NONE)
     int final_adds_part;       // FINAL adds part[row] (the matrix has more than one block)
     int win_cap;               // doubles of shared-memory gather window per warp (0 = none)
-    int guard;                 // bound the drift between the warps of the launch to < 2 blocks
+    int guard;                 // 0: none; g > 0: block b starts when every warp has finished block b - g (1 = one live slice)
     int check_done;            // plain product launched from the solve loop: nothing to do once the solver has stopped
     DevState *st;
     Ssq *aux;                  // FIN_APROD, multi-GPU: where the local sum u'^2 goes instead of step_after_aprod
@@ -396,11 +396,14 @@ spmv_kernel(SpmvArgs a)
             bc.ptr = a.ptr + (int64_t)b * a.ptr_stride;
             bc.mode = (b == a.nblocks - 1 && a.last_is_final) ? BM_FINAL : (b == 0 ? a.first_mode : BM_ACC);
             bc.adds_part = a.final_adds_part != 0;
-            if (a.guard && b >= 2) {
-                // do not run more than one block ahead of the slowest warp: two gathered slices stay L2-resident
+            if (a.guard && b >= a.guard) {
+                // guard = 1: a block starts when EVERY warp has finished the previous one, so exactly one gathered slice
+                // is live in L2 (measured: a warp that runs ahead touches the whole next slice within microseconds --
+                // random gathers -- and two 48 MB slices do not fit; C5/4 Atprod 7.3 ms vs 5.4 ms).  guard = 2: one
+                // block of slack.
                 if (lane == 0) {
-                    const volatile unsigned int *done = &st->blk_done[b - 2];
-                    while (*done < (unsigned int)nw) __nanosleep(200);
+                    const volatile unsigned int *done = &st->blk_done[b - a.guard];
+                    while (*done < (unsigned int)nw) __nanosleep(100);
                 }
                 __syncwarp();
             }
@@ -412,7 +415,7 @@ spmv_kernel(SpmvArgs a)
                 if (d0.row == d1.row) continue;                 // no row starts in this tile (inside a long row)
                 warp_tile<FIN>(a, bc, epi, su, wbuf, d0, d1, lane, pol_stream, pol_keep);
             }
-            if (a.guard && b + 2 < a.nblocks) {
+            if (a.guard && b + 1 < a.nblocks) {
                 __syncwarp();
                 if (lane == 0) atomicAdd(&st->blk_done[b], 1u);
             }
@@ -422,7 +425,7 @@ spmv_kernel(SpmvArgs a)
     if (kFused) {
         Ssq total;
         if (finish_ssq<kWThreads>(st, 0, st->partial, epi.sq, s_exc, s_red, &total)) {
-            if (a.guard) for (int b = 0; b + 2 < a.nblocks; ++b) st->blk_done[b] = 0;
+            if (a.guard) for (int b = 0; b + 1 < a.nblocks; ++b) st->blk_done[b] = 0;
             if (tracing) st->trace[1][st->tr_n & (kTraceSlots - 1)] = globaltimer_ns();
             if (FIN == FIN_APROD) {
                 if (a.aux) *a.aux = total; else step_after_aprod(*st, ssq_norm(total));
@@ -436,11 +439,11 @@ spmv_kernel(SpmvArgs a)
         __syncthreads();
         if (tid == 0) __threadfence_system();
         if (last_block_ticket(st, 0)) {
-            if (a.guard) for (int b = 0; b + 2 < a.nblocks; ++b) st->blk_done[b] = 0;
+            if (a.guard) for (int b = 0; b + 1 < a.nblocks; ++b) st->blk_done[b] = 0;
             peer_publish_partials(st, *a.peer);
         }
-    } else if (a.guard && a.nblocks > 2) {
-        if (last_block_ticket(st, 0)) for (int b = 0; b + 2 < a.nblocks; ++b) st->blk_done[b] = 0;
+    } else if (a.guard && a.nblocks > 1) {
+        if (last_block_ticket(st, 0)) for (int b = 0; b + 1 < a.nblocks; ++b) st->blk_done[b] = 0;
     }
 }
 

@@ -392,6 +392,83 @@ class LsqrSolver:
         return out
 
 
+class LsqrSolverHost(LsqrSolver):
+    """The abstract ``lsqr_solver`` with the reference's OWN signatures (src/lsqr.f90:16-30,67-82): every vector is a
+    host (numpy) array and the operator is host code.  Extend it and override
+
+        def aprod(self, mode, m, n, x, y) -> None        # mode 1: y += A x ; mode 2: x += A' y   (numpy views, in place)
+
+    The products make a host round trip per call; all vector arithmetic and the scalar recurrence run on the GPU.  This
+    is what an unmodified ``type,extends(lsqr_solver)`` of the reference binds to; a device operator (``LsqrSolver``)
+    is the fast path."""
+
+    def aprod(self, mode: int, m: int, n: int, x: np.ndarray, y: np.ndarray) -> None:   # deferred (:26)
+        raise NotImplementedError("aprod is deferred: extend LsqrSolverHost and provide it")
+
+    def _trampoline(self):
+        def thunk(_user, mode, m, n, xp, yp):
+            try:
+                x = np.ctypeslib.as_array(xp, shape=(max(n, 1),))[:n]
+                y = np.ctypeslib.as_array(yp, shape=(max(m, 1),))[:m]
+                self.aprod(mode, m, n, x, y)
+                return 0
+            except Exception as e:   # surfaced as LSQR_B200_ERR_CALLBACK
+                self._cb_error = e
+                return 1
+        return _lib.APROD_HOST_FN(thunk)
+
+    # LSQR, src/lsqr.f90:432-882, reference argument list: u (holds b, overwritten), v, w, x, se are host arrays
+    def lsqr(self, m, n, damp, wantse, u, v, w, x, se, atol, btol, conlim, itnlim, nout=None,
+             trace: bool = False, device: int = -1, stream: int = 0) -> SolveResult:
+        L = _lib.load()
+        tr = [] if trace else None
+        o, cb = self._options(nout, tr, device, stream)
+        fn = self._trampoline()
+        istop, itn = C.c_int32(), C.c_int32()
+        sc = [C.c_double() for _ in range(5)]
+        self._cb_error = None
+        rc = L.lsqr_b200_lsqr_host(fn, None, int(m), int(n), float(damp), int(bool(wantse)),
+                                   _ptr(u), _ptr(v), _ptr(w), _ptr(x), _ptr(se) if wantse else None,
+                                   float(atol), float(btol), float(conlim), int(itnlim), C.byref(o),
+                                   C.byref(istop), C.byref(itn), *[C.byref(s) for s in sc])
+        if rc == 15 and self._cb_error is not None:
+            raise self._cb_error
+        _lib.check(rc)
+        return SolveResult(x, istop.value, itn.value, *[s.value for s in sc], se=se if wantse else None,
+                           log=cb.lines, trace=tr or [])
+
+    def acheck(self, m, n, v, w, x, y, eps=float(np.finfo(np.float64).eps), nout=None, device=-1, stream=0):
+        o, cb = self._options(nout, None, device, stream)
+        fn = self._trampoline()
+        inform, rel = C.c_int32(), C.c_double()
+        self._cb_error = None
+        rc = _lib.load().lsqr_b200_acheck_host(fn, None, int(m), int(n), float(eps), _ptr(v), _ptr(w), _ptr(x), _ptr(y),
+                                               C.byref(o), C.byref(inform), C.byref(rel))
+        if rc == 15 and self._cb_error is not None:
+            raise self._cb_error
+        _lib.check(rc)
+        return inform.value, rel.value
+
+    def xcheck(self, m, n, anorm, damp, b, u, v, w, x, eps=float(np.finfo(np.float64).eps), nout=None,
+               device=-1, stream=0) -> dict:
+        o, cb = self._options(nout, None, device, stream)
+        fn = self._trampoline()
+        inform = C.c_int32()
+        t = [C.c_double() for _ in range(3)]
+        norms = (C.c_double * 6)()
+        self._cb_error = None
+        rc = _lib.load().lsqr_b200_xcheck_host(fn, None, int(m), int(n), float(anorm), float(damp), float(eps),
+                                               _ptr(b), _ptr(u), _ptr(v), _ptr(w), _ptr(x), C.byref(o),
+                                               C.byref(inform), *[C.byref(s) for s in t], norms)
+        if rc == 15 and self._cb_error is not None:
+            raise self._cb_error
+        _lib.check(rc)
+        keys = ("bnorm", "xnorm", "rho1", "sigma1", "rho2", "sigma2")
+        out = dict(inform=inform.value, test1=t[0].value, test2=t[1].value, test3=t[2].value, log=cb.lines)
+        out.update({k: norms[i] for i, k in enumerate(keys)})
+        return out
+
+
 class EzAsOperator(LsqrSolver):
     """Drives an initialized ``LsqrSolverEz`` through the low-level path, the way
     ``class(lsqr_solver_ez)`` *is a* ``lsqr_solver`` in the reference."""

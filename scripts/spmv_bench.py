@@ -28,6 +28,7 @@ MODES = {
     "default": {},
     "perblock": {"LSQR_B200_SINGLE_LAUNCH": "0"},
     "noguard": {"LSQR_B200_DRIFT_GUARD": "0"},
+    "guard2": {"LSQR_B200_DRIFT_GUARD": "2"},
     "nowindow": {"LSQR_B200_WINDOW": "0"},
     "nooverlap": {"LSQR_B200_OVERLAP_UPDATE": "0"},
 }

@@ -1,5 +1,6 @@
-"""Multi-GPU parity worker (launched by torchrun, one rank per GPU): the row-partitioned engine (local Aprod,
-one NCCL all-reduce of [A_p'u_p | sum u_p^2] per iteration) against the serial CPU oracle on the same problem.
+"""Multi-GPU parity worker (launched by torchrun, one rank per GPU): the row-partitioned engine (local Aprod, the
+partial A_p'u_p exchanged over NVLink peer memory -- or by one NCCL all-reduce -- every iteration) against the serial
+CPU oracle on the same problem.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tests/mgpu_worker.py
 """
@@ -25,20 +26,22 @@ def main():
     from lsqr_b200 import dist, synth, synth_device
     from oracle import oracle as O      # the checker
 
-        # (workload, scale, tolerance, se wanted, column chunks of the pipelined all-reduce, forced blocked layouts)
-    for name, scale, tol, want_se, chunks, blocked in (("C2", 20, 1e-10, False, 1, False), ("C3", 100, 1e-8, True, 3, False),
-                                                       ("C4", 200, 1e-10, False, 4, False), ("C5", 200, 1e-10, False, 1, True),
-                                                       ("C5", 200, 1e-10, False, 2, True)):
-        os.environ["LSQR_B200_COMM_CHUNKS"] = str(chunks)
-        # the layouts of the full-size multi-GPU runs: column-blocked A (fused last block) and row-blocked A'
-        for key, val in (("LSQR_B200_VBLOCK_COLS", "20000"), ("LSQR_B200_UBLOCK_ROWS", "90000")):
+    # (workload, scale, tolerance, se wanted, exchange over peer memory (else one NCCL all-reduce), forced blocked layouts)
+    cases = (("C2", 20, 1e-10, False, True, False), ("C3", 100, 1e-8, True, True, False), ("C4", 200, 1e-10, False, True, False),
+             ("C5", 200, 1e-10, False, True, True), ("C5", 200, 1e-10, True, False, True), ("C3", 100, 1e-8, True, False, False))
+    if os.environ.get("MGPU_CASES"):
+        cases = tuple(cases[int(i)] for i in os.environ["MGPU_CASES"].split(","))
+    for name, scale, tol, want_se, peer, blocked in cases:
+        os.environ["LSQR_B200_PEER_EXCHANGE"] = "1" if peer else "0"
+        # the layouts of the full-size multi-GPU runs: column-blocked A and row-blocked A' (3 blocks each per rank)
+        cfg = synth.scaled(name, scale)
+        m, n = cfg["m"], cfg["n"]
+        row0, row1 = dist.row_block(m, world, rank)
+        for key, val in (("LSQR_B200_VBLOCK_COLS", str(n // 3 + 1)), ("LSQR_B200_UBLOCK_ROWS", str((row1 - row0) // 3 + 1))):
             if blocked:
                 os.environ[key] = val
             else:
                 os.environ.pop(key, None)
-        cfg = synth.scaled(name, scale)
-        m, n = cfg["m"], cfg["n"]
-        row0, row1 = dist.row_block(m, world, rank)
         irow, icol, a = synth_device.coo_block(cfg["kind"], cfg["seed"], m, n, cfg["k"], row0, row1 - row0, dev)
         uid = dist.exchange_unique_id(world, rank)
         s = lsqr_b200.LsqrSolverEz().initialize(row1 - row0, n, a, irow, icol, atol=tol, btol=tol, conlim=1e8, itnlim=4000,
@@ -47,7 +50,12 @@ def main():
         # the whole problem on the host for the oracle (every rank builds it: small)
         I, J, A = synth.coo_block(cfg["kind"], cfg["seed"], m, n, cfg["k"])
         b = synth.rhs_block(I, J, A, m, synth.x_true(cfg["seed"], n), cfg["seed"])
+        plan = s.plan(False)
+        if peer:
+            assert plan["peer_exchange"] == 1, "the peer-memory exchange could not be set up (IPC mapping failed?)"
         r = s.solve(np.ascontiguousarray(b[row0:row1]), cfg["damp"], want_se=want_se)
+        r2 = s.solve(np.ascontiguousarray(b[row0:row1]), cfg["damp"], want_se=want_se)      # reusable and reproducible
+        assert r2.itn == r.itn and np.array_equal(np.asarray(r2.x), np.asarray(r.x))
         # every rank must hold the identical solution and scalars
         xs = [torch.zeros(n, dtype=torch.float64, device=dev) for _ in range(world)]
         td.all_gather(xs, torch.from_numpy(np.asarray(r.x)).to(dev))
@@ -62,7 +70,8 @@ def main():
             if want_se:
                 rse = np.linalg.norm(np.asarray(r.se) - ref.se) / np.linalg.norm(ref.se)
                 assert rse <= 1e-8, (name, rse)
-            print(f"MGPU_OK {name}/{scale} chunks={chunks} blocked={blocked} world={world} istop={r.istop} itn={r.itn} (oracle {ref.itn}) rel_x={rel:.2e}", flush=True)
+            print(f"MGPU_OK {name}/{scale} peer={int(bool(plan['peer_exchange']))} blocked={blocked} blocks={s.blocks(False)[0]}/{s.blocks(True)[0]} "
+                  f"world={world} istop={r.istop} itn={r.itn} (oracle {ref.itn}) rel_x={rel:.2e}", flush=True)
         del s
         td.barrier()
     td.destroy_process_group()
