@@ -201,6 +201,9 @@ typedef struct lsqr_b200_plan_info {
     int64_t span_median, span_max;  /* gather span of the pieces (entries of the dense vector)                  */
     int32_t single_launch;      /* one persistent launch walks every block of a product                         */
     int32_t peer_exchange;      /* multi-GPU: exchange over NVLink peer memory instead of one NCCL all-reduce   */
+    int32_t striped_gathers;    /* lane-consecutive gathers (rows with clustered / sorted indices)              */
+    int32_t reserved;
+    double  lines_per_gather;   /* 128-byte lines spanned by 32 consecutive stored entries (32 = no locality)   */
 } lsqr_b200_plan_info;
 LSQR_B200_API int lsqr_b200_ez_plan(const lsqr_b200_ez *me, int32_t which, lsqr_b200_plan_info *out);
 

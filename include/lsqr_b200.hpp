@@ -136,6 +136,56 @@ private:
 };
 
 // ------------------------------------------------------------------------------------------------
+// The same abstract class with the reference's OWN signatures: every vector is a HOST array and aprod is host code
+// (aprod_func, src/lsqr.f90:67-82).  Each product makes a host round trip; all vector arithmetic and the scalar
+// recurrence run on the GPU.  What an unmodified type,extends(lsqr_solver) of the reference maps to.
+// ------------------------------------------------------------------------------------------------
+class lsqr_solver_host {
+public:
+    virtual ~lsqr_solver_host() = default;
+    virtual void aprod(int mode, int m, int n, wp *x, wp *y) = 0;          // host arrays x(n), y(m), both inout
+
+    void lsqr(int m, int n, wp damp, bool wantse, wp *u, wp *v, wp *w, wp *x, wp *se,
+              wp atol, wp btol, wp conlim, int itnlim, std::FILE *nout,
+              int &istop, int &itn, wp &anorm, wp &acond, wp &rnorm, wp &arnorm, wp &xnorm)
+    {
+        lsqr_b200_options o = detail::options_with_nout(nout, nullptr);
+        int32_t is = 0, it = 0;
+        check(lsqr_b200_lsqr_host(&lsqr_solver_host::trampoline, this, m, n, damp, wantse ? 1 : 0, u, v, w, x, se,
+                                  atol, btol, conlim, itnlim, &o, &is, &it, &anorm, &acond, &rnorm, &arnorm, &xnorm));
+        istop = is;
+        itn = it;
+    }
+    void acheck(int m, int n, std::FILE *nout, wp eps, wp *v, wp *w, wp *x, wp *y, int &inform)
+    {
+        lsqr_b200_options o = detail::options_with_nout(nout, nullptr);
+        int32_t inf = 0;
+        check(lsqr_b200_acheck_host(&lsqr_solver_host::trampoline, this, m, n, eps, v, w, x, y, &o, &inf, nullptr));
+        inform = inf;
+    }
+    void xcheck(int m, int n, std::FILE *nout, wp anorm, wp damp, wp eps, const wp *b, wp *u, wp *v, wp *w, const wp *x,
+                int &inform, wp &test1, wp &test2, wp &test3)
+    {
+        lsqr_b200_options o = detail::options_with_nout(nout, nullptr);
+        int32_t inf = 0;
+        check(lsqr_b200_xcheck_host(&lsqr_solver_host::trampoline, this, m, n, anorm, damp, eps, b, u, v, w, x, &o,
+                                    &inf, &test1, &test2, &test3, nullptr));
+        inform = inf;
+    }
+
+private:
+    static int trampoline(void *user, int32_t mode, int32_t m, int32_t n, double *x, double *y)
+    {
+        try {
+            static_cast<lsqr_solver_host *>(user)->aprod(mode, m, n, x, y);
+            return 0;
+        } catch (...) {
+            return 1;
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
 // type,extends(lsqr_solver) :: lsqr_solver_ez  (src/lsqr.f90:32-65)
 // ------------------------------------------------------------------------------------------------
 class lsqr_solver_ez : public lsqr_solver {
@@ -204,7 +254,7 @@ private:
 
 }  // namespace lsqr_module
 
-// lsqpblas_module [sic] (src/lsqrblas.f90:8,16): dcopy, ddot, dnrm2, dscal on DEVICE arrays, stride 1
+// lsqpblas_module [sic] (src/lsqrblas.f90:8,16): dcopy, ddot, dnrm2, dscal on DEVICE or HOST arrays, stride 1
 namespace lsqpblas_module {
 inline void dcopy(int n, const double *dx, double *dy, void *stream = nullptr) { lsqr_module::check(lsqr_b200_dcopy(n, dx, dy, stream)); }
 inline double ddot(int n, const double *dx, const double *dy, void *stream = nullptr)

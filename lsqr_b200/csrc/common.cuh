@@ -84,6 +84,7 @@ struct DevState {
     // multi-GPU exchange (peer-memory path): iteration epoch the flags are compared with, error latch of a timed-out wait
     unsigned int epoch;
     int comm_error;
+    int guard_error;         // a guarded multi-block launch waited for seconds on the other warps of its grid
     Ssq usq_local, vsq_local, wsq_local;   // this rank's partial sums of squares of u', v' (slice), w' (slice)
 
     // scalars of the iteration whose x/w update is still outstanding; published to the host ring

@@ -319,9 +319,9 @@ static int ez_initialize_impl(lsqr_b200_ez *me, int64_t nnz, const double *a, co
     if (env_int("LSQR_B200_VERBOSE", 0)) {
         auto say = [&](const char *name, const Csr &M, const TilePlan &P) {
             fprintf(stderr, "[lsqr_b200] %s: blocks=%lld (block size %lld) tiles=%d (%llu work units) grid=%d CTAs x %d/SM  window=%d doubles "
-                            "(%.1f%% of the entries staged; piece span median %u, max %u)%s imbalance %.3f\n",
+                            "(%.1f%% of the entries staged; piece span median %u, max %u) lines/gather %.1f%s%s imbalance %.3f\n",
                     name, (long long)M.nblocks, (long long)M.block_rows, P.ntiles, (unsigned long long)P.tile, P.ctas, P.minb, P.win_cap,
-                    100.0 * P.windowed, P.span_p50, P.span_max, P.order ? " LPT" : "", P.imbalance);
+                    100.0 * P.windowed, P.span_p50, P.span_max, P.lines_per_gather, P.striped ? " STRIPED" : "", P.order ? " LPT" : "", P.imbalance);
         };
         fprintf(stderr, "[lsqr_b200] m=%d n=%d nnz=%lld single_launch=%d guard=%d\n", me->m, me->n, (long long)me->nnz, (int)me->single_launch, (int)me->guard);
         say("A ", me->A, me->planA);
@@ -469,6 +469,8 @@ int lsqr_b200_ez_plan(const lsqr_b200_ez *me, int32_t which, lsqr_b200_plan_info
     out->imbalance = P.imbalance;
     out->single_launch = me->single_launch && M.nblocks <= kMaxSpmvBlocks;
     out->peer_exchange = me->peer;
+    out->striped_gathers = P.striped;
+    out->lines_per_gather = P.lines_per_gather;
     return LSQR_B200_OK;
 }
 
@@ -624,8 +626,9 @@ static int enqueue_iteration(lsqr_b200_ez *me, bool wantse)
           peer_step_kernel<false><<<1, 32, 0, wk.stream>>>(me->pv, wk.st);
           wk.launches += 2; LSQRB_CUDA(cudaGetLastError()); }
         { ProfScope p(me, CLS_UPDATE);
-          LSQRB_TRY(launch_update<true>(wk, me->slice_len, me->xs + (size_t)me->opt.rank * (size_t)me->pv.cols, me->ws,
-                                        me->v + me->slice0, me->ses, wantse, 1)); }
+          const size_t off = (size_t)me->opt.rank * (size_t)me->pv.cols;      // this rank's slot of the gather buffers
+          LSQRB_TRY(launch_update<true>(wk, me->slice_len, me->xs + off, me->ws, me->v + me->slice0,
+                                        wantse ? me->ses + off : nullptr, wantse, 1)); }
         return LSQR_B200_OK;
     }
     if (me->opt.world_size > 1) {
@@ -784,6 +787,8 @@ static int ez_solve_fused(lsqr_b200_ez *me, const double *b, double damp, double
             LSQRB_TRY(join_side(me));
             me->times.iteration_launches = (wk.launches - before) / B;
         }
+        // peer path: a rank that never arrives makes the waits time out; the latch travels with the batch
+        if (peer) LSQRB_CUDA(cudaMemcpyAsync(&wk.err_h[nb & 3], &wk.st->comm_error, sizeof(int), cudaMemcpyDeviceToHost, wk.stream));
         LSQRB_CUDA(cudaEventRecord(wk.ev[nb & 3], wk.stream));
         enq += B;
         nb += 1;
@@ -792,6 +797,7 @@ static int ez_solve_fused(lsqr_b200_ez *me, const double *b, double damp, double
     auto check = [&](int upto) {
         stop = drain_ring(wk, lc, seen, upto);
         if (seen >= 0 && wk.ring_h[0].arnorm == 0.0) stop = true;   // alpha*beta = 0: no iterations (:646-648)
+        if (peer && done_batches > 0 && wk.err_h[(done_batches - 1) & 3]) stop = true;
     };
     // Keep two batches in flight.  The device stops by itself (done flag; istop = 5 at itnlim), so an
     // over-enqueued batch is a run of no-op kernels.  Launch decisions depend only on the records of
@@ -834,6 +840,7 @@ static int ez_solve_fused(lsqr_b200_ez *me, const double *b, double damp, double
     // any records the loop did not print yet (e.g. the stopping iteration)
     drain_ring(wk, lc, seen, wk.h.itn);
     if (wk.h.comm_error) { set_last_error("multi-GPU peer exchange timed out (a rank did not arrive)"); return LSQR_B200_ERR_NCCL; }
+    if (wk.h.guard_error) { set_last_error("multi-block SpMV launch: the drift guard timed out (grid not co-resident?)"); return LSQR_B200_ERR_CUDA; }
 
     int is = wk.h.istop;
     if (damp > 0.0 && is == 2) is = 3;   // :871

@@ -111,6 +111,7 @@ struct Work {
     DevState h;                                   // host mirror (header part only is copied)
     lsqr_b200_iter_record *ring_h = nullptr;      // pinned, mapped
     lsqr_b200_iter_record *ring_d = nullptr;      // device alias of ring_h
+    int *err_h = nullptr;                         // pinned: comm_error of the last 4 batches (multi-GPU peer path)
     int max_grid = kNumSMs * 8;
     int sms = kNumSMs;
     int64_t launches = 0;
@@ -144,6 +145,9 @@ struct Work {
         LSQRB_CUDA(cudaMemsetAsync(st, 0, sizeof(DevState), stream));
         LSQRB_CUDA(cudaHostAlloc(&ring_h, sizeof(lsqr_b200_iter_record) * kRingSize, cudaHostAllocMapped));
         LSQRB_CUDA(cudaHostGetDevicePointer(&ring_d, ring_h, 0));
+        LSQRB_CUDA(cudaHostAlloc(&err_h, sizeof(int) * 4, cudaHostAllocDefault));
+        memset(err_h, 0, sizeof(int) * 4);
+        h.epoch = 0;
         for (auto &e : ev) LSQRB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDefault));
         LSQRB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
         sms = std::max(1, sms);
@@ -155,6 +159,8 @@ struct Work {
     {
         if (st) cudaFree(st);
         if (ring_h) cudaFreeHost(ring_h);
+        if (err_h) cudaFreeHost(err_h);
+        err_h = nullptr;
         for (auto &e : ev) if (e) cudaEventDestroy(e);
         if (own_stream && stream) cudaStreamDestroy(stream);
         st = nullptr; ring_h = nullptr; stream = nullptr;

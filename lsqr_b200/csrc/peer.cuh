@@ -53,7 +53,7 @@ __device__ __forceinline__ void peer_wait(DevState *st, const unsigned int *flag
     const unsigned long long t0 = globaltimer_ns();
     for (int p = 0; p < world; ++p) {
         while ((int)(ld_acquire_sys(flags + p) - want) < 0) {
-            if (st->comm_error) return;
+            if (*(volatile int *)&st->comm_error) return;
             if (globaltimer_ns() - t0 > 20000000000ull) { st->comm_error = 1; return; }
             __nanosleep(100);
         }

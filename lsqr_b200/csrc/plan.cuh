@@ -30,6 +30,9 @@ struct TilePlan {
     size_t smem = 0;             // dynamic shared memory per CTA
     double imbalance = 1.0;      // most loaded warp / mean load under the schedule in use (diagnostic)
     double windowed = 0.0;       // fraction of the stored entries whose gathers are served from shared memory
+    int striped = 0;             // lane-consecutive gathers (matrices whose rows hold clustered / sorted indices)
+    double lines_per_gather = 32.0;   // 128-byte lines that 32 consecutive stored entries span (32 = no locality)
+    unsigned long long *stat = nullptr;   // device scratch of the locality measurement
     uint32_t span_p50 = 0, span_max = 0;   // gather span (entries of the dense vector) of the pieces: median, maximum
 };
 
@@ -37,7 +40,8 @@ static inline void plan_free(TilePlan &p)
 {
     if (p.tiles) cudaFree(p.tiles);
     if (p.order) cudaFree(p.order);
-    p.tiles = nullptr; p.order = nullptr;
+    if (p.stat) cudaFree(p.stat);
+    p.tiles = nullptr; p.order = nullptr; p.stat = nullptr;
 }
 
 constexpr int kWinCap4 = 640;    // 8 warps x (128 + 640) doubles = 48 KB per CTA, 4 CTAs per SM
@@ -50,31 +54,36 @@ static inline size_t plan_smem(int win_cap) { return (size_t)kWWarps * (size_t)(
 // The shared-memory carve-out is set to what the resident CTAs need and no more: what is left of the 228 KB is L1,
 // and the divergent gathers of the non-windowed path live on L1 (every pending miss holds a line: with the
 // carve-out at 100 % the same kernel ran at HALF speed on every workload, profiles/r02/run1).
-template <int FIN, int MINB>
+template <int FIN, int MINB, bool STRIPED>
 static int spmv_prepare(size_t smem, int *ctas_per_sm)
 {
-    LSQRB_CUDA(cudaFuncSetAttribute(spmv_kernel<FIN, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan_smem(MINB == 4 ? kWinCap4 : kWinCap2)));
+    LSQRB_CUDA(cudaFuncSetAttribute(spmv_kernel<FIN, MINB, STRIPED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan_smem(MINB == 4 ? kWinCap4 : kWinCap2)));
     cudaFuncAttributes fa;
-    LSQRB_CUDA(cudaFuncGetAttributes(&fa, spmv_kernel<FIN, MINB>));
+    LSQRB_CUDA(cudaFuncGetAttributes(&fa, spmv_kernel<FIN, MINB, STRIPED>));
     const size_t per_cta = smem + fa.sharedSizeBytes + 1024;   // + the 1 KB the hardware reserves per CTA
-    int pct = (int)((per_cta * (size_t)MINB * 100 + 228 * 1024 - 1) / (228 * 1024)) + 1;
+    // the carve-out comes in steps and the preference is rounded to the NEAREST step, up or down: name the smallest
+    // step that holds MINB CTAs exactly (a rounded-down carve-out would leave the persistent grid partly non-resident)
+    static const int steps_kb[] = {0, 8, 16, 32, 64, 100, 132, 164, 196, 228};
+    int pct = 100;
+    for (int kb : steps_kb)
+        if ((size_t)kb * 1024 >= per_cta * (size_t)MINB) { pct = (kb * 100 + 227) / 228; break; }
     pct = std::max(0, std::min(env_int("LSQR_B200_SMEM_CARVEOUT_PCT", pct), 100));
-    LSQRB_CUDA(cudaFuncSetAttribute(spmv_kernel<FIN, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+    LSQRB_CUDA(cudaFuncSetAttribute(spmv_kernel<FIN, MINB, STRIPED>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
     int n = 0;
-    LSQRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, spmv_kernel<FIN, MINB>, kWThreads, smem));
+    LSQRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, spmv_kernel<FIN, MINB, STRIPED>, kWThreads, smem));
     *ctas_per_sm = std::min(n, MINB);
     return LSQR_B200_OK;
 }
 
-template <int MINB>
+template <int MINB, bool STRIPED>
 static int spmv_prepare_all(size_t smem, int *ctas_per_sm)
 {
     int occ = MINB, o = 0;
-    LSQRB_TRY((spmv_prepare<FIN_NONE, MINB>(smem, &o)));        occ = std::min(occ, o);
-    LSQRB_TRY((spmv_prepare<FIN_APROD, MINB>(smem, &o)));       occ = std::min(occ, o);
-    LSQRB_TRY((spmv_prepare<FIN_ATPROD, MINB>(smem, &o)));      occ = std::min(occ, o);
-    LSQRB_TRY((spmv_prepare<FIN_INIT_ATPROD, MINB>(smem, &o))); occ = std::min(occ, o);
-    LSQRB_TRY((spmv_prepare<FIN_PUSH, MINB>(smem, &o)));        occ = std::min(occ, o);
+    LSQRB_TRY((spmv_prepare<FIN_NONE, MINB, STRIPED>(smem, &o)));        occ = std::min(occ, o);
+    LSQRB_TRY((spmv_prepare<FIN_APROD, MINB, STRIPED>(smem, &o)));       occ = std::min(occ, o);
+    LSQRB_TRY((spmv_prepare<FIN_ATPROD, MINB, STRIPED>(smem, &o)));      occ = std::min(occ, o);
+    LSQRB_TRY((spmv_prepare<FIN_INIT_ATPROD, MINB, STRIPED>(smem, &o))); occ = std::min(occ, o);
+    LSQRB_TRY((spmv_prepare<FIN_PUSH, MINB, STRIPED>(smem, &o)));        occ = std::min(occ, o);
     *ctas_per_sm = occ;
     return LSQR_B200_OK;
 }
@@ -110,8 +119,14 @@ static int plan_cut(Work &wk, const Csr &M, TilePlan *p, uint64_t forced_tile)
     build_tiles_kernel<<<(int)((nt + 1 + 255) / 256), 256, 0, wk.stream>>>(M.ptr, nrows, (int)nb, (int)nt, tile, p->row_w, p->tiles);
     LSQRB_CUDA(cudaGetLastError());
     const int64_t np = nb * (nt + 1);
-    tile_span_kernel<<<(int)std::min<int64_t>((np * 32 + 255) / 256, (int64_t)wk.sms * 16), 256, 0, wk.stream>>>(M.idx, p->tiles, np, (int)nt);
+    if (!p->stat) LSQRB_CUDA(cudaMalloc(&p->stat, 2 * sizeof(unsigned long long)));
+    LSQRB_CUDA(cudaMemsetAsync(p->stat, 0, 2 * sizeof(unsigned long long), wk.stream));
+    tile_span_kernel<<<(int)std::min<int64_t>((np * 32 + 255) / 256, (int64_t)wk.sms * 16), 256, 0, wk.stream>>>(M.idx, p->tiles, np, (int)nt, p->stat);
     LSQRB_CUDA(cudaGetLastError());
+    unsigned long long h[2] = {0, 0};
+    LSQRB_CUDA(cudaMemcpyAsync(h, p->stat, sizeof h, cudaMemcpyDeviceToHost, wk.stream));
+    LSQRB_CUDA(cudaStreamSynchronize(wk.stream));
+    p->lines_per_gather = h[1] ? (double)h[0] / (double)h[1] : 32.0;
     return LSQR_B200_OK;
 }
 
@@ -226,8 +241,8 @@ static int build_plan(Work &wk, const Csr &M, TilePlan *p, int reserve_sms = 0)
     auto prepare = [&](int *occ) -> int {
         p->smem = plan_smem(p->win_cap);
         *occ = 0;
-        if (p->minb == 4) LSQRB_TRY(spmv_prepare_all<4>(p->smem, occ));
-        else              LSQRB_TRY(spmv_prepare_all<2>(p->smem, occ));
+        if (p->minb == 4) { if (p->striped) LSQRB_TRY((spmv_prepare_all<4, true>(p->smem, occ))); else LSQRB_TRY((spmv_prepare_all<4, false>(p->smem, occ))); }
+        else              { if (p->striped) LSQRB_TRY((spmv_prepare_all<2, true>(p->smem, occ))); else LSQRB_TRY((spmv_prepare_all<2, false>(p->smem, occ))); }
         if (*occ < 1) { set_last_error("spmv kernel does not fit an SM"); return LSQR_B200_ERR_CUDA; }
         return LSQR_B200_OK;
     };
@@ -236,38 +251,47 @@ static int build_plan(Work &wk, const Csr &M, TilePlan *p, int reserve_sms = 0)
     p->ctas = std::max(1, wk.sms - reserve_sms) * occ;
     LSQRB_TRY(plan_cut(wk, M, p, 0));
     LSQRB_TRY(plan_fetch(wk, *p, &t));
-    if (want_window && M.nnz > 0) {
+    p->striped = 0;
+    const int forced_cap = env_int("LSQR_B200_WINDOW_CAP", 0);
+    if (M.nnz > 0) {
         // gather spans -> window: the narrow window keeps 32 warps per SM, the wide one halves them
         double f4 = 0, f2 = 0;
         uint32_t n4 = 0, n2 = 0;
         window_stats(*p, t, kWinCap4, &f4, &n4);
         window_stats(*p, t, kWinCap2, &f2, &n2);
-        const int forced_cap = env_int("LSQR_B200_WINDOW_CAP", 0);
-        if (forced_cap > 0) {
+        if (!want_window) {
+        } else if (forced_cap > 0) {
             p->win_cap = std::min((forced_cap + 1) & ~1, kWinCap2);
             p->minb = p->win_cap <= kWinCap4 ? 4 : 2;
-        } else if (f4 >= min_frac && f4 >= f2 - 0.25) {
+        } else if (f4 >= min_frac) {
             p->win_cap = (int)((n4 + 1u) & ~1u);
             p->minb = 4;
-        } else if (f2 >= min_frac) {
+        } else if (f2 >= min_frac && env_int("LSQR_B200_WINDOW_WIDE", 0)) {
+            // wide windows halve the resident warps: measured SLOWER than global gathers on the banded A' (C3 full size:
+            // 1.74 ms vs 1.38 ms, profiles/r02/run2), so they are opt-in
             p->win_cap = (int)((n2 + 1u) & ~1u);
             p->minb = 2;
         }
-        if (p->win_cap > 0) {
-            LSQRB_TRY(prepare(&occ));
-            const int ctas = std::max(1, wk.sms - reserve_sms) * occ;
-            if (ctas != p->ctas) {          // a different persistent grid: cut again for it, and size the window for the new pieces
-                p->ctas = ctas;
-                LSQRB_TRY(plan_cut(wk, M, p, 0));
-                LSQRB_TRY(plan_fetch(wk, *p, &t));
-                if (forced_cap <= 0) {
-                    const uint32_t cap = p->minb == 4 ? kWinCap4 : kWinCap2;
-                    double f = 0;
-                    uint32_t need = 0;
-                    window_stats(*p, t, cap, &f, &need);
-                    p->win_cap = (int)((need + 1u) & ~1u);
-                    LSQRB_TRY(prepare(&occ));      // (occupancy cannot drop: the window only shrank or stayed under the flavour's cap)
-                }
+        // lane-consecutive gathers where 32 consecutive stored entries share lines and no window serves most of them
+        const int forced = env_int("LSQR_B200_STRIPED", -1);
+        const double max_lines = 1e-1 * env_int("LSQR_B200_STRIPED_MAX_LINES_X10", 200);
+        const bool mostly_windowed = p->win_cap > 0 && forced_cap <= 0;
+        p->striped = forced >= 0 ? (forced != 0) : (p->lines_per_gather <= max_lines && !mostly_windowed);
+    }
+    if (p->win_cap > 0 || p->striped) {
+        LSQRB_TRY(prepare(&occ));
+        const int ctas = std::max(1, wk.sms - reserve_sms) * occ;
+        if (ctas != p->ctas) {          // a different persistent grid: cut again for it, and size the window for the new pieces
+            p->ctas = ctas;
+            LSQRB_TRY(plan_cut(wk, M, p, 0));
+            LSQRB_TRY(plan_fetch(wk, *p, &t));
+            if (forced_cap <= 0 && p->win_cap > 0) {
+                const uint32_t cap = p->minb == 4 ? kWinCap4 : kWinCap2;
+                double f = 0;
+                uint32_t need = 0;
+                window_stats(*p, t, cap, &f, &need);
+                p->win_cap = (int)((need + 1u) & ~1u);
+                LSQRB_TRY(prepare(&occ));      // (occupancy cannot drop: the window only shrank or stayed under the flavour's cap)
             }
         }
     }
@@ -319,8 +343,19 @@ template <int FIN>
 static int launch_piece(Work &wk, const TilePlan &P, const SpmvArgs &a)
 {
     const int grid = P.order ? P.ctas : std::max(1, std::min((P.ntiles + kWWarps - 1) / kWWarps, P.ctas));
-    if (P.minb == 4) spmv_kernel<FIN, 4><<<grid, kWThreads, P.smem, wk.stream>>>(a);
-    else             spmv_kernel<FIN, 2><<<grid, kWThreads, P.smem, wk.stream>>>(a);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kWThreads);
+    cfg.dynamicSmemBytes = P.smem;
+    cfg.stream = wk.stream;
+    cudaLaunchAttribute attr[1];
+    memset(attr, 0, sizeof attr);
+    // a guarded multi-block launch spins on the other warps of its grid: launched COOPERATIVELY, so that the driver
+    // either makes the whole grid co-resident or refuses the launch -- never a partly resident grid that waits for ever
+    if (a.guard) { attr[0].id = cudaLaunchAttributeCooperative; attr[0].val.cooperative = 1; cfg.attrs = attr; cfg.numAttrs = 1; }
+    if (P.minb == 4) { if (P.striped) LSQRB_CUDA(cudaLaunchKernelEx(&cfg, spmv_kernel<FIN, 4, true>, a)); else LSQRB_CUDA(cudaLaunchKernelEx(&cfg, spmv_kernel<FIN, 4, false>, a)); }
+    else             { if (P.striped) LSQRB_CUDA(cudaLaunchKernelEx(&cfg, spmv_kernel<FIN, 2, true>, a)); else LSQRB_CUDA(cudaLaunchKernelEx(&cfg, spmv_kernel<FIN, 2, false>, a)); }
     wk.launches++;
     LSQRB_CUDA(cudaGetLastError());
     return LSQR_B200_OK;

@@ -166,27 +166,51 @@ struct ChunkRegs {
     int32_t c[4];
 };
 
-// Loads one lane's share of the chunk that starts at entry `cb` of the piece [e0, e1): entries [cb+4 lane, +4).
+__device__ __forceinline__ int32_t ldg_stream_s32_1(const int32_t *p, uint64_t pol)
+{
+    int32_t r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(pol));
+    return r;
+}
+
+// Loads one lane's share of the chunk that starts at entry `cb` of the piece [e0, e1).  Values: entries
+// [cb+4 lane, +4) (blocked: what the segmented scan wants).  Indices: the same entries, or -- STRIPED -- entries
+// cb + 32 k + lane, k = 0..3, so that one gather instruction covers 32 CONSECUTIVE stored entries: in a matrix whose
+// rows hold clustered / sorted indices (banded A', FEM, tomography) those fall into a handful of 128-byte lines
+// instead of 32, and the L1TEX tag stage -- one line per clock -- stops being the limiter.
 // Entries outside the piece (they belong to the neighbouring pieces or to the allocation slack) get the value 0 and
 // the index `safe` (inside the piece's gather window), so they add nothing to any row and gather harmlessly.
+template <bool STRIPED>
 __device__ __forceinline__ void load_chunk(const SpmvArgs &a, uint32_t cb, int lane, uint32_t e0, uint32_t e1,
                                            int32_t safe, uint64_t pol_stream, ChunkRegs &r)
 {
     const uint32_t q = cb + 4u * (uint32_t)lane;
     if (cb >= e0 && cb + kChunk <= e1) {   // steady state: the whole chunk lies inside the piece
         ldg_stream_f64x4(a.val + q, r.v);
-        ldg_stream_s32x4(a.idx + q, r.c, pol_stream);
+        if (STRIPED) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) r.c[k] = ldg_stream_s32_1(a.idx + cb + 32u * k + (uint32_t)lane, pol_stream);
+        } else {
+            ldg_stream_s32x4(a.idx + q, r.c, pol_stream);
+        }
         return;
     }
     if (q < e1) {
         ldg_stream_f64x4(a.val + q, r.v);
-        ldg_stream_s32x4(a.idx + q, r.c, pol_stream);
+        if (!STRIPED) ldg_stream_s32x4(a.idx + q, r.c, pol_stream);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-            if (q + k < e0 || q + k >= e1) { r.v[k] = 0.0; r.c[k] = safe; }
+            if (q + k < e0 || q + k >= e1) { r.v[k] = 0.0; if (!STRIPED) r.c[k] = safe; }
     } else {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) { r.v[k] = 0.0; r.c[k] = safe; }
+        for (int k = 0; k < 4; ++k) { r.v[k] = 0.0; if (!STRIPED) r.c[k] = safe; }
+    }
+    if (STRIPED) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t e = cb + 32u * k + (uint32_t)lane;
+            r.c[k] = (e >= e0 && e < e1) ? ldg_stream_s32_1(a.idx + e, pol_stream) : safe;
+        }
     }
 }
 
@@ -286,8 +310,10 @@ __device__ __forceinline__ void warp_chunk_core(const SpmvArgs &a, const BlockCt
 }
 
 // Processes the chunk [base, base+128) held in `cur`; `nxt` receives the following chunk, whose loads stay in
-// flight while this one is reduced.  WIN: the gathers are reads of the warp's staged window.
-template <int FIN, bool WIN>
+// flight while this one is reduced.  WIN: the gathers are reads of the warp's staged window.  STRIPED: the gathered
+// values arrive in striped order (entry 32 k + lane) and are transposed to the blocked order of the values (entries
+// 4 lane .. 4 lane + 3) through the warp's shared buffer.
+template <int FIN, bool WIN, bool STRIPED>
 __device__ __forceinline__ void warp_chunk(const SpmvArgs &a, const BlockCtx &bc, Epilogue<FIN> &epi, double *su,
                                            const double *xw /* WIN: window - win_lo */, WarpTileState<FIN> &ts,
                                            const ChunkRegs &cur, ChunkRegs &nxt, uint32_t base, uint32_t r1,
@@ -303,11 +329,20 @@ __device__ __forceinline__ void warp_chunk(const SpmvArgs &a, const BlockCtx &bc
         x2 = ldg_keep_f64(a.x + cur.c[2], pol_keep);
         x3 = ldg_keep_f64(a.x + cur.c[3], pol_keep);
     }
-    load_chunk(a, base + kChunk, lane, e0, e1, safe, pol_stream, nxt);
+    load_chunk<STRIPED>(a, base + kChunk, lane, e0, e1, safe, pol_stream, nxt);
+    if (STRIPED) {
+        // (su is free here: the previous chunk's row sums were consumed before its closing __syncwarp)
+        su[lane] = x0; su[32 + lane] = x1; su[64 + lane] = x2; su[96 + lane] = x3;
+        __syncwarp();
+        const double2 p = *reinterpret_cast<const double2 *>(su + 4 * lane);
+        const double2 q = *reinterpret_cast<const double2 *>(su + 4 * lane + 2);
+        x0 = p.x; x1 = p.y; x2 = q.x; x3 = q.y;
+        __syncwarp();                   // every lane has its values before the scan overwrites su
+    }
     warp_chunk_core<FIN>(a, bc, epi, su, ts, cur.v, x0, x1, x2, x3, base, r1, e1, lane);
 }
 
-template <int FIN, bool WIN>
+template <int FIN, bool WIN, bool STRIPED>
 __device__ __forceinline__ void warp_tile_loop(const SpmvArgs &a, const BlockCtx &bc, Epilogue<FIN> &epi, double *su,
                                                const double *xw, uint32_t r0, uint32_t r1, uint32_t e0, uint32_t e1,
                                                int32_t safe, int lane, uint64_t pol_stream, uint64_t pol_keep)
@@ -319,21 +354,21 @@ __device__ __forceinline__ void warp_tile_loop(const SpmvArgs &a, const BlockCtx
     ts.carry = 0.0;
     ts.win.load(a, bc, r0, r1, lane);
     ChunkRegs ra, rb;
-    load_chunk(a, a0, lane, e0, e1, safe, pol_stream, ra);
+    load_chunk<STRIPED>(a, a0, lane, e0, e1, safe, pol_stream, ra);
     // two chunks per trip so that the register double buffer needs no copies; at least one chunk is processed
     // even for a piece without entries, so that its (empty) rows still get their epilogue
     for (uint32_t base = a0;;) {
-        warp_chunk<FIN, WIN>(a, bc, epi, su, xw, ts, ra, rb, base, r1, e0, e1, safe, lane, pol_stream, pol_keep);
+        warp_chunk<FIN, WIN, STRIPED>(a, bc, epi, su, xw, ts, ra, rb, base, r1, e0, e1, safe, lane, pol_stream, pol_keep);
         base += kChunk;
         if (base >= e1) break;
-        warp_chunk<FIN, WIN>(a, bc, epi, su, xw, ts, rb, ra, base, r1, e0, e1, safe, lane, pol_stream, pol_keep);
+        warp_chunk<FIN, WIN, STRIPED>(a, bc, epi, su, xw, ts, rb, ra, base, r1, e0, e1, safe, lane, pol_stream, pol_keep);
         base += kChunk;
         if (base >= e1) break;
     }
 }
 
 // One piece: stage the gather window if the piece has one, then stream its chunks.
-template <int FIN>
+template <int FIN, bool STRIPED>
 __device__ __forceinline__ void warp_tile(const SpmvArgs &a, const BlockCtx &bc, Epilogue<FIN> &epi, double *su, double *wbuf,
                                           const TileDesc &d0, const TileDesc &d1, int lane,
                                           uint64_t pol_stream, uint64_t pol_keep)
@@ -343,16 +378,17 @@ __device__ __forceinline__ void warp_tile(const SpmvArgs &a, const BlockCtx &bc,
         const double *src = a.x + d0.win_lo;
         for (uint32_t i = (uint32_t)lane; i < d0.win_len; i += 32u) wbuf[i] = ldg_keep_f64(src + i, pol_keep);
         __syncwarp();
-        warp_tile_loop<FIN, true>(a, bc, epi, su, wbuf - d0.win_lo, d0.row, d1.row, d0.entry, d1.entry,
-                                  (int32_t)d0.win_lo, lane, pol_stream, pol_keep);
+        // (a staged window is conflict-bound, not line-bound: the blocked index layout with its single 128-bit load)
+        warp_tile_loop<FIN, true, false>(a, bc, epi, su, wbuf - d0.win_lo, d0.row, d1.row, d0.entry, d1.entry,
+                                         (int32_t)d0.win_lo, lane, pol_stream, pol_keep);
     } else {
-        warp_tile_loop<FIN, false>(a, bc, epi, su, nullptr, d0.row, d1.row, d0.entry, d1.entry, 0, lane, pol_stream, pol_keep);
+        warp_tile_loop<FIN, false, STRIPED>(a, bc, epi, su, nullptr, d0.row, d1.row, d0.entry, d1.entry, 0, lane, pol_stream, pol_keep);
     }
 }
 
 // MINB: resident CTAs per SM the kernel is compiled for (4: <= 64 registers, 32 warps per SM; 2: <= 128 registers,
-// 16 warps per SM with room for wide gather windows).
-template <int FIN, int MINB>
+// 16 warps per SM with room for wide gather windows).  STRIPED: lane-consecutive gathers (see load_chunk).
+template <int FIN, int MINB, bool STRIPED>
 __global__ void __launch_bounds__(kWThreads, MINB)
 spmv_kernel(SpmvArgs a)
 {
@@ -403,7 +439,14 @@ spmv_kernel(SpmvArgs a)
                 // block of slack.
                 if (lane == 0) {
                     const volatile unsigned int *done = &st->blk_done[b - a.guard];
-                    while (*done < (unsigned int)nw) __nanosleep(100);
+                    const unsigned long long t0 = globaltimer_ns();
+                    while (*done < (unsigned int)nw) {
+                        __nanosleep(100);
+                        // (belt and braces: the launch is cooperative, so the grid IS co-resident; should a warp still
+                        // wait for seconds, latch an error the host reports instead of hanging the GPU)
+                        if (*(volatile int *)&st->guard_error) break;
+                        if (globaltimer_ns() - t0 > 4000000000ull) { st->guard_error = 1; break; }
+                    }
                 }
                 __syncwarp();
             }
@@ -413,7 +456,7 @@ spmv_kernel(SpmvArgs a)
                 if (t == kNoTile) break;                        // this warp's list is exhausted
                 const TileDesc d0 = tiles[t], d1 = tiles[t + 1];
                 if (d0.row == d1.row) continue;                 // no row starts in this tile (inside a long row)
-                warp_tile<FIN>(a, bc, epi, su, wbuf, d0, d1, lane, pol_stream, pol_keep);
+                warp_tile<FIN, STRIPED>(a, bc, epi, su, wbuf, d0, d1, lane, pol_stream, pol_keep);
             }
             if (a.guard && b + 1 < a.nblocks) {
                 __syncwarp();
@@ -480,29 +523,38 @@ __global__ void build_tiles_kernel(const uint32_t *__restrict__ ptr, int64_t nro
     }
 }
 
-// Gather span of every piece: one warp per piece scans its indices (min / max), 16 bytes per lane and step.
+// Gather span of every piece: one warp per piece scans its indices (min / max).  On the way it measures how local 32
+// CONSECUTIVE stored entries are: stat[0] += 128-byte lines a gather of such a group can touch at most
+// (span of the group / 16 + 1, capped at 32), stat[1] += groups.  Integer atomics: order-independent.
 __global__ void __launch_bounds__(256)
-tile_span_kernel(const int32_t *__restrict__ idx, TileDesc *tiles, int64_t npieces_with_sentinels, int ntiles)
+tile_span_kernel(const int32_t *__restrict__ idx, TileDesc *tiles, int64_t npieces_with_sentinels, int ntiles,
+                 unsigned long long *stat)
 {
     const int lane = threadIdx.x & 31;
     const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    unsigned long long lines = 0, groups = 0;
     for (int64_t p = w; p < npieces_with_sentinels; p += nwarps) {
         if ((p % ((int64_t)ntiles + 1)) == ntiles) continue;      // the sentinel entry that closes a block's list
         const uint32_t e0 = tiles[p].entry, e1 = tiles[p + 1].entry;
         int32_t lo = INT32_MAX, hi = INT32_MIN;
-        for (uint32_t e = e0 + (uint32_t)lane; e < e1; e += 32u) {
-            const int32_t c = idx[e];
-            lo = min(lo, c);
-            hi = max(hi, c);
+        for (uint32_t eb = e0; eb < e1; eb += 32u) {
+            const uint32_t e = eb + (uint32_t)lane;
+            const bool ok = e < e1;
+            const int32_t c = ok ? idx[e] : 0;
+            const int32_t glo = __reduce_min_sync(0xffffffffu, ok ? c : INT32_MAX);
+            const int32_t ghi = __reduce_max_sync(0xffffffffu, ok ? c : INT32_MIN);
+            lo = min(lo, glo);
+            hi = max(hi, ghi);
+            lines += (unsigned long long)min(32, (ghi - glo) / 16 + 1);
+            groups += 1;
         }
-        lo = __reduce_min_sync(0xffffffffu, lo);
-        hi = __reduce_max_sync(0xffffffffu, hi);
         if (lane == 0) {
             tiles[p].win_lo = e1 > e0 ? (uint32_t)lo : 0u;
             tiles[p].win_len = e1 > e0 ? (uint32_t)(hi - lo + 1) : 0u;   // span; the host clears it where it exceeds the window
         }
     }
+    if (lane == 0 && groups) { atomicAdd(stat, lines); atomicAdd(stat + 1, groups); }
 }
 
 // win_len > cap (or an empty piece) -> 0: that piece gathers from global memory

@@ -173,3 +173,99 @@ def test_two_process_gloo_row_partition(tmp_path):
                        capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     assert r.stdout.count("RANK_OK") == 2
+
+
+# ------------------------------------------------------------------ struct layouts across the three host layers
+_F2C = {"real(c_double)": "double", "integer(c_int32_t)": "int32_t", "integer(c_int64_t)": "int64_t",
+        "type(c_ptr)": "ptr", "type(c_funptr)": "ptr"}
+
+
+def _fortran_bind_c_fields(type_name):
+    """(name, C kind) of every component of `type,bind(C) :: <type_name>` in the Fortran shim, in order."""
+    text = open(os.path.join(ROOT, "fortran", "lsqr_b200_shim.F90")).read()
+    body = re.search(r"type,bind\(C\)\s*::\s*%s\b(.*?)end type" % type_name, text, re.S).group(1)
+    fields = []
+    for line in body.splitlines():
+        line = line.split("!")[0].strip()
+        mm = re.match(r"(real\(c_double\)|integer\(c_int32_t\)|integer\(c_int64_t\)|type\(c_ptr\)|type\(c_funptr\))\s*::\s*(.*)", line)
+        if mm:
+            for decl in mm.group(2).split(","):
+                fields.append((decl.split("=")[0].strip(), _F2C[mm.group(1)]))
+    return fields
+
+
+def test_options_struct_layout_agrees_in_c_python_and_fortran(tmp_path):
+    """No Fortran compiler exists in this image, so the bind(C) struct of the shim is checked against the C header
+    the hard way: a C program prints offsetof / sizeof of every field of lsqr_b200_options as the C compiler lays it
+    out; ctypes (the Python mirror) must give the same offsets, and the Fortran component list must have the same
+    names in the same order with interoperable kinds of the same size (iso_c_binding then guarantees the layout)."""
+    import lsqr_b200
+    from lsqr_b200._lib import Options, KernelTimes, PlanInfo, IterRecord
+    fields = [f[0] for f in Options._fields_]
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "lsqr_b200.h"\nint main(void) {\n' +
+                   "".join('printf("%s %%zu %%zu\\n", offsetof(lsqr_b200_options, %s), sizeof(((lsqr_b200_options *)0)->%s));\n' % (f, f, f)
+                           for f in fields) +
+                   'printf("sizeof %zu %zu %zu %zu\\n", sizeof(lsqr_b200_options), sizeof(lsqr_b200_kernel_times), '
+                   'sizeof(lsqr_b200_plan_info), sizeof(lsqr_b200_iter_record));\nreturn 0; }\n')
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split("\n")
+    c_layout = {}
+    for line in out:
+        t = line.split()
+        if len(t) == 3:
+            c_layout[t[0]] = (int(t[1]), int(t[2]))
+        elif t and t[0] == "sizeof":
+            sizes = [int(v) for v in t[1:]]
+    assert list(c_layout) == fields                                       # the header declares them in this order
+    for f in fields:
+        d = getattr(Options, f)
+        assert (d.offset, d.size) == c_layout[f], (f, d.offset, d.size, c_layout[f])
+    assert sizes == [C.sizeof(Options), C.sizeof(KernelTimes), C.sizeof(PlanInfo), C.sizeof(IterRecord)]
+    # Fortran: same names, same order, interoperable kinds of the same size
+    fort = _fortran_bind_c_fields("lsqr_b200_options")
+    assert [n for n, _ in fort] == fields
+    size_of = {"double": 8, "int32_t": 4, "int64_t": 8, "ptr": C.sizeof(C.c_void_p)}
+    for (name, kind) in fort:
+        assert size_of[kind] == c_layout[name][1], (name, kind)
+    # and its defaults are the reference's (src/lsqr.f90:46-51) / the C defaults
+    text = open(os.path.join(ROOT, "fortran", "lsqr_b200_shim.F90")).read()
+    assert "itnlim = 100_c_int32_t" in text and "use_graph = 1" in text and "world_size = 1" in text
+
+
+def test_fortran_shim_keeps_the_reference_names_and_argument_lists():
+    """b8: modules lsqr_kinds / lsqr_module / lsqpblas_module, types lsqr_solver / lsqr_solver_ez, bindings
+    initialize / solve / aprod / lsqr / acheck / xcheck with the reference's dummy-argument lists (checked textually
+    against /root/reference when it is present, else against the lists recorded here from src/lsqr.f90)."""
+    text = open(os.path.join(ROOT, "fortran", "lsqr_b200_shim.F90")).read().lower()
+    for mod in ("lsqr_kinds", "lsqr_module", "lsqpblas_module"):
+        assert re.search(r"^\s*module %s\b" % mod, text, re.M), mod
+    want = {   # src/lsqr.f90:91,134,207,432-435,908-909,1015-1017; src/lsqrblas.f90:25,74,123,166
+        "initialize_ez": "me,m,n,a,irow,icol,atol,btol,conlim,itnlim,nout",
+        "aprod_ez": "me,mode,m,n,x,y",
+        "solve_ez": "me,b,damp,x,istop,se,itn,anorm,acond,rnorm,arnorm,xnorm",
+        "lsqr": "me,m,n,damp,wantse,u,v,w,x,se,atol,btol,conlim,itnlim,nout,istop,itn,anorm,acond,rnorm,arnorm,xnorm",
+        "acheck": "me,m,n,nout,eps,v,w,x,y,inform",
+        "xcheck": "me,m,n,nout,anorm,damp,eps,b,u,v,w,x,inform,test1,test2,test3",
+        "dcopy": "n,dx,incx,dy,incy", "ddot": "n,dx,incx,dy,incy", "dnrm2": "n,x,incx", "dscal": "n,da,dx,incx",
+    }
+    ref_dir = "/root/reference/src"
+    ref_text = ""
+    if os.path.isdir(ref_dir):
+        ref_text = "".join(open(os.path.join(ref_dir, f)).read().lower() for f in ("lsqr.f90", "lsqrblas.f90"))
+
+    def arglist(src, name):
+        mm = re.search(r"(?:subroutine|function)\s+%s\s*\((.*?)\)" % name, src, re.S)
+        assert mm, name
+        return re.sub(r"[\s&]", "", mm.group(1))
+
+    for name, args in want.items():
+        assert arglist(text, name) == args, (name, arglist(text, name))
+        if ref_text:
+            assert arglist(ref_text, name) == args, ("reference", name)
+    for binding in ("initialize => initialize_ez", "solve      => solve_ez", "aprod      => aprod_ez"):
+        assert binding in text
+    assert re.search(r"procedure\(aprod_func\),deferred,public :: aprod", text)
+    for proc in ("lsqr", "acheck", "xcheck"):
+        assert re.search(r"procedure,public :: %s\b" % proc, text)
