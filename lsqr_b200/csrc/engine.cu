@@ -692,7 +692,7 @@ static int build_graph(lsqr_b200_ez *me, bool wantse)
     cudaError_t e = cudaStreamEndCapture(wk.stream, &graph);
     me->graph_launches = wk.launches - saved;
     wk.launches = saved;
-    if (rc != LSQR_B200_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (rc != LSQR_B200_OK) { if (graph) cudaGraphDestroy(graph); cudaGetLastError(); return rc; }   // (clears the capture's sticky error)
     LSQRB_CUDA(e);
     LSQRB_CUDA(cudaGraphInstantiate(&me->graph_exec, graph, 0));
     cudaGraphDestroy(graph);

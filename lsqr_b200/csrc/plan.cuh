@@ -30,6 +30,7 @@ struct TilePlan {
     size_t smem = 0;             // dynamic shared memory per CTA
     double imbalance = 1.0;      // most loaded warp / mean load under the schedule in use (diagnostic)
     double windowed = 0.0;       // fraction of the stored entries whose gathers are served from shared memory
+    int resident_checked = 0;    // 1: the probe found the first grid co-resident, -1: the grid had to shrink
     int striped = 0;             // lane-consecutive gathers (matrices whose rows hold clustered / sorted indices)
     double lines_per_gather = 32.0;   // 128-byte lines that 32 consecutive stored entries span (32 = no locality)
     unsigned long long *stat = nullptr;   // device scratch of the locality measurement
@@ -230,6 +231,8 @@ static void window_stats(const TilePlan &p, const std::vector<TileDesc> &t, uint
     *need = mx;
 }
 
+static int plan_probe(Work &wk, const TilePlan &P, bool *resident);
+
 static int build_plan(Work &wk, const Csr &M, TilePlan *p, int reserve_sms = 0)
 {
     p->row_w = (uint32_t)std::max(0, env_int("LSQR_B200_TILE_ROW_WEIGHT", 4));
@@ -295,6 +298,21 @@ static int build_plan(Work &wk, const Csr &M, TilePlan *p, int reserve_sms = 0)
             }
         }
     }
+    if (M.nblocks > 1) {
+        // the guarded multi-block launch needs the whole persistent grid resident at once: prove it, or shrink the grid
+        for (int tries = 0; tries < 3; ++tries) {
+            bool resident = false;
+            LSQRB_TRY(plan_probe(wk, *p, &resident));
+            if (resident) break;
+            const int per_sm = std::max(1, p->ctas / std::max(1, wk.sms - reserve_sms) - 1);
+            if (env_int("LSQR_B200_VERBOSE", 0)) fprintf(stderr, "[lsqr_b200] persistent grid of %d CTAs is not co-resident: %d CTAs per SM\n", p->ctas, per_sm);
+            p->ctas = std::max(1, wk.sms - reserve_sms) * per_sm;
+            LSQRB_TRY(plan_cut(wk, M, p, 0));
+            LSQRB_TRY(plan_fetch(wk, *p, &t));
+            p->resident_checked = -1;
+        }
+        if (p->resident_checked == 0) p->resident_checked = 1;
+    }
     {   // span statistics (diagnostic) and the final window assignment
         std::vector<uint32_t> spans;
         const size_t st = (size_t)p->ntiles + 1;
@@ -349,15 +367,33 @@ static int launch_piece(Work &wk, const TilePlan &P, const SpmvArgs &a)
     cfg.blockDim = dim3(kWThreads);
     cfg.dynamicSmemBytes = P.smem;
     cfg.stream = wk.stream;
-    cudaLaunchAttribute attr[1];
-    memset(attr, 0, sizeof attr);
-    // a guarded multi-block launch spins on the other warps of its grid: launched COOPERATIVELY, so that the driver
-    // either makes the whole grid co-resident or refuses the launch -- never a partly resident grid that waits for ever
-    if (a.guard) { attr[0].id = cudaLaunchAttributeCooperative; attr[0].val.cooperative = 1; cfg.attrs = attr; cfg.numAttrs = 1; }
+    // (a guarded multi-block launch is a grid barrier per block: its grid was PROVEN co-resident by the probe at
+    // initialize; a cooperative launch would be the textbook guarantee, but the runtime refused these grids -- "too
+    // many blocks in cooperative launch" -- although the occupancy API reports the same 4 CTAs per SM)
     if (P.minb == 4) { if (P.striped) LSQRB_CUDA(cudaLaunchKernelEx(&cfg, spmv_kernel<FIN, 4, true>, a)); else LSQRB_CUDA(cudaLaunchKernelEx(&cfg, spmv_kernel<FIN, 4, false>, a)); }
     else             { if (P.striped) LSQRB_CUDA(cudaLaunchKernelEx(&cfg, spmv_kernel<FIN, 2, true>, a)); else LSQRB_CUDA(cudaLaunchKernelEx(&cfg, spmv_kernel<FIN, 2, false>, a)); }
     wk.launches++;
     LSQRB_CUDA(cudaGetLastError());
+    return LSQR_B200_OK;
+}
+
+// Launches the flavour's kernel in probe mode on the plan's grid: true if every CTA saw every other one arrive.
+static int plan_probe(Work &wk, const TilePlan &P, bool *resident)
+{
+    *resident = false;
+    LSQRB_CUDA(cudaMemsetAsync(&wk.st->probe_count, 0, sizeof(unsigned int) + sizeof(int), wk.stream));
+    SpmvArgs a;
+    memset(&a, 0, sizeof a);
+    a.probe = 1;
+    a.st = wk.st;
+    TilePlan Q = P;
+    Q.order = reinterpret_cast<uint32_t *>(1);      // (forces the full persistent grid; never dereferenced in probe mode)
+    LSQRB_TRY(launch_piece<FIN_ATPROD>(wk, Q, a));
+    wk.launches--;
+    int fail = 1;
+    LSQRB_CUDA(cudaMemcpyAsync(&fail, &wk.st->probe_fail, sizeof(int), cudaMemcpyDeviceToHost, wk.stream));
+    LSQRB_CUDA(cudaStreamSynchronize(wk.stream));
+    *resident = fail == 0;
     return LSQR_B200_OK;
 }
 

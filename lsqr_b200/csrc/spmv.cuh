@@ -80,6 +80,7 @@ struct SpmvArgs {
     int win_cap;               // doubles of shared-memory gather window per warp (0 = none)
     int guard;                 // 0: none; g > 0: block b starts when every warp has finished block b - g (1 = one live slice)
     int check_done;            // plain product launched from the solve loop: nothing to do once the solver has stopped
+    int probe;                 // residency probe: arrive, wait for the whole grid (or 20 ms), leave
     DevState *st;
     Ssq *aux;                  // FIN_APROD, multi-GPU: where the local sum u'^2 goes instead of step_after_aprod
     // FIN_PUSH: push[q] = where this rank's contributions to the columns owned by rank q go (q's receive buffer,
@@ -400,6 +401,19 @@ spmv_kernel(SpmvArgs a)
     DevState *st = a.st;
     const int tid = threadIdx.x;
     bool tracing = false;
+    if (a.probe) {
+        // Residency probe (initialize): do ALL CTAs of this grid run at the same time, with this kernel's registers and
+        // this launch's shared memory?  The drift guard of a multi-block launch is a grid barrier and relies on it.
+        if (tid == 0) {
+            atomicAdd(&st->probe_count, 1u);
+            const unsigned long long t0 = globaltimer_ns();
+            while (*(volatile unsigned int *)&st->probe_count < gridDim.x) {
+                if (globaltimer_ns() - t0 > 20000000ull) { st->probe_fail = 1; break; }
+                __nanosleep(200);
+            }
+        }
+        return;
+    }
     if (kFused) {
         if (st->done) return;
         if (FIN == FIN_APROD && st->istop != 0) return;   // the stop is decided: only the x/w update of that iteration is left
@@ -433,22 +447,23 @@ spmv_kernel(SpmvArgs a)
             bc.mode = (b == a.nblocks - 1 && a.last_is_final) ? BM_FINAL : (b == 0 ? a.first_mode : BM_ACC);
             bc.adds_part = a.final_adds_part != 0;
             if (a.guard && b >= a.guard) {
-                // guard = 1: a block starts when EVERY warp has finished the previous one, so exactly one gathered slice
+                // guard = 1: a block starts when EVERY CTA has finished the previous one, so exactly one gathered slice
                 // is live in L2 (measured: a warp that runs ahead touches the whole next slice within microseconds --
                 // random gathers -- and two 48 MB slices do not fit; C5/4 Atprod 7.3 ms vs 5.4 ms).  guard = 2: one
-                // block of slack.
-                if (lane == 0) {
+                // block of slack.  One thread per CTA polls (4736 polling warps stole L1TEX cycles from the stragglers
+                // they were waiting for: 6 % on C5/4); the launch is cooperative, so the grid is co-resident.
+                if (tid == 0) {
                     const volatile unsigned int *done = &st->blk_done[b - a.guard];
                     const unsigned long long t0 = globaltimer_ns();
-                    while (*done < (unsigned int)nw) {
-                        __nanosleep(100);
-                        // (belt and braces: the launch is cooperative, so the grid IS co-resident; should a warp still
-                        // wait for seconds, latch an error the host reports instead of hanging the GPU)
+                    while (*done < gridDim.x) {
+                        __nanosleep(400);
+                        // (belt and braces: should a CTA still wait for seconds, latch an error the host reports
+                        // instead of hanging the GPU)
                         if (*(volatile int *)&st->guard_error) break;
                         if (globaltimer_ns() - t0 > 4000000000ull) { st->guard_error = 1; break; }
                     }
                 }
-                __syncwarp();
+                __syncthreads();
             }
             const TileDesc *__restrict__ tiles = a.tiles + (size_t)b * ((size_t)a.ntiles + 1);
             for (int s = (int)blockIdx.x * kWWarps + wib; s < nslots; s += nw) {
@@ -459,8 +474,8 @@ spmv_kernel(SpmvArgs a)
                 warp_tile<FIN, STRIPED>(a, bc, epi, su, wbuf, d0, d1, lane, pol_stream, pol_keep);
             }
             if (a.guard && b + 1 < a.nblocks) {
-                __syncwarp();
-                if (lane == 0) atomicAdd(&st->blk_done[b], 1u);
+                __syncthreads();                                // every warp of this CTA has finished block b
+                if (tid == 0) atomicAdd(&st->blk_done[b], 1u);
             }
         }
     }
