@@ -193,7 +193,7 @@ typedef struct lsqr_b200_plan_info {
     int64_t nblocks;            /* blocks along the gathered coordinate (1 = plain CSR)                         */
     int64_t ntiles;             /* row-aligned tiles; the same row cuts in every block                          */
     int32_t grid_ctas;          /* persistent grid                                                              */
-    int32_t ctas_per_sm;        /* kernel flavour: 4 (32 warps per SM) or 2 (16 warps, wide gather windows)     */
+    int32_t ctas_per_sm;        /* resident CTAs per SM of the kernel flavour: 4 (EPL 4) or 2 (EPL 8)            */
     int32_t window_doubles;     /* shared-memory gather window per warp, in doubles (0 = gathers stay global)   */
     int32_t balanced;           /* largest-first tile schedule in use (very uneven row lengths)                 */
     double  windowed_fraction;  /* fraction of the stored entries whose gathers are served from shared memory   */
@@ -201,7 +201,7 @@ typedef struct lsqr_b200_plan_info {
     int64_t span_median, span_max;  /* gather span of the pieces (entries of the dense vector)                  */
     int32_t single_launch;      /* one persistent launch walks every block of a product                         */
     int32_t peer_exchange;      /* multi-GPU: exchange over NVLink peer memory instead of one NCCL all-reduce   */
-    int32_t striped_gathers;    /* lane-consecutive gathers (rows with clustered / sorted indices)              */
+    int32_t entries_per_lane;   /* kernel flavour: 4 (gather-bound matrices) or 8 (matrices with local gathers)  */
     int32_t reserved;
     double  lines_per_gather;   /* 128-byte lines spanned by 32 consecutive stored entries (32 = no locality)   */
 } lsqr_b200_plan_info;

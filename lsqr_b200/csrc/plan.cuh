@@ -25,13 +25,12 @@ struct TilePlan {
     uint32_t *order = nullptr;   // device: balanced schedule, or nullptr = round robin
     int nslots = 0;
     int ctas = 0;                // persistent grid the plan was cut for
-    int minb = 4;                // kernel flavour: resident CTAs per SM
+    int epl = 4;                 // kernel flavour: stored entries per lane and chunk (4: 4 CTAs per SM, 8: 2 CTAs per SM)
     int win_cap = 0;             // doubles of gather window per warp (0 = no staging)
     size_t smem = 0;             // dynamic shared memory per CTA
     double imbalance = 1.0;      // most loaded warp / mean load under the schedule in use (diagnostic)
     double windowed = 0.0;       // fraction of the stored entries whose gathers are served from shared memory
     int resident_checked = 0;    // 1: the probe found the first grid co-resident, -1: the grid had to shrink
-    int striped = 0;             // lane-consecutive gathers (matrices whose rows hold clustered / sorted indices)
     double lines_per_gather = 32.0;   // 128-byte lines that 32 consecutive stored entries span (32 = no locality)
     unsigned long long *stat = nullptr;   // device scratch of the locality measurement
     uint32_t span_p50 = 0, span_max = 0;   // gather span (entries of the dense vector) of the pieces: median, maximum
@@ -45,22 +44,23 @@ static inline void plan_free(TilePlan &p)
     p.tiles = nullptr; p.order = nullptr; p.stat = nullptr;
 }
 
-constexpr int kWinCap4 = 640;    // 8 warps x (128 + 640) doubles = 48 KB per CTA, 4 CTAs per SM
-constexpr int kWinCap2 = 1600;   // 8 warps x (128 + 1600) doubles = 108 KB per CTA, 2 CTAs per SM
+constexpr int kWinCap4 = 640;    // EPL = 4: 8 warps x (128 + 640) doubles = 48 KB per CTA, 4 CTAs per SM
+constexpr int kWinCap2 = 1472;   // EPL = 8: 8 warps x (256 + 1472) doubles = 108 KB per CTA, 2 CTAs per SM
 
-static inline size_t plan_smem(int win_cap) { return (size_t)kWWarps * (size_t)(kChunk + win_cap) * sizeof(double); }
+static inline size_t plan_smem(int epl, int win_cap) { return (size_t)kWWarps * (size_t)(32 * epl + win_cap) * sizeof(double); }
 
 // Opt in to the dynamic shared memory the flavour needs and measure its co-residency (the soft drift guard of a
 // multi-block launch spins on the other warps of the grid: the grid must fit the GPU).
 // The shared-memory carve-out is set to what the resident CTAs need and no more: what is left of the 228 KB is L1,
 // and the divergent gathers of the non-windowed path live on L1 (every pending miss holds a line: with the
 // carve-out at 100 % the same kernel ran at HALF speed on every workload, profiles/r02/run1).
-template <int FIN, int MINB, bool STRIPED>
+template <int FIN, int EPL>
 static int spmv_prepare(size_t smem, int *ctas_per_sm)
 {
-    LSQRB_CUDA(cudaFuncSetAttribute(spmv_kernel<FIN, MINB, STRIPED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan_smem(MINB == 4 ? kWinCap4 : kWinCap2)));
+    constexpr int MINB = EPL == 4 ? 4 : 2;
+    LSQRB_CUDA(cudaFuncSetAttribute(spmv_kernel<FIN, EPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan_smem(EPL, EPL == 4 ? kWinCap4 : kWinCap2)));
     cudaFuncAttributes fa;
-    LSQRB_CUDA(cudaFuncGetAttributes(&fa, spmv_kernel<FIN, MINB, STRIPED>));
+    LSQRB_CUDA(cudaFuncGetAttributes(&fa, spmv_kernel<FIN, EPL>));
     const size_t per_cta = smem + fa.sharedSizeBytes + 1024;   // + the 1 KB the hardware reserves per CTA
     // the carve-out comes in steps and the preference is rounded to the NEAREST step, up or down: name the smallest
     // step that holds MINB CTAs exactly (a rounded-down carve-out would leave the persistent grid partly non-resident)
@@ -69,22 +69,22 @@ static int spmv_prepare(size_t smem, int *ctas_per_sm)
     for (int kb : steps_kb)
         if ((size_t)kb * 1024 >= per_cta * (size_t)MINB) { pct = (kb * 100 + 227) / 228; break; }
     pct = std::max(0, std::min(env_int("LSQR_B200_SMEM_CARVEOUT_PCT", pct), 100));
-    LSQRB_CUDA(cudaFuncSetAttribute(spmv_kernel<FIN, MINB, STRIPED>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+    LSQRB_CUDA(cudaFuncSetAttribute(spmv_kernel<FIN, EPL>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
     int n = 0;
-    LSQRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, spmv_kernel<FIN, MINB, STRIPED>, kWThreads, smem));
+    LSQRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, spmv_kernel<FIN, EPL>, kWThreads, smem));
     *ctas_per_sm = std::min(n, MINB);
     return LSQR_B200_OK;
 }
 
-template <int MINB, bool STRIPED>
+template <int EPL>
 static int spmv_prepare_all(size_t smem, int *ctas_per_sm)
 {
-    int occ = MINB, o = 0;
-    LSQRB_TRY((spmv_prepare<FIN_NONE, MINB, STRIPED>(smem, &o)));        occ = std::min(occ, o);
-    LSQRB_TRY((spmv_prepare<FIN_APROD, MINB, STRIPED>(smem, &o)));       occ = std::min(occ, o);
-    LSQRB_TRY((spmv_prepare<FIN_ATPROD, MINB, STRIPED>(smem, &o)));      occ = std::min(occ, o);
-    LSQRB_TRY((spmv_prepare<FIN_INIT_ATPROD, MINB, STRIPED>(smem, &o))); occ = std::min(occ, o);
-    LSQRB_TRY((spmv_prepare<FIN_PUSH, MINB, STRIPED>(smem, &o)));        occ = std::min(occ, o);
+    int occ = EPL == 4 ? 4 : 2, o = 0;
+    LSQRB_TRY((spmv_prepare<FIN_NONE, EPL>(smem, &o)));        occ = std::min(occ, o);
+    LSQRB_TRY((spmv_prepare<FIN_APROD, EPL>(smem, &o)));       occ = std::min(occ, o);
+    LSQRB_TRY((spmv_prepare<FIN_ATPROD, EPL>(smem, &o)));      occ = std::min(occ, o);
+    LSQRB_TRY((spmv_prepare<FIN_INIT_ATPROD, EPL>(smem, &o))); occ = std::min(occ, o);
+    LSQRB_TRY((spmv_prepare<FIN_PUSH, EPL>(smem, &o)));        occ = std::min(occ, o);
     *ctas_per_sm = occ;
     return LSQR_B200_OK;
 }
@@ -236,16 +236,16 @@ static int plan_probe(Work &wk, const TilePlan &P, bool *resident);
 static int build_plan(Work &wk, const Csr &M, TilePlan *p, int reserve_sms = 0)
 {
     p->row_w = (uint32_t)std::max(0, env_int("LSQR_B200_TILE_ROW_WEIGHT", 4));
-    p->minb = 4;
+    p->epl = 4;
     p->win_cap = 0;
     std::vector<TileDesc> t;
     const int want_window = env_int("LSQR_B200_WINDOW", 1);
     const double min_frac = 1e-2 * env_int("LSQR_B200_WINDOW_MIN_PERCENT", 50);
     auto prepare = [&](int *occ) -> int {
-        p->smem = plan_smem(p->win_cap);
+        p->smem = plan_smem(p->epl, p->win_cap);
         *occ = 0;
-        if (p->minb == 4) { if (p->striped) LSQRB_TRY((spmv_prepare_all<4, true>(p->smem, occ))); else LSQRB_TRY((spmv_prepare_all<4, false>(p->smem, occ))); }
-        else              { if (p->striped) LSQRB_TRY((spmv_prepare_all<2, true>(p->smem, occ))); else LSQRB_TRY((spmv_prepare_all<2, false>(p->smem, occ))); }
+        if (p->epl == 4) LSQRB_TRY(spmv_prepare_all<4>(p->smem, occ));
+        else             LSQRB_TRY(spmv_prepare_all<8>(p->smem, occ));
         if (*occ < 1) { set_last_error("spmv kernel does not fit an SM"); return LSQR_B200_ERR_CUDA; }
         return LSQR_B200_OK;
     };
@@ -254,34 +254,32 @@ static int build_plan(Work &wk, const Csr &M, TilePlan *p, int reserve_sms = 0)
     p->ctas = std::max(1, wk.sms - reserve_sms) * occ;
     LSQRB_TRY(plan_cut(wk, M, p, 0));
     LSQRB_TRY(plan_fetch(wk, *p, &t));
-    p->striped = 0;
     const int forced_cap = env_int("LSQR_B200_WINDOW_CAP", 0);
     if (M.nnz > 0) {
-        // gather spans -> window: the narrow window keeps 32 warps per SM, the wide one halves them
+        // Flavour.  A matrix whose gathers are cheap -- every piece inside a shared-memory window, or 32 consecutive
+        // stored entries inside a few 128-byte lines -- is bound by instruction issue, not by the gather path: it gets
+        // the 8-entries-per-lane flavour (fewer instructions per entry, wide windows).  Everything else keeps 4
+        // entries per lane and 32 warps per SM.
         double f4 = 0, f2 = 0;
         uint32_t n4 = 0, n2 = 0;
         window_stats(*p, t, kWinCap4, &f4, &n4);
         window_stats(*p, t, kWinCap2, &f2, &n2);
+        const int forced_epl = env_int("LSQR_B200_EPL", 0);
+        const double max_lines = 1e-1 * env_int("LSQR_B200_LOCAL_MAX_LINES_X10", 200);
+        const bool local = (want_window && f2 >= min_frac) || p->lines_per_gather <= max_lines;
+        p->epl = forced_epl == 4 || forced_epl == 8 ? forced_epl : (local ? 8 : 4);
+        const uint32_t cap = (uint32_t)std::min<int>(p->epl == 4 ? kWinCap4 : kWinCap2, std::max(0, env_int("LSQR_B200_WINDOW_MAX", 1 << 20)));
+        double fw = p->epl == 4 ? f4 : f2;
+        uint32_t nw_need = p->epl == 4 ? n4 : n2;
+        if (cap < (uint32_t)(p->epl == 4 ? kWinCap4 : kWinCap2)) window_stats(*p, t, cap, &fw, &nw_need);
         if (!want_window) {
         } else if (forced_cap > 0) {
-            p->win_cap = std::min((forced_cap + 1) & ~1, kWinCap2);
-            p->minb = p->win_cap <= kWinCap4 ? 4 : 2;
-        } else if (f4 >= min_frac) {
-            p->win_cap = (int)((n4 + 1u) & ~1u);
-            p->minb = 4;
-        } else if (f2 >= min_frac && env_int("LSQR_B200_WINDOW_WIDE", 0)) {
-            // wide windows halve the resident warps: measured SLOWER than global gathers on the banded A' (C3 full size:
-            // 1.74 ms vs 1.38 ms, profiles/r02/run2), so they are opt-in
-            p->win_cap = (int)((n2 + 1u) & ~1u);
-            p->minb = 2;
+            p->win_cap = std::min((forced_cap + 1) & ~1, (int)cap);
+        } else if (fw >= min_frac) {
+            p->win_cap = (int)((nw_need + 1u) & ~1u);
         }
-        // lane-consecutive gathers where 32 consecutive stored entries share lines and no window serves most of them
-        const int forced = env_int("LSQR_B200_STRIPED", -1);
-        const double max_lines = 1e-1 * env_int("LSQR_B200_STRIPED_MAX_LINES_X10", 200);
-        const bool mostly_windowed = p->win_cap > 0 && forced_cap <= 0;
-        p->striped = forced >= 0 ? (forced != 0) : (p->lines_per_gather <= max_lines && !mostly_windowed);
     }
-    if (p->win_cap > 0 || p->striped) {
+    if (p->win_cap > 0 || p->epl != 4) {
         LSQRB_TRY(prepare(&occ));
         const int ctas = std::max(1, wk.sms - reserve_sms) * occ;
         if (ctas != p->ctas) {          // a different persistent grid: cut again for it, and size the window for the new pieces
@@ -289,10 +287,9 @@ static int build_plan(Work &wk, const Csr &M, TilePlan *p, int reserve_sms = 0)
             LSQRB_TRY(plan_cut(wk, M, p, 0));
             LSQRB_TRY(plan_fetch(wk, *p, &t));
             if (forced_cap <= 0 && p->win_cap > 0) {
-                const uint32_t cap = p->minb == 4 ? kWinCap4 : kWinCap2;
                 double f = 0;
                 uint32_t need = 0;
-                window_stats(*p, t, cap, &f, &need);
+                window_stats(*p, t, (uint32_t)std::min<int>(p->epl == 4 ? kWinCap4 : kWinCap2, std::max(0, env_int("LSQR_B200_WINDOW_MAX", 1 << 20))), &f, &need);
                 p->win_cap = (int)((need + 1u) & ~1u);
                 LSQRB_TRY(prepare(&occ));      // (occupancy cannot drop: the window only shrank or stayed under the flavour's cap)
             }
@@ -370,8 +367,8 @@ static int launch_piece(Work &wk, const TilePlan &P, const SpmvArgs &a)
     // (a guarded multi-block launch is a grid barrier per block: its grid was PROVEN co-resident by the probe at
     // initialize; a cooperative launch would be the textbook guarantee, but the runtime refused these grids -- "too
     // many blocks in cooperative launch" -- although the occupancy API reports the same 4 CTAs per SM)
-    if (P.minb == 4) { if (P.striped) LSQRB_CUDA(cudaLaunchKernelEx(&cfg, spmv_kernel<FIN, 4, true>, a)); else LSQRB_CUDA(cudaLaunchKernelEx(&cfg, spmv_kernel<FIN, 4, false>, a)); }
-    else             { if (P.striped) LSQRB_CUDA(cudaLaunchKernelEx(&cfg, spmv_kernel<FIN, 2, true>, a)); else LSQRB_CUDA(cudaLaunchKernelEx(&cfg, spmv_kernel<FIN, 2, false>, a)); }
+    if (P.epl == 4) LSQRB_CUDA(cudaLaunchKernelEx(&cfg, spmv_kernel<FIN, 4>, a));
+    else            LSQRB_CUDA(cudaLaunchKernelEx(&cfg, spmv_kernel<FIN, 8>, a));
     wk.launches++;
     LSQRB_CUDA(cudaGetLastError());
     return LSQR_B200_OK;
@@ -404,6 +401,7 @@ template <int FIN>
 static int launch_product(Work &wk, const Csr &M, const TilePlan &P, const ProductIo &io, bool single, int guard)
 {
     SpmvArgs a;
+    memset(&a, 0, sizeof a);        // (probe = 0 in particular)
     a.idx = M.idx; a.val = M.val;
     a.ptr_stride = M.nkeys;
     a.ntiles = P.ntiles;

@@ -34,7 +34,6 @@ namespace lsqrb {
 
 constexpr int kWThreads = 256;               // 8 warps per CTA
 constexpr int kWWarps = kWThreads / 32;
-constexpr uint32_t kChunk = 128;             // stored entries per warp step (4 per lane)
 constexpr uint32_t kPtrSentinel = 0xFFFFFFFFu;
 constexpr uint32_t kNoTile = 0xFFFFFFFFu;
 constexpr int kMaxSpmvBlocks = 64;           // DevState::blk_done
@@ -161,57 +160,53 @@ struct Epilogue {
     }
 };
 
-// One lane's share of a chunk: 4 consecutive stored entries.
+// One lane's share of a chunk: EPL consecutive stored entries (a chunk is 32 * EPL entries).
+//   EPL = 4: 24 registers of double buffer, 4 CTAs / 32 warps per SM -- the flavour for gather-bound matrices
+//            (uniformly random columns: the L1TEX tag stage is the limit, warps are what hides its latency);
+//   EPL = 8: the per-chunk work that does not depend on the chunk length (head mask, warp scan, row-end pass, window
+//            upkeep: ~2/3 of the instructions at EPL = 4) is spent once per 256 entries.  On matrices whose gathers are
+//            cheap (banded / local: shared-memory window or a few lines per gather) the kernel is bound by instruction
+//            issue, and this flavour (2 CTAs / 16 warps per SM, <= 128 registers, the same bytes and gathers in flight)
+//            is the faster one.
+template <int EPL>
 struct ChunkRegs {
-    double v[4];
-    int32_t c[4];
+    double v[EPL];
+    int32_t c[EPL];
 };
 
-__device__ __forceinline__ int32_t ldg_stream_s32_1(const int32_t *p, uint64_t pol)
+template <int EPL>
+__device__ __forceinline__ void ldg_chunk(const SpmvArgs &a, uint32_t q, uint64_t pol_stream, ChunkRegs<EPL> &r)
 {
-    int32_t r;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(pol));
-    return r;
+    if constexpr (EPL == 4) {
+        ldg_stream_f64x4(a.val + q, *reinterpret_cast<double (*)[4]>(&r.v[0]));
+        ldg_stream_s32x4(a.idx + q, *reinterpret_cast<int32_t (*)[4]>(&r.c[0]), pol_stream);
+    } else {
+        ldg_stream_f64x4(a.val + q, *reinterpret_cast<double (*)[4]>(&r.v[0]));
+        ldg_stream_f64x4(a.val + q + 4, *reinterpret_cast<double (*)[4]>(&r.v[EPL - 4]));
+        ldg_stream_s32x8(a.idx + q, *reinterpret_cast<int32_t (*)[8]>(&r.c[0]));
+    }
 }
 
-// Loads one lane's share of the chunk that starts at entry `cb` of the piece [e0, e1).  Values: entries
-// [cb+4 lane, +4) (blocked: what the segmented scan wants).  Indices: the same entries, or -- STRIPED -- entries
-// cb + 32 k + lane, k = 0..3, so that one gather instruction covers 32 CONSECUTIVE stored entries: in a matrix whose
-// rows hold clustered / sorted indices (banded A', FEM, tomography) those fall into a handful of 128-byte lines
-// instead of 32, and the L1TEX tag stage -- one line per clock -- stops being the limiter.
+// Loads one lane's share of the chunk that starts at entry `cb` of the piece [e0, e1): entries [cb + EPL lane, + EPL).
 // Entries outside the piece (they belong to the neighbouring pieces or to the allocation slack) get the value 0 and
 // the index `safe` (inside the piece's gather window), so they add nothing to any row and gather harmlessly.
-template <bool STRIPED>
+template <int EPL>
 __device__ __forceinline__ void load_chunk(const SpmvArgs &a, uint32_t cb, int lane, uint32_t e0, uint32_t e1,
-                                           int32_t safe, uint64_t pol_stream, ChunkRegs &r)
+                                           int32_t safe, uint64_t pol_stream, ChunkRegs<EPL> &r)
 {
-    const uint32_t q = cb + 4u * (uint32_t)lane;
-    if (cb >= e0 && cb + kChunk <= e1) {   // steady state: the whole chunk lies inside the piece
-        ldg_stream_f64x4(a.val + q, r.v);
-        if (STRIPED) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) r.c[k] = ldg_stream_s32_1(a.idx + cb + 32u * k + (uint32_t)lane, pol_stream);
-        } else {
-            ldg_stream_s32x4(a.idx + q, r.c, pol_stream);
-        }
+    const uint32_t q = cb + (uint32_t)EPL * (uint32_t)lane;
+    if (cb >= e0 && cb + 32u * EPL <= e1) {   // steady state: the whole chunk lies inside the piece
+        ldg_chunk<EPL>(a, q, pol_stream, r);
         return;
     }
     if (q < e1) {
-        ldg_stream_f64x4(a.val + q, r.v);
-        if (!STRIPED) ldg_stream_s32x4(a.idx + q, r.c, pol_stream);
+        ldg_chunk<EPL>(a, q, pol_stream, r);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-            if (q + k < e0 || q + k >= e1) { r.v[k] = 0.0; if (!STRIPED) r.c[k] = safe; }
+        for (int k = 0; k < EPL; ++k)
+            if (q + k < e0 || q + k >= e1) { r.v[k] = 0.0; r.c[k] = safe; }
     } else {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) { r.v[k] = 0.0; if (!STRIPED) r.c[k] = safe; }
-    }
-    if (STRIPED) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const uint32_t e = cb + 32u * k + (uint32_t)lane;
-            r.c[k] = (e >= e0 && e < e1) ? ldg_stream_s32_1(a.idx + e, pol_stream) : safe;
-        }
+        for (int k = 0; k < EPL; ++k) { r.v[k] = 0.0; r.c[k] = safe; }
     }
 }
 
@@ -222,27 +217,27 @@ struct WarpTileState {
     double carry;          // running sum of the row that is open at the chunk boundary
 };
 
-// Reduces the chunk [base, base+128): `cv` = the lane's 4 stored values, x0..x3 = the gathered vector entries.
-template <int FIN>
+// Reduces the chunk [base, base + 32 EPL): t[] = the lane's EPL products (stored value * gathered vector entry).
+template <int FIN, int EPL>
 __device__ __forceinline__ void warp_chunk_core(const SpmvArgs &a, const BlockCtx &bc, Epilogue<FIN> &epi, double *su,
-                                                WarpTileState<FIN> &ts, const double (&cv)[4],
-                                                double x0, double x1, double x2, double x3,
+                                                WarpTileState<FIN> &ts, double (&t)[EPL],
                                                 uint32_t base, uint32_t r1, uint32_t e1, int lane)
 {
-    const uint32_t endp = base + kChunk;
-    // ---- head mask of the chunk: bit i set <=> a row starts at entry base+i
-    uint32_t m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+    constexpr uint32_t kC = 32u * EPL;
+    const uint32_t endp = base + kC;
+    // ---- head mask of the chunk: bit i set <=> a row starts at entry base+i  (EPL words of 32 bits)
+    uint32_t m[EPL];
+#pragma unroll
+    for (int k = 0; k < EPL; ++k) m[k] = 0u;
     {
         uint32_t p = ts.win.P;
         uint32_t wb2 = ts.wb;
         for (;;) {
             const uint32_t rel = p - base;
-            const uint32_t bit = rel < kChunk ? (1u << (rel & 31u)) : 0u;
+            const uint32_t bit = rel < kC ? (1u << (rel & 31u)) : 0u;
             const uint32_t w = rel >> 5;
-            m0 |= __reduce_or_sync(0xffffffffu, w == 0u ? bit : 0u);
-            m1 |= __reduce_or_sync(0xffffffffu, w == 1u ? bit : 0u);
-            m2 |= __reduce_or_sync(0xffffffffu, w == 2u ? bit : 0u);
-            m3 |= __reduce_or_sync(0xffffffffu, w == 3u ? bit : 0u);
+#pragma unroll
+            for (int k = 0; k < EPL; ++k) m[k] |= __reduce_or_sync(0xffffffffu, w == (uint32_t)k ? bit : 0u);
             const uint32_t p31 = __shfl_sync(0xffffffffu, p, 31);
             if (p31 >= endp || wb2 + 32u >= r1) break;     // (the sentinel ends the walk too)
             wb2 += 32u;                                    // more than a window of rows starts in this chunk
@@ -250,24 +245,23 @@ __device__ __forceinline__ void warp_chunk_core(const SpmvArgs &a, const BlockCt
             p = r < r1 ? bc.ptr[r] : kPtrSentinel;
         }
     }
-    const uint32_t mw = (lane < 8) ? m0 : (lane < 16) ? m1 : (lane < 24) ? m2 : m3;
-    const uint32_t f = (mw >> ((lane & 7) * 4)) & 0xFu;
+    // the lane's EPL head flags: word (lane * EPL) / 32, bit offset (lane * EPL) % 32
+    uint32_t mw = m[0];
+#pragma unroll
+    for (int k = 1; k < EPL; ++k) mw = ((uint32_t)lane * EPL) / 32u == (uint32_t)k ? m[k] : mw;
+    const uint32_t f = (mw >> (((uint32_t)lane * EPL) & 31u)) & ((1u << EPL) - 1u);
 
-    // ---- products; segmented running sums inside the lane (t_k = sum of the lane's entries of the segment
-    // that entry k belongs to, up to and including k)
-    double t0 = cv[0] * x0;
-    if (lane == 0 && !(f & 1u)) t0 = ts.carry + t0;        // row that began in an earlier chunk
-    double t1 = cv[1] * x1;
-    if (!(f & 2u)) t1 += t0;
-    double t2 = cv[2] * x2;
-    if (!(f & 4u)) t2 += t1;
-    double t3 = cv[3] * x3;
-    if (!(f & 8u)) t3 += t2;
+    // ---- segmented running sums inside the lane (t_k = sum of the lane's entries of the segment that entry k
+    // belongs to, up to and including k)
+    if (lane == 0 && !(f & 1u)) t[0] = ts.carry + t[0];    // row that began in an earlier chunk
+#pragma unroll
+    for (int k = 1; k < EPL; ++k)
+        if (!(f & (1u << k))) t[k] += t[k - 1];
     // ---- ... and across lanes (Kogge-Stone; lane l takes lane l-d iff no head lies in lanes (l-d, l])
     const uint32_t hb = __ballot_sync(0xffffffffu, f != 0u);
     const uint32_t below = hb & (0xffffffffu >> (31 - lane));
     const int reach = lane - (below ? 31 - __clz(below) : 0);   // how far down this lane's open segment extends
-    double vs = t3;
+    double vs = t[EPL - 1];
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
         const double y = __shfl_up_sync(0xffffffffu, vs, d);
@@ -276,13 +270,12 @@ __device__ __forceinline__ void warp_chunk_core(const SpmvArgs &a, const BlockCt
     double cin = __shfl_up_sync(0xffffffffu, vs, 1);
     if (lane == 0) cin = 0.0;
     // entries that precede the lane's first head continue the segment of the lanes below
-    if (!(f & 1u)) t0 += cin;
-    if (!(f & 3u)) t1 += cin;
-    if (!(f & 7u)) t2 += cin;
-    if (!(f & 15u)) t3 += cin;
-    ts.carry = __shfl_sync(0xffffffffu, t3, 31);
-    *reinterpret_cast<double2 *>(su + 4 * lane) = make_double2(t0, t1);
-    *reinterpret_cast<double2 *>(su + 4 * lane + 2) = make_double2(t2, t3);
+#pragma unroll
+    for (int k = 0; k < EPL; ++k)
+        if (!(f & ((2u << k) - 1u))) t[k] += cin;
+    ts.carry = __shfl_sync(0xffffffffu, t[EPL - 1], 31);
+#pragma unroll
+    for (int k = 0; k < EPL; k += 2) *reinterpret_cast<double2 *>(su + EPL * lane + k) = make_double2(t[k], t[k + 1]);
     __syncwarp();
 
     // ---- rows that end in this chunk: lane j finishes row wb+j (the sentinel of absent rows never ends)
@@ -310,66 +303,51 @@ __device__ __forceinline__ void warp_chunk_core(const SpmvArgs &a, const BlockCt
     }
 }
 
-// Processes the chunk [base, base+128) held in `cur`; `nxt` receives the following chunk, whose loads stay in
-// flight while this one is reduced.  WIN: the gathers are reads of the warp's staged window.  STRIPED: the gathered
-// values arrive in striped order (entry 32 k + lane) and are transposed to the blocked order of the values (entries
-// 4 lane .. 4 lane + 3) through the warp's shared buffer.
-template <int FIN, bool WIN, bool STRIPED>
+// Processes the chunk [base, base + 32 EPL) held in `cur`; `nxt` receives the following chunk, whose loads stay in
+// flight while this one is reduced.  WIN: the gathers are reads of the warp's staged window.
+template <int FIN, bool WIN, int EPL>
 __device__ __forceinline__ void warp_chunk(const SpmvArgs &a, const BlockCtx &bc, Epilogue<FIN> &epi, double *su,
                                            const double *xw /* WIN: window - win_lo */, WarpTileState<FIN> &ts,
-                                           const ChunkRegs &cur, ChunkRegs &nxt, uint32_t base, uint32_t r1,
+                                           const ChunkRegs<EPL> &cur, ChunkRegs<EPL> &nxt, uint32_t base, uint32_t r1,
                                            uint32_t e0, uint32_t e1, int32_t safe, int lane,
                                            uint64_t pol_stream, uint64_t pol_keep)
 {
-    double x0, x1, x2, x3;
-    if (WIN) {
-        x0 = xw[cur.c[0]]; x1 = xw[cur.c[1]]; x2 = xw[cur.c[2]]; x3 = xw[cur.c[3]];
-    } else {
-        x0 = ldg_keep_f64(a.x + cur.c[0], pol_keep);
-        x1 = ldg_keep_f64(a.x + cur.c[1], pol_keep);
-        x2 = ldg_keep_f64(a.x + cur.c[2], pol_keep);
-        x3 = ldg_keep_f64(a.x + cur.c[3], pol_keep);
-    }
-    load_chunk<STRIPED>(a, base + kChunk, lane, e0, e1, safe, pol_stream, nxt);
-    if (STRIPED) {
-        // (su is free here: the previous chunk's row sums were consumed before its closing __syncwarp)
-        su[lane] = x0; su[32 + lane] = x1; su[64 + lane] = x2; su[96 + lane] = x3;
-        __syncwarp();
-        const double2 p = *reinterpret_cast<const double2 *>(su + 4 * lane);
-        const double2 q = *reinterpret_cast<const double2 *>(su + 4 * lane + 2);
-        x0 = p.x; x1 = p.y; x2 = q.x; x3 = q.y;
-        __syncwarp();                   // every lane has its values before the scan overwrites su
-    }
-    warp_chunk_core<FIN>(a, bc, epi, su, ts, cur.v, x0, x1, x2, x3, base, r1, e1, lane);
+    double t[EPL];
+#pragma unroll
+    for (int k = 0; k < EPL; ++k) t[k] = WIN ? xw[cur.c[k]] : ldg_keep_f64(a.x + cur.c[k], pol_keep);
+    load_chunk<EPL>(a, base + 32u * EPL, lane, e0, e1, safe, pol_stream, nxt);
+#pragma unroll
+    for (int k = 0; k < EPL; ++k) t[k] *= cur.v[k];
+    warp_chunk_core<FIN, EPL>(a, bc, epi, su, ts, t, base, r1, e1, lane);
 }
 
-template <int FIN, bool WIN, bool STRIPED>
+template <int FIN, bool WIN, int EPL>
 __device__ __forceinline__ void warp_tile_loop(const SpmvArgs &a, const BlockCtx &bc, Epilogue<FIN> &epi, double *su,
                                                const double *xw, uint32_t r0, uint32_t r1, uint32_t e0, uint32_t e1,
                                                int32_t safe, int lane, uint64_t pol_stream, uint64_t pol_keep)
 {
-    const uint32_t a0 = e0 & ~3u;
+    const uint32_t a0 = e0 & ~(uint32_t)(EPL - 1);
     WarpTileState<FIN> ts;
     ts.wb = r0;
     ts.woff = 0;
     ts.carry = 0.0;
     ts.win.load(a, bc, r0, r1, lane);
-    ChunkRegs ra, rb;
-    load_chunk<STRIPED>(a, a0, lane, e0, e1, safe, pol_stream, ra);
+    ChunkRegs<EPL> ra, rb;
+    load_chunk<EPL>(a, a0, lane, e0, e1, safe, pol_stream, ra);
     // two chunks per trip so that the register double buffer needs no copies; at least one chunk is processed
     // even for a piece without entries, so that its (empty) rows still get their epilogue
     for (uint32_t base = a0;;) {
-        warp_chunk<FIN, WIN, STRIPED>(a, bc, epi, su, xw, ts, ra, rb, base, r1, e0, e1, safe, lane, pol_stream, pol_keep);
-        base += kChunk;
+        warp_chunk<FIN, WIN, EPL>(a, bc, epi, su, xw, ts, ra, rb, base, r1, e0, e1, safe, lane, pol_stream, pol_keep);
+        base += 32u * EPL;
         if (base >= e1) break;
-        warp_chunk<FIN, WIN, STRIPED>(a, bc, epi, su, xw, ts, rb, ra, base, r1, e0, e1, safe, lane, pol_stream, pol_keep);
-        base += kChunk;
+        warp_chunk<FIN, WIN, EPL>(a, bc, epi, su, xw, ts, rb, ra, base, r1, e0, e1, safe, lane, pol_stream, pol_keep);
+        base += 32u * EPL;
         if (base >= e1) break;
     }
 }
 
 // One piece: stage the gather window if the piece has one, then stream its chunks.
-template <int FIN, bool STRIPED>
+template <int FIN, int EPL>
 __device__ __forceinline__ void warp_tile(const SpmvArgs &a, const BlockCtx &bc, Epilogue<FIN> &epi, double *su, double *wbuf,
                                           const TileDesc &d0, const TileDesc &d1, int lane,
                                           uint64_t pol_stream, uint64_t pol_keep)
@@ -379,22 +357,21 @@ __device__ __forceinline__ void warp_tile(const SpmvArgs &a, const BlockCtx &bc,
         const double *src = a.x + d0.win_lo;
         for (uint32_t i = (uint32_t)lane; i < d0.win_len; i += 32u) wbuf[i] = ldg_keep_f64(src + i, pol_keep);
         __syncwarp();
-        // (a staged window is conflict-bound, not line-bound: the blocked index layout with its single 128-bit load)
-        warp_tile_loop<FIN, true, false>(a, bc, epi, su, wbuf - d0.win_lo, d0.row, d1.row, d0.entry, d1.entry,
-                                         (int32_t)d0.win_lo, lane, pol_stream, pol_keep);
+        warp_tile_loop<FIN, true, EPL>(a, bc, epi, su, wbuf - d0.win_lo, d0.row, d1.row, d0.entry, d1.entry,
+                                       (int32_t)d0.win_lo, lane, pol_stream, pol_keep);
     } else {
-        warp_tile_loop<FIN, false, STRIPED>(a, bc, epi, su, nullptr, d0.row, d1.row, d0.entry, d1.entry, 0, lane, pol_stream, pol_keep);
+        warp_tile_loop<FIN, false, EPL>(a, bc, epi, su, nullptr, d0.row, d1.row, d0.entry, d1.entry, 0, lane, pol_stream, pol_keep);
     }
 }
 
-// MINB: resident CTAs per SM the kernel is compiled for (4: <= 64 registers, 32 warps per SM; 2: <= 128 registers,
-// 16 warps per SM with room for wide gather windows).  STRIPED: lane-consecutive gathers (see load_chunk).
-template <int FIN, int MINB, bool STRIPED>
-__global__ void __launch_bounds__(kWThreads, MINB)
+// EPL: stored entries per lane and chunk (see ChunkRegs); EPL = 4 runs 4 CTAs per SM (<= 64 registers), EPL = 8 runs 2
+// (<= 128 registers, room for wide gather windows).
+template <int FIN, int EPL>
+__global__ void __launch_bounds__(kWThreads, EPL == 4 ? 4 : 2)
 spmv_kernel(SpmvArgs a)
 {
     constexpr bool kFused = (FIN == FIN_APROD || FIN == FIN_ATPROD || FIN == FIN_INIT_ATPROD);
-    extern __shared__ __align__(16) double s_dyn[];          // per warp: su[128] | gather window[win_cap]
+    extern __shared__ __align__(16) double s_dyn[];          // per warp: su[32 EPL] | gather window[win_cap]
     __shared__ double s_red[kWWarps];
     __shared__ double s_exc[2 * kWThreads];
 
@@ -437,8 +414,8 @@ spmv_kernel(SpmvArgs a)
         const uint64_t pol_keep = l2_policy_evict_last();
         const int lane = tid & 31, wib = tid >> 5;
         const int nw = (int)gridDim.x * kWWarps;
-        double *su = s_dyn + (size_t)wib * (kChunk + (size_t)a.win_cap);
-        double *wbuf = su + kChunk;
+        double *su = s_dyn + (size_t)wib * (32u * EPL + (size_t)a.win_cap);
+        double *wbuf = su + 32 * EPL;
         const uint32_t *__restrict__ order = a.order;
         const int nslots = order ? a.nslots : a.ntiles;
         for (int b = 0; b < a.nblocks; ++b) {
@@ -471,7 +448,7 @@ spmv_kernel(SpmvArgs a)
                 if (t == kNoTile) break;                        // this warp's list is exhausted
                 const TileDesc d0 = tiles[t], d1 = tiles[t + 1];
                 if (d0.row == d1.row) continue;                 // no row starts in this tile (inside a long row)
-                warp_tile<FIN, STRIPED>(a, bc, epi, su, wbuf, d0, d1, lane, pol_stream, pol_keep);
+                warp_tile<FIN, EPL>(a, bc, epi, su, wbuf, d0, d1, lane, pol_stream, pol_keep);
             }
             if (a.guard && b + 1 < a.nblocks) {
                 __syncthreads();                                // every warp of this CTA has finished block b

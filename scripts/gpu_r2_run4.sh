@@ -3,12 +3,12 @@
 mkdir -p gpurun_out
 echo "== pytest"; timeout 900 python -m pytest tests -m gpu -q -p no:cacheprovider --timeout=300 > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"
 tail -12 gpurun_out/pytest_gpu.log | cut -c1-300
-echo "== spmv A/B"; timeout 600 python scripts/spmv_bench.py --modes default,perblock,blockedgather --workloads C3:1,C5:4,C2:1,C4:1 --reps 10 > gpurun_out/spmv_bench.jsonl 2> gpurun_out/spmv_bench.err; echo "spmv rc=$?"
+echo "== spmv A/B"; timeout 600 python scripts/spmv_bench.py --modes default,epl4,epl8,epl8nowindow,epl8win640,perblock --workloads C3:1,C5:4,C2:1,C4:2 --reps 10 > gpurun_out/spmv_bench.jsonl 2> gpurun_out/spmv_bench.err; echo "spmv rc=$?"
 python - <<'P'
 import json
 for l in open("gpurun_out/spmv_bench.jsonl"):
     d = json.loads(l)
-    print({k: d.get(k) for k in ("workload", "mode", "blocks", "window", "striped", "ctas_per_sm", "mode1_us", "mode1_frac", "mode2_us", "mode2_frac", "alt_frac", "us_per_iter", "loop_frac", "slope_us_graph", "itn", "x_rel_vs_first")})
+    print({k: d.get(k) for k in ("workload", "mode", "blocks", "window", "epl", "ctas_per_sm", "mode1_us", "mode1_frac", "mode2_us", "mode2_frac", "alt_frac", "us_per_iter", "loop_frac", "slope_us_graph", "itn", "x_rel_vs_first")})
 P
 tail -5 gpurun_out/spmv_bench.err
 echo "== bench"; LSQR_B200_VERBOSE=1 timeout 1200 python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; echo "bench rc=$?"
@@ -31,4 +31,5 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:spmv
 echo "== ncu full: C5/4 kernels"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:spmv_kernel -s 30 -c 4 -f -o gpurun_out/prof_c5q \
    python bench.py --workload C5 --scale 4 --steps 1 --warmup 3 --secondary none --no-cpu-baseline --no-graph --no-oracle-check > gpurun_out/ncu_c5q.log 2>&1; tail -2 gpurun_out/ncu_c5q.log | cut -c1-200
+echo "== trace C5"; LSQR_B200_TRACE=1 timeout 300 python bench.py --steps 1 --warmup 3 --secondary none --no-cpu-baseline --no-oracle-check 2> gpurun_out/trace_c5.txt > /dev/null; grep "trace\]" gpurun_out/trace_c5.txt | tail -30
 ls -la gpurun_out | tail -8

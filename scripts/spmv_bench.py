@@ -31,9 +31,11 @@ MODES = {
     "guard2": {"LSQR_B200_DRIFT_GUARD": "2"},
     "nowindow": {"LSQR_B200_WINDOW": "0"},
     "nooverlap": {"LSQR_B200_OVERLAP_UPDATE": "0"},
-    "widewindow": {"LSQR_B200_WINDOW_WIDE": "1"},
-    "blockedgather": {"LSQR_B200_STRIPED": "0", "LSQR_B200_WINDOW": "0"},
-    "nostriped": {"LSQR_B200_STRIPED": "0"},
+    "epl4": {"LSQR_B200_EPL": "4"},
+    "epl8": {"LSQR_B200_EPL": "8"},
+    "epl8nowindow": {"LSQR_B200_EPL": "8", "LSQR_B200_WINDOW": "0"},
+    "epl8win640": {"LSQR_B200_EPL": "8", "LSQR_B200_WINDOW_MAX": "640"},
+    "epl4nowindow": {"LSQR_B200_EPL": "4", "LSQR_B200_WINDOW": "0"},
 }
 
 
@@ -74,7 +76,7 @@ def main():
                    "blocks": [pa["nblocks"], pat["nblocks"]], "window": [pa["window_doubles"], pat["window_doubles"]],
                    "windowed": [round(pa["windowed_fraction"], 3), round(pat["windowed_fraction"], 3)],
                    "ctas_per_sm": [pa["ctas_per_sm"], pat["ctas_per_sm"]], "span_max": [pa["span_max"], pat["span_max"]],
-                   "striped": [pa["striped_gathers"], pat["striped_gathers"]],
+                   "epl": [pa["entries_per_lane"], pat["entries_per_lane"]],
                    "lines": [round(pa["lines_per_gather"], 1), round(pat["lines_per_gather"], 1)]}
             for mode in (1, 2):
                 x = xt.clone()

@@ -29,9 +29,9 @@ KERNEL_MODES = {
     "noguard": {"LSQR_B200_DRIFT_GUARD": "0"},
     "nowindow": {"LSQR_B200_WINDOW": "0"},                 # gathers stay global (A/B of the staged window)
     "smallwindow": {"LSQR_B200_WINDOW_CAP": "208"},        # a window too narrow for many pieces: staged and global pieces mixed
-    "widewindow": {"LSQR_B200_WINDOW_WIDE": "1"},          # 2-CTA-per-SM flavour with wide windows (opt-in)
-    "blockedgather": {"LSQR_B200_STRIPED": "0", "LSQR_B200_WINDOW": "0"},   # neither window nor lane-consecutive gathers
-    "stripedgather": {"LSQR_B200_STRIPED": "1", "LSQR_B200_WINDOW": "0"},   # lane-consecutive gathers forced on
+    "epl4": {"LSQR_B200_EPL": "4"},                        # 4 stored entries per lane and chunk, 4 CTAs per SM (forced)
+    "epl8": {"LSQR_B200_EPL": "8"},                        # 8 stored entries per lane and chunk, 2 CTAs per SM (forced)
+    "epl8nowindow": {"LSQR_B200_EPL": "8", "LSQR_B200_WINDOW": "0"},
 }
 
 
@@ -241,7 +241,7 @@ def test_solve_parity_scaled_configs(lb, name, scale, shuffle, tol):
 
 
 @pytest.mark.parametrize("name,scale", [("C2", 10), ("C3", 100), ("C4", 100)])
-@pytest.mark.parametrize("mode", ["perblock", "nowindow", "smallwindow", "widewindow", "blockedgather", "stripedgather"])
+@pytest.mark.parametrize("mode", ["perblock", "nowindow", "smallwindow", "epl4", "epl8", "epl8nowindow"])
 def test_solve_parity_kernel_modes(lb, name, scale, mode, monkeypatch):
     """The A/B switches of the SpMV kernel against the oracle and against the default mode.  Launching block by block
     adds the same terms in the same order as the single launch (the plan fixes the order), so that solution must be
@@ -264,11 +264,11 @@ def test_solve_parity_kernel_modes(lb, name, scale, mode, monkeypatch):
 
 
 def test_banded_matrix_gathers_from_the_shared_window(lb, monkeypatch):
-    """C3 family (north_star (2)): every piece of A touches a narrow span of v, so the plan stages it in shared memory;
-    the pieces of A' span ~1300 entries of u -- too wide for the 4-CTA flavour -- but 32 consecutive stored entries of
-    A' share a few 128-byte lines, so its gathers are issued lane-consecutively.  Products agree with the oracle and,
-    bit for bit, with the plain global-gather mode (the plan fixes the order of the additions, the mode only changes
-    where a gather is served from)."""
+    """C3 family (north_star (2)): every piece of A and of A' touches a narrow span of the gathered vector, so the plan
+    stages it in shared memory and picks the 8-entries-per-lane flavour (such matrices are bound by instruction
+    issue, not by the gather path).  Products agree with the oracle in every mode, and bit for bit between modes that
+    share the tile cut (the plan fixes the order of the additions; the mode only changes where a gather is served
+    from)."""
     from lsqr_b200 import synth
     cfg = synth.scaled("C3", 50)                       # 200 000 x 40 000, 1e7 entries
     m, n = cfg["m"], cfg["n"]
@@ -276,20 +276,19 @@ def test_banded_matrix_gathers_from_the_shared_window(lb, monkeypatch):
     rng = np.random.default_rng(21)
     x, y = rng.standard_normal(n), rng.standard_normal(m)
     outs = {}
-    for mode in ("default", "blockedgather", "widewindow"):
+    for mode in ("default", "epl8nowindow", "epl4", "nowindow"):
         set_kernel_mode(monkeypatch, mode)
         s = lb.LsqrSolverEz().initialize(m, n, a, irow, icol)
         pa, pat = s.plan(False), s.plan(True)
         if mode == "default":
-            assert pa["window_doubles"] > 0 and pa["windowed_fraction"] >= 0.99 and pa["ctas_per_sm"] == 4, pa
-            assert pa["span_max"] <= pa["window_doubles"]
-            assert pat["window_doubles"] == 0 and pat["striped_gathers"] == 1 and pat["lines_per_gather"] <= 16, pat
-        elif mode == "blockedgather":
-            assert pa["window_doubles"] == 0 and pat["window_doubles"] == 0
-            assert pa["striped_gathers"] == 0 and pat["striped_gathers"] == 0
-        else:
-            assert pat["window_doubles"] > 0 and pat["windowed_fraction"] >= 0.99 and pat["ctas_per_sm"] == 2, pat
-            assert pat["span_max"] <= pat["window_doubles"]
+            for p in (pa, pat):
+                assert p["entries_per_lane"] == 8 and p["ctas_per_sm"] == 2 and p["lines_per_gather"] <= 16, p
+                assert p["window_doubles"] > 0 and p["windowed_fraction"] >= 0.99 and p["span_max"] <= p["window_doubles"], p
+        elif mode == "epl8nowindow":
+            assert pa["window_doubles"] == 0 and pat["window_doubles"] == 0 and pa["entries_per_lane"] == 8
+        elif mode == "epl4":
+            assert pa["entries_per_lane"] == 4 and pa["ctas_per_sm"] == 4 and pa["window_doubles"] > 0     # narrow window of A
+            assert pat["window_doubles"] == 0                                                            # too wide for 4 CTAs per SM
         y1, x2 = y.copy(), x.copy()
         s.aprod(1, m, n, x, y1)
         s.aprod(2, m, n, x2, y)
@@ -300,17 +299,17 @@ def test_banded_matrix_gathers_from_the_shared_window(lb, monkeypatch):
     ref.aprod(1, x.copy(), yr); ref.aprod(2, xr, y.copy())
     for mode in outs:
         assert relerr(outs[mode][0], yr) <= 1e-14 and relerr(outs[mode][1], xr) <= 1e-14, mode
-    # same persistent grid => same tile cut => the same additions in the same order
-    assert np.array_equal(outs["default"][0], outs["blockedgather"][0])
-    assert np.array_equal(outs["default"][1], outs["blockedgather"][1])
-    # uniformly random columns: no window (the span of a piece is the whole vector), no locality
+    # same flavour => same persistent grid => same tile cut => the same additions in the same order
+    assert np.array_equal(outs["default"][0], outs["epl8nowindow"][0])
+    assert np.array_equal(outs["default"][1], outs["epl8nowindow"][1])
+    # uniformly random columns: no window (the span of a piece is the whole vector), no locality, 4 entries per lane
     set_kernel_mode(monkeypatch, "default")
     cfg = synth.scaled("C2", 10)
     irow, icol, a = synth.coo_block(cfg["kind"], cfg["seed"], cfg["m"], cfg["n"], cfg["k"])
     s = lb.LsqrSolverEz().initialize(cfg["m"], cfg["n"], a, irow, icol)
     for tr in (False, True):
         p = s.plan(tr)
-        assert p["window_doubles"] == 0 and p["striped_gathers"] == 0 and p["lines_per_gather"] >= 28, p
+        assert p["window_doubles"] == 0 and p["entries_per_lane"] == 4 and p["lines_per_gather"] >= 28, p
 
 
 def test_balanced_tile_schedule_power_law(lb, monkeypatch):
