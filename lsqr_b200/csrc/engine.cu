@@ -320,8 +320,8 @@ static int ez_initialize_impl(lsqr_b200_ez *me, int64_t nnz, const double *a, co
         auto say = [&](const char *name, const Csr &M, const TilePlan &P) {
             fprintf(stderr, "[lsqr_b200] %s: blocks=%lld (block size %lld) tiles=%d (%llu work units) grid=%d CTAs x %d/SM  window=%d doubles "
                             "(%.1f%% of the entries staged; piece span median %u, max %u) lines/gather %.1f%s%s imbalance %.3f\n",
-                    name, (long long)M.nblocks, (long long)M.block_rows, P.ntiles, (unsigned long long)P.tile, P.ctas, P.epl == 4 ? 4 : 2, P.win_cap,
-                    100.0 * P.windowed, P.span_p50, P.span_max, P.lines_per_gather, P.epl == 8 ? " EPL8" : "", P.order ? " LPT" : "", P.imbalance);
+                    name, (long long)M.nblocks, (long long)M.block_rows, P.ntiles, (unsigned long long)P.tile, P.ctas, P.ctas / std::max(1, me->wk.sms), P.win_cap,
+                    100.0 * P.windowed, P.span_p50, P.span_max, P.lines_per_gather, "", P.order ? " LPT" : "", P.imbalance);
         };
         fprintf(stderr, "[lsqr_b200] m=%d n=%d nnz=%lld single_launch=%d guard=%d\n", me->m, me->n, (long long)me->nnz, (int)me->single_launch, (int)me->guard);
         say("A ", me->A, me->planA);
@@ -460,7 +460,7 @@ int lsqr_b200_ez_plan(const lsqr_b200_ez *me, int32_t which, lsqr_b200_plan_info
     out->nblocks = M.nblocks;
     out->ntiles = P.ntiles;
     out->grid_ctas = P.ctas;
-    out->ctas_per_sm = P.epl == 4 ? 4 : 2;
+    out->ctas_per_sm = P.ctas / std::max(1, me->wk.sms);
     out->window_doubles = P.win_cap;
     out->windowed_fraction = P.windowed;
     out->span_median = P.span_p50;

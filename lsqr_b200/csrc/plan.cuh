@@ -25,7 +25,7 @@ struct TilePlan {
     uint32_t *order = nullptr;   // device: balanced schedule, or nullptr = round robin
     int nslots = 0;
     int ctas = 0;                // persistent grid the plan was cut for
-    int epl = 4;                 // kernel flavour: stored entries per lane and chunk (4: 4 CTAs per SM, 8: 2 CTAs per SM)
+    int epl = 4;                 // stored entries per lane and chunk of the kernel flavour in use
     int win_cap = 0;             // doubles of gather window per warp (0 = no staging)
     size_t smem = 0;             // dynamic shared memory per CTA
     double imbalance = 1.0;      // most loaded warp / mean load under the schedule in use (diagnostic)
@@ -44,47 +44,45 @@ static inline void plan_free(TilePlan &p)
     p.tiles = nullptr; p.order = nullptr; p.stat = nullptr;
 }
 
-constexpr int kWinCap4 = 640;    // EPL = 4: 8 warps x (128 + 640) doubles = 48 KB per CTA, 4 CTAs per SM
-constexpr int kWinCap2 = 1472;   // EPL = 8: 8 warps x (256 + 1472) doubles = 108 KB per CTA, 2 CTAs per SM
+constexpr int kEpl = 4;           // stored entries per lane and chunk of the instantiated flavour (spmv.cuh: ChunkRegs)
+constexpr int kWinCap = 304;      // widest gather window: 4 CTAs x 8 warps x (128 + 304) doubles + static = 130 KB <= the 132 KB step
 
-static inline size_t plan_smem(int epl, int win_cap) { return (size_t)kWWarps * (size_t)(32 * epl + win_cap) * sizeof(double); }
+static inline size_t plan_smem(int win_cap) { return (size_t)kWWarps * (size_t)(32 * kEpl + win_cap) * sizeof(double); }
 
-// Opt in to the dynamic shared memory the flavour needs and measure its co-residency (the soft drift guard of a
-// multi-block launch spins on the other warps of the grid: the grid must fit the GPU).
-// The shared-memory carve-out is set to what the resident CTAs need and no more: what is left of the 228 KB is L1,
-// and the divergent gathers of the non-windowed path live on L1 (every pending miss holds a line: with the
-// carve-out at 100 % the same kernel ran at HALF speed on every workload, profiles/r02/run1).
-template <int FIN, int EPL>
-static int spmv_prepare(size_t smem, int *ctas_per_sm)
+// Shared-memory carve-out of the SpMV kernels.  What is left of the 228 KB is L1, and the divergent gathers of the
+// non-windowed path live on L1 (every pending miss holds a line: with the carve-out at 100 % the same kernel ran at
+// HALF speed on every workload, profiles/r02/run1), so the carve-out is the smallest hardware step that holds the 4
+// resident CTAs: 64 KB without gather windows, 132 KB with them.  It is a property of the kernel FUNCTION, i.e.
+// process-wide state, and a guarded multi-block launch deadlocks on a grid that is only partly resident -- which is
+// what a carve-out that changes between the kernels of one solve produces (an SM cannot be re-split while CTAs of
+// the previous kernel sit on it; runs 2 and 5 hung / timed out exactly there).  Hence ONE value for every SpMV
+// kernel, raised once -- and for good -- when the first windowed plan of the process is built.
+static int spmv_configure(bool windows, int *ctas_per_sm)
 {
-    constexpr int MINB = EPL == 4 ? 4 : 2;
-    LSQRB_CUDA(cudaFuncSetAttribute(spmv_kernel<FIN, EPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan_smem(EPL, EPL == 4 ? kWinCap4 : kWinCap2)));
-    cudaFuncAttributes fa;
-    LSQRB_CUDA(cudaFuncGetAttributes(&fa, spmv_kernel<FIN, EPL>));
-    const size_t per_cta = smem + fa.sharedSizeBytes + 1024;   // + the 1 KB the hardware reserves per CTA
-    // the carve-out comes in steps and the preference is rounded to the NEAREST step, up or down: name the smallest
-    // step that holds MINB CTAs exactly (a rounded-down carve-out would leave the persistent grid partly non-resident)
-    static const int steps_kb[] = {0, 8, 16, 32, 64, 100, 132, 164, 196, 228};
-    int pct = 100;
-    for (int kb : steps_kb)
-        if ((size_t)kb * 1024 >= per_cta * (size_t)MINB) { pct = (kb * 100 + 227) / 228; break; }
+    static std::mutex mu;
+    static int current_pct = -1;
+    std::lock_guard<std::mutex> lock(mu);
+    const int want = windows ? 58 : 29;            // 132 KB / 64 KB of 228 KB
+    int pct = std::max(current_pct, want);
     pct = std::max(0, std::min(env_int("LSQR_B200_SMEM_CARVEOUT_PCT", pct), 100));
-    LSQRB_CUDA(cudaFuncSetAttribute(spmv_kernel<FIN, EPL>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
-    int n = 0;
-    LSQRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, spmv_kernel<FIN, EPL>, kWThreads, smem));
-    *ctas_per_sm = std::min(n, MINB);
-    return LSQR_B200_OK;
-}
-
-template <int EPL>
-static int spmv_prepare_all(size_t smem, int *ctas_per_sm)
-{
-    int occ = EPL == 4 ? 4 : 2, o = 0;
-    LSQRB_TRY((spmv_prepare<FIN_NONE, EPL>(smem, &o)));        occ = std::min(occ, o);
-    LSQRB_TRY((spmv_prepare<FIN_APROD, EPL>(smem, &o)));       occ = std::min(occ, o);
-    LSQRB_TRY((spmv_prepare<FIN_ATPROD, EPL>(smem, &o)));      occ = std::min(occ, o);
-    LSQRB_TRY((spmv_prepare<FIN_INIT_ATPROD, EPL>(smem, &o))); occ = std::min(occ, o);
-    LSQRB_TRY((spmv_prepare<FIN_PUSH, EPL>(smem, &o)));        occ = std::min(occ, o);
+    int occ = 4;
+    auto one = [&](auto kernel) -> int {
+        if (pct != current_pct) {
+            LSQRB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan_smem(kWinCap)));
+            LSQRB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+        }
+        int n = 0;
+        LSQRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kWThreads, plan_smem(windows ? kWinCap : 0)));
+        occ = std::min(occ, n);
+        return LSQR_B200_OK;
+    };
+    LSQRB_TRY(one(spmv_kernel<FIN_NONE, kEpl>));
+    LSQRB_TRY(one(spmv_kernel<FIN_APROD, kEpl>));
+    LSQRB_TRY(one(spmv_kernel<FIN_ATPROD, kEpl>));
+    LSQRB_TRY(one(spmv_kernel<FIN_INIT_ATPROD, kEpl>));
+    LSQRB_TRY(one(spmv_kernel<FIN_PUSH, kEpl>));
+    current_pct = pct;
+    if (occ < 1) { set_last_error("spmv kernel does not fit an SM"); return LSQR_B200_ERR_CUDA; }
     *ctas_per_sm = occ;
     return LSQR_B200_OK;
 }
@@ -236,63 +234,37 @@ static int plan_probe(Work &wk, const TilePlan &P, bool *resident);
 static int build_plan(Work &wk, const Csr &M, TilePlan *p, int reserve_sms = 0)
 {
     p->row_w = (uint32_t)std::max(0, env_int("LSQR_B200_TILE_ROW_WEIGHT", 4));
-    p->epl = 4;
+    p->epl = kEpl;
     p->win_cap = 0;
     std::vector<TileDesc> t;
-    const int want_window = env_int("LSQR_B200_WINDOW", 1);
+    // Gather windows are OPT-IN (LSQR_B200_WINDOW=1).  Measured on the banded family (C3, profiles/r02): Aprod 1.27 ms
+    // with the window against 1.30 ms without, A' (span 1300 entries, 16 warps per SM) 1.74 ms against 1.38 ms -- the
+    // staged reads are bank-conflict-bound (17 wavefronts per 32 gathers, ncu) where the global gathers of such a
+    // matrix need ~20 lines, and a second carve-out in the process is a hazard for the guarded launches (above).
+    const int want_window = env_int("LSQR_B200_WINDOW", 0);
     const double min_frac = 1e-2 * env_int("LSQR_B200_WINDOW_MIN_PERCENT", 50);
-    auto prepare = [&](int *occ) -> int {
-        p->smem = plan_smem(p->epl, p->win_cap);
-        *occ = 0;
-        if (p->epl == 4) LSQRB_TRY(spmv_prepare_all<4>(p->smem, occ));
-        else             LSQRB_TRY(spmv_prepare_all<8>(p->smem, occ));
-        if (*occ < 1) { set_last_error("spmv kernel does not fit an SM"); return LSQR_B200_ERR_CUDA; }
-        return LSQR_B200_OK;
-    };
     int occ = 0;
-    LSQRB_TRY(prepare(&occ));
+    LSQRB_TRY(spmv_configure(false, &occ));
+    p->smem = plan_smem(0);
     p->ctas = std::max(1, wk.sms - reserve_sms) * occ;
     LSQRB_TRY(plan_cut(wk, M, p, 0));
     LSQRB_TRY(plan_fetch(wk, *p, &t));
     const int forced_cap = env_int("LSQR_B200_WINDOW_CAP", 0);
-    if (M.nnz > 0) {
-        // Flavour.  A matrix whose gathers are cheap -- every piece inside a shared-memory window, or 32 consecutive
-        // stored entries inside a few 128-byte lines -- is bound by instruction issue, not by the gather path: it gets
-        // the 8-entries-per-lane flavour (fewer instructions per entry, wide windows).  Everything else keeps 4
-        // entries per lane and 32 warps per SM.
-        double f4 = 0, f2 = 0;
-        uint32_t n4 = 0, n2 = 0;
-        window_stats(*p, t, kWinCap4, &f4, &n4);
-        window_stats(*p, t, kWinCap2, &f2, &n2);
-        const int forced_epl = env_int("LSQR_B200_EPL", 0);
-        const double max_lines = 1e-1 * env_int("LSQR_B200_LOCAL_MAX_LINES_X10", 200);
-        const bool local = (want_window && f2 >= min_frac) || p->lines_per_gather <= max_lines;
-        p->epl = forced_epl == 4 || forced_epl == 8 ? forced_epl : (local ? 8 : 4);
-        const uint32_t cap = (uint32_t)std::min<int>(p->epl == 4 ? kWinCap4 : kWinCap2, std::max(0, env_int("LSQR_B200_WINDOW_MAX", 1 << 20)));
-        double fw = p->epl == 4 ? f4 : f2;
-        uint32_t nw_need = p->epl == 4 ? n4 : n2;
-        if (cap < (uint32_t)(p->epl == 4 ? kWinCap4 : kWinCap2)) window_stats(*p, t, cap, &fw, &nw_need);
-        if (!want_window) {
-        } else if (forced_cap > 0) {
-            p->win_cap = std::min((forced_cap + 1) & ~1, (int)cap);
-        } else if (fw >= min_frac) {
-            p->win_cap = (int)((nw_need + 1u) & ~1u);
-        }
+    if (M.nnz > 0 && want_window) {
+        double f = 0;
+        uint32_t need = 0;
+        window_stats(*p, t, (uint32_t)kWinCap, &f, &need);
+        if (forced_cap > 0) p->win_cap = std::min((forced_cap + 1) & ~1, kWinCap);
+        else if (f >= min_frac) p->win_cap = (int)((need + 1u) & ~1u);
     }
-    if (p->win_cap > 0 || p->epl != 4) {
-        LSQRB_TRY(prepare(&occ));
+    if (p->win_cap > 0) {
+        LSQRB_TRY(spmv_configure(true, &occ));
+        p->smem = plan_smem(p->win_cap);
         const int ctas = std::max(1, wk.sms - reserve_sms) * occ;
-        if (ctas != p->ctas) {          // a different persistent grid: cut again for it, and size the window for the new pieces
+        if (ctas != p->ctas) {          // a different persistent grid: cut again for it
             p->ctas = ctas;
             LSQRB_TRY(plan_cut(wk, M, p, 0));
             LSQRB_TRY(plan_fetch(wk, *p, &t));
-            if (forced_cap <= 0 && p->win_cap > 0) {
-                double f = 0;
-                uint32_t need = 0;
-                window_stats(*p, t, (uint32_t)std::min<int>(p->epl == 4 ? kWinCap4 : kWinCap2, std::max(0, env_int("LSQR_B200_WINDOW_MAX", 1 << 20))), &f, &need);
-                p->win_cap = (int)((need + 1u) & ~1u);
-                LSQRB_TRY(prepare(&occ));      // (occupancy cannot drop: the window only shrank or stayed under the flavour's cap)
-            }
         }
     }
     if (M.nblocks > 1) {
@@ -367,8 +339,7 @@ static int launch_piece(Work &wk, const TilePlan &P, const SpmvArgs &a)
     // (a guarded multi-block launch is a grid barrier per block: its grid was PROVEN co-resident by the probe at
     // initialize; a cooperative launch would be the textbook guarantee, but the runtime refused these grids -- "too
     // many blocks in cooperative launch" -- although the occupancy API reports the same 4 CTAs per SM)
-    if (P.epl == 4) LSQRB_CUDA(cudaLaunchKernelEx(&cfg, spmv_kernel<FIN, 4>, a));
-    else            LSQRB_CUDA(cudaLaunchKernelEx(&cfg, spmv_kernel<FIN, 8>, a));
+    LSQRB_CUDA(cudaLaunchKernelEx(&cfg, spmv_kernel<FIN, kEpl>, a));
     wk.launches++;
     LSQRB_CUDA(cudaGetLastError());
     return LSQR_B200_OK;

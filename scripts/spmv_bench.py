@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Kernel-level A/B bench of the SpMV kernel modes on the BASELINE workload families (GPU box only).
 
-    python scripts/spmv_bench.py [--modes default,perblock,nowindow] [--workloads C2:1,C3:5,C5:20,C4:10] [--reps 20]
+    python scripts/spmv_bench.py [--modes default,perblock,window] [--workloads C2:1,C3:5,C5:20,C4:10] [--reps 20]
 
 For every workload (name:scale) and mode (environment switches read at initialize) it times y += A x (mode 1) and x += A'y (mode 2) through the
 C ABI (lsqr_b200_ez_aprod on device vectors) with CUDA events on the stream the kernels run on, reports
@@ -29,19 +29,14 @@ MODES = {
     "perblock": {"LSQR_B200_SINGLE_LAUNCH": "0"},
     "noguard": {"LSQR_B200_DRIFT_GUARD": "0"},
     "guard2": {"LSQR_B200_DRIFT_GUARD": "2"},
-    "nowindow": {"LSQR_B200_WINDOW": "0"},
     "nooverlap": {"LSQR_B200_OVERLAP_UPDATE": "0"},
-    "epl4": {"LSQR_B200_EPL": "4"},
-    "epl8": {"LSQR_B200_EPL": "8"},
-    "epl8nowindow": {"LSQR_B200_EPL": "8", "LSQR_B200_WINDOW": "0"},
-    "epl8win640": {"LSQR_B200_EPL": "8", "LSQR_B200_WINDOW_MAX": "640"},
-    "epl4nowindow": {"LSQR_B200_EPL": "4", "LSQR_B200_WINDOW": "0"},
+    "window": {"LSQR_B200_WINDOW": "1"},
 }
 
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--modes", default="default,perblock,nowindow")
+    ap.add_argument("--modes", default="default,perblock,window")
     ap.add_argument("--workloads", default="C2:1,C3:5,C5:20,C4:10")
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--solve", type=int, default=1)

@@ -22,16 +22,14 @@ def lb():
 
 
 # Kernel modes (environment switches read at initialize): the default is one persistent launch per product that walks
-# every block of a blocked matrix, with the shared-memory gather window where the matrix is local.
+# every block of a blocked matrix, block by block behind a grid-wide guard, gathers straight from global memory.
 KERNEL_MODES = {
     "default": {},
     "perblock": {"LSQR_B200_SINGLE_LAUNCH": "0"},          # one launch per block (A/B of the single launch)
     "noguard": {"LSQR_B200_DRIFT_GUARD": "0"},
-    "nowindow": {"LSQR_B200_WINDOW": "0"},                 # gathers stay global (A/B of the staged window)
-    "smallwindow": {"LSQR_B200_WINDOW_CAP": "208"},        # a window too narrow for many pieces: staged and global pieces mixed
-    "epl4": {"LSQR_B200_EPL": "4"},                        # 4 stored entries per lane and chunk, 4 CTAs per SM (forced)
-    "epl8": {"LSQR_B200_EPL": "8"},                        # 8 stored entries per lane and chunk, 2 CTAs per SM (forced)
-    "epl8nowindow": {"LSQR_B200_EPL": "8", "LSQR_B200_WINDOW": "0"},
+    "guard2": {"LSQR_B200_DRIFT_GUARD": "2"},
+    "window": {"LSQR_B200_WINDOW": "1"},                   # shared-memory gather window where the pieces are narrow (opt-in)
+    "smallwindow": {"LSQR_B200_WINDOW": "1", "LSQR_B200_WINDOW_CAP": "208"},   # staged and global pieces mixed
 }
 
 
@@ -241,12 +239,11 @@ def test_solve_parity_scaled_configs(lb, name, scale, shuffle, tol):
 
 
 @pytest.mark.parametrize("name,scale", [("C2", 10), ("C3", 100), ("C4", 100)])
-@pytest.mark.parametrize("mode", ["perblock", "nowindow", "smallwindow", "epl4", "epl8", "epl8nowindow"])
+@pytest.mark.parametrize("mode", ["perblock", "noguard", "guard2", "window", "smallwindow"])
 def test_solve_parity_kernel_modes(lb, name, scale, mode, monkeypatch):
-    """The A/B switches of the SpMV kernel against the oracle and against the default mode.  Launching block by block
-    adds the same terms in the same order as the single launch (the plan fixes the order), so that solution must be
-    BIT-identical to the default mode's; a different window can change the kernel flavour and with it the tile cut,
-    i.e. the rounding."""
+    """The A/B switches of the SpMV kernel against the oracle and against the default mode.  Every mode adds the same
+    terms in the same order (the plan fixes the order; the mode only changes how the blocks are launched and where a
+    gather is served from), so the solutions must be BIT-identical to the default mode's."""
     from lsqr_b200 import synth
     cfg = synth.scaled(name, scale)
     monkeypatch.setenv("LSQR_B200_VBLOCK_COLS", str(max(64, cfg["n"] // 3 + 1)))     # 3 column blocks of A
@@ -256,19 +253,17 @@ def test_solve_parity_kernel_modes(lb, name, scale, mode, monkeypatch):
     _assert_parity(data, r1, ref)
     set_kernel_mode(monkeypatch, "default")
     _, r3, _ = _solve_both(lb, cfg, 1e-10, 1e-10, 1e8, 4000)
-    assert r1.istop == r3.istop and abs(r1.itn - r3.itn) <= 1
-    if mode == "perblock":
-        assert r1.itn == r3.itn and np.array_equal(np.asarray(r1.x), np.asarray(r3.x))
-    else:
-        assert relerr(r1.x, r3.x) <= RTOL
+    assert r1.istop == r3.istop and r1.itn == r3.itn
+    assert np.array_equal(np.asarray(r1.x), np.asarray(r3.x))
 
 
 def test_banded_matrix_gathers_from_the_shared_window(lb, monkeypatch):
-    """C3 family (north_star (2)): every piece of A and of A' touches a narrow span of the gathered vector, so the plan
-    stages it in shared memory and picks the 8-entries-per-lane flavour (such matrices are bound by instruction
-    issue, not by the gather path).  Products agree with the oracle in every mode, and bit for bit between modes that
-    share the tile cut (the plan fixes the order of the additions; the mode only changes where a gather is served
-    from)."""
+    """C3 family, north_star (2) "shared-memory staging of the dense x-vector": with LSQR_B200_WINDOW=1 every piece of A
+    touches a narrow span of v (~230 entries) and gathers from a staged shared-memory window; the pieces of A' span
+    ~1300 entries of u, too wide for 4 resident CTAs per SM, and keep gathering from global memory.  Products agree
+    with the oracle and, bit for bit, with the default (no window) mode: the plan fixes the order of the additions,
+    the window only changes where a gather is served from.  (The window is opt-in because it measured within 3 % of
+    the global gathers on this family -- DESIGN.md 4.2.)"""
     from lsqr_b200 import synth
     cfg = synth.scaled("C3", 50)                       # 200 000 x 40 000, 1e7 entries
     m, n = cfg["m"], cfg["n"]
@@ -276,19 +271,17 @@ def test_banded_matrix_gathers_from_the_shared_window(lb, monkeypatch):
     rng = np.random.default_rng(21)
     x, y = rng.standard_normal(n), rng.standard_normal(m)
     outs = {}
-    for mode in ("default", "epl8nowindow", "epl4", "nowindow"):
+    for mode in ("default", "window"):
         set_kernel_mode(monkeypatch, mode)
         s = lb.LsqrSolverEz().initialize(m, n, a, irow, icol)
         pa, pat = s.plan(False), s.plan(True)
-        if mode == "default":
-            for p in (pa, pat):
-                assert p["entries_per_lane"] == 8 and p["ctas_per_sm"] == 2 and p["lines_per_gather"] <= 16, p
-                assert p["window_doubles"] > 0 and p["windowed_fraction"] >= 0.99 and p["span_max"] <= p["window_doubles"], p
-        elif mode == "epl8nowindow":
-            assert pa["window_doubles"] == 0 and pat["window_doubles"] == 0 and pa["entries_per_lane"] == 8
-        elif mode == "epl4":
-            assert pa["entries_per_lane"] == 4 and pa["ctas_per_sm"] == 4 and pa["window_doubles"] > 0     # narrow window of A
-            assert pat["window_doubles"] == 0                                                            # too wide for 4 CTAs per SM
+        assert pa["ctas_per_sm"] == 4 and pat["ctas_per_sm"] == 4
+        assert pa["lines_per_gather"] <= 16 and pat["lines_per_gather"] <= 16          # local gathers, measured at initialize
+        if mode == "window":
+            assert 0 < pa["window_doubles"] <= 304 and pa["windowed_fraction"] >= 0.99, pa
+            assert pat["window_doubles"] == 0 and pat["span_median"] > 304, pat
+        else:
+            assert pa["window_doubles"] == 0 and pat["window_doubles"] == 0
         y1, x2 = y.copy(), x.copy()
         s.aprod(1, m, n, x, y1)
         s.aprod(2, m, n, x2, y)
@@ -299,17 +292,15 @@ def test_banded_matrix_gathers_from_the_shared_window(lb, monkeypatch):
     ref.aprod(1, x.copy(), yr); ref.aprod(2, xr, y.copy())
     for mode in outs:
         assert relerr(outs[mode][0], yr) <= 1e-14 and relerr(outs[mode][1], xr) <= 1e-14, mode
-    # same flavour => same persistent grid => same tile cut => the same additions in the same order
-    assert np.array_equal(outs["default"][0], outs["epl8nowindow"][0])
-    assert np.array_equal(outs["default"][1], outs["epl8nowindow"][1])
-    # uniformly random columns: no window (the span of a piece is the whole vector), no locality, 4 entries per lane
-    set_kernel_mode(monkeypatch, "default")
+    assert np.array_equal(outs["default"][0], outs["window"][0])
+    assert np.array_equal(outs["default"][1], outs["window"][1])
+    # uniformly random columns: the span of a piece is the whole vector, 32 consecutive entries touch 32 lines
     cfg = synth.scaled("C2", 10)
     irow, icol, a = synth.coo_block(cfg["kind"], cfg["seed"], cfg["m"], cfg["n"], cfg["k"])
     s = lb.LsqrSolverEz().initialize(cfg["m"], cfg["n"], a, irow, icol)
     for tr in (False, True):
         p = s.plan(tr)
-        assert p["window_doubles"] == 0 and p["entries_per_lane"] == 4 and p["lines_per_gather"] >= 28, p
+        assert p["window_doubles"] == 0 and p["lines_per_gather"] >= 28, p
 
 
 def test_balanced_tile_schedule_power_law(lb, monkeypatch):
@@ -703,6 +694,8 @@ def _log_rows_agree(got: str, want: str) -> bool:
             continue
         if abs(a) < 1e-9 and abs(b) < 1e-9:             # (exit block: rnorm / arnorm of a consistent system are noise too)
             continue
+        if k >= 2 and tw[k - 2] == "arnorm" and 0.2 <= a / b <= 5.0:
+            continue                                    # the ESTIMATE arnorm = alpha |tau| is noise-dominated at convergence
         tol = 2e-6 if (is_row and k in (1, 2)) else 2e-2             # 10-digit columns / 2- to 6-digit columns
         if abs(a - b) > tol * abs(b) + 1e-13:
             return False
@@ -933,7 +926,7 @@ def test_row_blocked_transpose(lb, mode, monkeypatch):
     assert relerr(r.se, rr.se) <= 1e-8
 
 
-@pytest.mark.parametrize("mode", ["default", "perblock", "nowindow"])
+@pytest.mark.parametrize("mode", ["default", "perblock", "window"])
 @pytest.mark.parametrize("also_rows", [False, True])
 def test_column_blocked_matrix(lb, mode, also_rows, monkeypatch):
     """Forces small column blocks of A (and, optionally, row blocks of A' as well): blocked CSR bit-exact against
