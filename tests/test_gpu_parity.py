@@ -702,17 +702,21 @@ def _log_rows_agree(got: str, want: str) -> bool:
     return True
 
 
-@pytest.mark.parametrize("case", ["ez1", "ez2", "c3"])
+@pytest.mark.parametrize("case", ["ez1", "ez2", "damped"])
 def test_log_lines_follow_reference_format(lb, case):
     """EVERY line of the nout log (header, column titles, each iteration row, exit block; src/lsqr.f90:589-595,
     655-671,813-837,872-880) against the oracle's log of the same solve."""
     from lsqr_b200 import synth
-    if case == "c3":
-        cfg = synth.scaled("C3", 2000)                         # 5000 x 1000, damped: 'Norm Abar' titles, many rows
+    if case == "damped":
+        # 5000 x 1250 power-law rows, damp = 0.2: 'Norm Abar' titles, ~40 iterations, rows thinned to every 10th.
+        # (The trajectory of this problem is stable: the oracle itself reproduces every row to 1e-15 when the triplets
+        # are reordered.  Tiny BANDED instances are not -- the oracle's own residual at iteration 18 moves by 30 %
+        # when b is perturbed by 1e-15 -- so they cannot pin a log.)
+        cfg = synth.scaled("C4", 4000)
         m, n = cfg["m"], cfg["n"]
         irow, icol, a = synth.coo_block(cfg["kind"], cfg["seed"], m, n, cfg["k"])
         b = synth.rhs_block(irow, icol, a, m, synth.x_true(cfg["seed"], n), cfg["seed"])
-        damp, opts = cfg["damp"], dict(atol=1e-8, btol=1e-8, conlim=1e8, itnlim=500)
+        damp, opts = 0.2, dict(atol=1e-8, btol=1e-8, conlim=1e8, itnlim=500)
     else:
         m, n, a, irow, icol, b = ez1() if case == "ez1" else ez2()
         damp, opts = 0.0, dict(itnlim=100)
