@@ -128,6 +128,9 @@ __device__ __forceinline__ double d2norm(double a, double b)
 // put the whole kernel under the ABI's register conventions: measured 40 % slower fused SpMV kernels).
 __device__ __forceinline__ void ssq_add(double &med, double *exc, int stride, double r)
 {
+#ifdef LSQRB_EXPERIMENT_PLAIN_SSQ   // measurement only (cost of the scaling test): NOT overflow-safe, never shipped
+    med += r * r; (void)exc; (void)stride; return;
+#endif
     const unsigned e = ((unsigned)__double2hiint(r) >> 20) & 0x7ffu;
     if (e - kBlueExpLo <= kBlueExpSpan) {                    // the common case: one subtract + compare
         med += r * r;

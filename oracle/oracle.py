@@ -62,15 +62,18 @@ def build(force: bool = False) -> str:
     return _LIB_PATH
 
 
+_BUILD_FLAGS = "-O2 -ffp-contract=off"
+
+
 def use_native_build() -> str:
     """For the TIMED CPU baseline only: compile a copy of the oracle for the CPU of the box it runs on
     (gcc -O3 -march=native -ffp-contract=off) and make lib() load it.  Call before the first
     use of the oracle in a process.  Returns the flags in use; falls back to the portable -O2 build if the compile
     fails or the library is already loaded."""
-    global _LIB_PATH
-    flags = "-O2 -ffp-contract=off"
+    global _LIB_PATH, _BUILD_FLAGS
     if _lib is not None:
-        return flags
+        return _BUILD_FLAGS          # (already loaded: report what was loaded)
+    flags = _BUILD_FLAGS
     native = os.path.join(_HERE, "build", "liblsqr_oracle_native.so")
     try:
         subprocess.run(["make", "-B", "-C", _HERE, "native"], check=True, capture_output=True)   # always for THIS CPU
@@ -79,6 +82,7 @@ def use_native_build() -> str:
             flags = "-O3 -march=native -ffp-contract=off"
     except Exception:
         pass
+    _BUILD_FLAGS = flags
     return flags
 
 
