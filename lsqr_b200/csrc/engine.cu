@@ -308,6 +308,7 @@ static int ez_initialize_impl(lsqr_b200_ez *me, int64_t nnz, const double *a, co
     me->single_launch = env_int("LSQR_B200_SINGLE_LAUNCH", 1) != 0;
     me->guard = std::max(0, std::min(env_int("LSQR_B200_DRIFT_GUARD", 1), 8));
     me->overlap_update = me->opt.world_size == 1 && env_int("LSQR_B200_OVERLAP_UPDATE", 1) != 0;
+    me->wk.pdl = env_int("LSQR_B200_PDL", 0) != 0;
     if (me->overlap_update) {
         LSQRB_CUDA(cudaStreamCreateWithFlags(&me->side, cudaStreamNonBlocking));
         LSQRB_CUDA(cudaEventCreateWithFlags(&me->ev_fork, cudaEventDisableTiming));
@@ -584,6 +585,9 @@ static int do_aprod(lsqr_b200_ez *me, Ssq *aux)
 {
     ProductIo io;
     io.x = me->v; io.out = me->u; io.part = me->gu; io.first_mode = BM_STORE; io.aux = aux;
+    // the A v kernel directly follows the A'u kernel of the previous iteration in the stream: with LSQR_B200_PDL its
+    // launch and prologue overlap that kernel's tail, grid reduction and scalar step
+    io.pdl = me->wk.pdl && me->opt.world_size == 1;
     return launch_product<FIN_APROD>(me->wk, me->A, me->planA, io, me->single_launch, me->guard);
 }
 template <int FIN>   // FIN_ATPROD / FIN_INIT_ATPROD: v' = ct_mat (A'u) + ct_vec v, ||v'||: one launch
@@ -653,7 +657,8 @@ static int enqueue_iteration(lsqr_b200_ez *me, bool wantse)
         {
             cudaStream_t main_stream = wk.stream;
             wk.stream = me->side;
-            int rc = launch_update<true>(wk, me->n, me->x, me->w, me->v, me->se, wantse);
+            int rc;
+            { ProfScope p(me, CLS_UPDATE); rc = launch_update<true>(wk, me->n, me->x, me->w, me->v, me->se, wantse); }
             wk.stream = main_stream;
             LSQRB_TRY(rc);
         }
@@ -692,10 +697,17 @@ static int build_graph(lsqr_b200_ez *me, bool wantse)
     cudaError_t e = cudaStreamEndCapture(wk.stream, &graph);
     me->graph_launches = wk.launches - saved;
     wk.launches = saved;
-    if (rc != LSQR_B200_OK) { if (graph) cudaGraphDestroy(graph); cudaGetLastError(); return rc; }   // (clears the capture's sticky error)
+    if (rc == LSQR_B200_OK && e == cudaSuccess) e = cudaGraphInstantiate(&me->graph_exec, graph, 0);
+    if (graph) cudaGraphDestroy(graph);
+    if ((rc != LSQR_B200_OK || e != cudaSuccess) && wk.pdl) {
+        // a runtime that cannot capture programmatic launch edges: capture again with ordinary edges
+        cudaGetLastError();
+        if (me->graph_exec) { cudaGraphExecDestroy(me->graph_exec); me->graph_exec = nullptr; }
+        wk.pdl = 0;
+        return build_graph(me, wantse);
+    }
+    if (rc != LSQR_B200_OK) { cudaGetLastError(); return rc; }   // (clears the capture's sticky error)
     LSQRB_CUDA(e);
-    LSQRB_CUDA(cudaGraphInstantiate(&me->graph_exec, graph, 0));
-    cudaGraphDestroy(graph);
     me->graph_wantse = (int)wantse;
     return LSQR_B200_OK;
 }

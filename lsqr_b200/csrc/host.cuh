@@ -115,6 +115,7 @@ struct Work {
     int max_grid = kNumSMs * 8;
     int sms = kNumSMs;
     int64_t launches = 0;
+    int pdl = 0;             // LSQR_B200_PDL: programmatic dependent launch of the A v kernel behind the A'u kernel
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 
     // user_stream == NULL: a library-owned BLOCKING stream (it synchronises implicitly with the legacy default stream,

@@ -76,11 +76,16 @@ static int spmv_configure(bool windows, int *ctas_per_sm)
         occ = std::min(occ, n);
         return LSQR_B200_OK;
     };
-    LSQRB_TRY(one(spmv_kernel<FIN_NONE, kEpl>));
-    LSQRB_TRY(one(spmv_kernel<FIN_APROD, kEpl>));
-    LSQRB_TRY(one(spmv_kernel<FIN_ATPROD, kEpl>));
-    LSQRB_TRY(one(spmv_kernel<FIN_INIT_ATPROD, kEpl>));
-    LSQRB_TRY(one(spmv_kernel<FIN_PUSH, kEpl>));
+    LSQRB_TRY(one(spmv_kernel<FIN_NONE, kEpl, false>));
+    LSQRB_TRY(one(spmv_kernel<FIN_APROD, kEpl, false>));
+    LSQRB_TRY(one(spmv_kernel<FIN_ATPROD, kEpl, false>));
+    LSQRB_TRY(one(spmv_kernel<FIN_INIT_ATPROD, kEpl, false>));
+    LSQRB_TRY(one(spmv_kernel<FIN_PUSH, kEpl, false>));
+    LSQRB_TRY(one(spmv_kernel<FIN_NONE, kEpl, true>));
+    LSQRB_TRY(one(spmv_kernel<FIN_APROD, kEpl, true>));
+    LSQRB_TRY(one(spmv_kernel<FIN_ATPROD, kEpl, true>));
+    LSQRB_TRY(one(spmv_kernel<FIN_INIT_ATPROD, kEpl, true>));
+    LSQRB_TRY(one(spmv_kernel<FIN_PUSH, kEpl, true>));
     current_pct = pct;
     if (occ < 1) { set_last_error("spmv kernel does not fit an SM"); return LSQR_B200_ERR_CUDA; }
     *ctas_per_sm = occ;
@@ -324,6 +329,7 @@ struct ProductIo {
     double *const *push = nullptr;
     int64_t push_cols = 0;
     const PeerView *peer = nullptr;
+    int pdl = 0;                 // programmatic dependent launch behind the previous kernel of the stream
 };
 
 template <int FIN>
@@ -339,7 +345,15 @@ static int launch_piece(Work &wk, const TilePlan &P, const SpmvArgs &a)
     // (a guarded multi-block launch is a grid barrier per block: its grid was PROVEN co-resident by the probe at
     // initialize; a cooperative launch would be the textbook guarantee, but the runtime refused these grids -- "too
     // many blocks in cooperative launch" -- although the occupancy API reports the same 4 CTAs per SM)
-    LSQRB_CUDA(cudaLaunchKernelEx(&cfg, spmv_kernel<FIN, kEpl>, a));
+    cudaLaunchAttribute attr[1];
+    if (a.pdl) {
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+    }
+    if (P.win_cap > 0) LSQRB_CUDA(cudaLaunchKernelEx(&cfg, spmv_kernel<FIN, kEpl, true>, a));
+    else               LSQRB_CUDA(cudaLaunchKernelEx(&cfg, spmv_kernel<FIN, kEpl, false>, a));
     wk.launches++;
     LSQRB_CUDA(cudaGetLastError());
     return LSQR_B200_OK;
@@ -384,6 +398,7 @@ static int launch_product(Work &wk, const Csr &M, const TilePlan &P, const Produ
     a.st = wk.st; a.aux = io.aux;
     a.push = io.push; a.push_cols = io.push_cols; a.peer = io.peer;
     a.final_adds_part = M.nblocks > 1;
+    a.pdl = io.pdl;
     const int nb = (int)M.nblocks;
     if (single && nb <= kMaxSpmvBlocks) {
         a.ptr = M.ptr; a.tiles = P.tiles; a.nblocks = nb;

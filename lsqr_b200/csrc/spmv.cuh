@@ -81,6 +81,7 @@ struct SpmvArgs {
     int check_done;            // plain product launched from the solve loop: nothing to do once the solver has stopped
     int probe;                 // residency probe: arrive, wait for the whole grid (or 20 ms), leave
     DevState *st;
+    int pdl;                   // launched as a programmatic dependent of the previous kernel: see spmv_kernel
     Ssq *aux;                  // FIN_APROD, multi-GPU: where the local sum u'^2 goes instead of step_after_aprod
     // FIN_PUSH: push[q] = where this rank's contributions to the columns owned by rank q go (q's receive buffer,
     // already offset to this rank's slot); columns [q * push_cols, (q+1) * push_cols) belong to rank q
@@ -347,12 +348,12 @@ __device__ __forceinline__ void warp_tile_loop(const SpmvArgs &a, const BlockCtx
 }
 
 // One piece: stage the gather window if the piece has one, then stream its chunks.
-template <int FIN, int EPL>
+template <int FIN, int EPL, bool WINS>
 __device__ __forceinline__ void warp_tile(const SpmvArgs &a, const BlockCtx &bc, Epilogue<FIN> &epi, double *su, double *wbuf,
                                           const TileDesc &d0, const TileDesc &d1, int lane,
                                           uint64_t pol_stream, uint64_t pol_keep)
 {
-    if (d0.win_len != 0u) {
+    if (WINS && d0.win_len != 0u) {
         // coalesced 8-byte loads: no alignment requirement on x, which may be the caller's own array (aprod)
         const double *src = a.x + d0.win_lo;
         for (uint32_t i = (uint32_t)lane; i < d0.win_len; i += 32u) wbuf[i] = ldg_keep_f64(src + i, pol_keep);
@@ -366,7 +367,10 @@ __device__ __forceinline__ void warp_tile(const SpmvArgs &a, const BlockCtx &bc,
 
 // EPL: stored entries per lane and chunk (see ChunkRegs); EPL = 4 runs 4 CTAs per SM (<= 64 registers), EPL = 8 runs 2
 // (<= 128 registers, room for wide gather windows).
-template <int FIN, int EPL>
+// WINS: the flavour for plans with staged gather windows (opt-in).  The default flavour does not carry the second
+// copy of the chunk loop: the kernel is a third smaller, which measured 2-4 % on the gather-bound families (the
+// unrolled chunk loops of both paths together overflow the instruction cache next to each other).
+template <int FIN, int EPL, bool WINS>
 __global__ void __launch_bounds__(kWThreads, EPL == 4 ? 4 : 2)
 spmv_kernel(SpmvArgs a)
 {
@@ -390,6 +394,25 @@ spmv_kernel(SpmvArgs a)
             }
         }
         return;
+    }
+    if (a.pdl) {
+        // Programmatic dependent launch: this grid was allowed to start while the previous kernel of the stream drains
+        // (its last CTAs, its grid reduction and the scalar step).  Nothing the previous kernel writes may be read
+        // before griddepcontrol.wait; the matrix is constant, so the warp's first chunk is pulled towards L2 meanwhile.
+        asm volatile("griddepcontrol.launch_dependents;");
+        const int s0 = (int)blockIdx.x * kWWarps + (tid >> 5);
+        const int ns = a.order ? a.nslots : a.ntiles;
+        if (s0 < ns) {
+            const uint32_t t = a.order ? a.order[s0] : (uint32_t)s0;
+            if (t != kNoTile) {
+                const TileDesc d0 = a.tiles[t];
+                const uint32_t q = (d0.entry & ~3u) + 4u * (uint32_t)(tid & 31);
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(a.val + q));
+                if ((tid & 1) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.idx + q));
+                if ((tid & 31) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.ptr + d0.row));
+            }
+        }
+        asm volatile("griddepcontrol.wait;" ::: "memory");
     }
     if (kFused) {
         if (st->done) return;
@@ -448,7 +471,7 @@ spmv_kernel(SpmvArgs a)
                 if (t == kNoTile) break;                        // this warp's list is exhausted
                 const TileDesc d0 = tiles[t], d1 = tiles[t + 1];
                 if (d0.row == d1.row) continue;                 // no row starts in this tile (inside a long row)
-                warp_tile<FIN, EPL>(a, bc, epi, su, wbuf, d0, d1, lane, pol_stream, pol_keep);
+                warp_tile<FIN, EPL, WINS>(a, bc, epi, su, wbuf, d0, d1, lane, pol_stream, pol_keep);
             }
             if (a.guard && b + 1 < a.nblocks) {
                 __syncthreads();                                // every warp of this CTA has finished block b
@@ -459,15 +482,21 @@ spmv_kernel(SpmvArgs a)
 
     if (kFused) {
         Ssq total;
-        if (finish_ssq<kWThreads>(st, 0, st->partial, epi.sq, s_exc, s_red, &total)) {
-            if (a.guard) for (int b = 0; b + 1 < a.nblocks; ++b) st->blk_done[b] = 0;
-            if (tracing) st->trace[1][st->tr_n & (kTraceSlots - 1)] = globaltimer_ns();
+        // the step after A'u (rotations, estimates, stopping tests) is run by a whole warp: step_after_atprod_impl
+        if (finish_ssq<kWThreads, FIN == FIN_ATPROD && kWarpStep>(st, 0, st->partial, epi.sq, s_exc, s_red, &total)) {
+            if (tid == 0) {
+                if (a.guard) for (int b = 0; b + 1 < a.nblocks; ++b) st->blk_done[b] = 0;
+                if (tracing) st->trace[1][st->tr_n & (kTraceSlots - 1)] = globaltimer_ns();
+            }
             if (FIN == FIN_APROD) {
                 if (a.aux) *a.aux = total; else step_after_aprod(*st, ssq_norm(total));
             }
-            else if (FIN == FIN_ATPROD) step_after_atprod(*st, ssq_norm(total), true);
+            else if (FIN == FIN_ATPROD) {
+                if (kWarpStep) step_after_atprod_warp(*st, ssq_norm(total), true, tid & 31);
+                else           step_after_atprod(*st, ssq_norm(total), true);
+            }
             else step_init_alpha(*st, ssq_norm(total));
-            if (tracing) { st->trace[2][st->tr_n & (kTraceSlots - 1)] = globaltimer_ns(); st->tr_n += 1; }
+            if (tracing && tid == 0) { st->trace[2][st->tr_n & (kTraceSlots - 1)] = globaltimer_ns(); st->tr_n += 1; }
         }
     } else if (FIN == FIN_PUSH) {
         // this block's peer stores are fenced system-wide before its ticket; the last block publishes the flags

@@ -11,6 +11,11 @@
 namespace lsqrb {
 
 constexpr int kThreads = 256;
+#ifdef LSQRB_EXPERIMENT_SERIAL_STEP   // A/B only: the fused A'u kernel runs its scalar step in one thread
+constexpr bool kWarpStep = false;
+#else
+constexpr bool kWarpStep = true;
+#endif
 
 // after ||b||:  src/lsqr.f90:632-636
 __device__ __forceinline__ void step_init_beta(DevState &s, double nrm)
@@ -72,100 +77,194 @@ __device__ __forceinline__ void step_after_aprod(DevState &s, double nrm)
     }
 }
 
-// after ||v'||: rotations, estimates and stopping tests, src/lsqr.f90:695-721,724-726,751-810,843-850
-__device__ __forceinline__ void step_after_atprod(DevState &s, double nrm, bool new_alpha)
+// ---- lane-parallel divisions and square roots --------------------------------------------------------------------
+// The step after A'u is a chain of ~36 FP64 divisions and ~15 square roots (each an inline Newton sequence with a
+// branch, so one thread runs them strictly one after the other: measured 8-14 us per iteration, a tenth of a C2
+// iteration).  Its dependency graph is only ~9 levels deep, so the fused SpMV kernel hands it to a whole warp: every
+// lane holds every scalar, the K independent quotients (roots) of one level are computed by lanes 0..K-1 and broadcast
+// by shuffles.  Division and square root are correctly rounded and everything else is the same source code, so the
+// one-thread form (WARP = false; the small kernels of the other paths) produces the same bits.
+template <bool WARP, int K>
+__device__ __forceinline__ void par_div(int lane, const double (&n)[K], const double (&d)[K], double (&r)[K])
 {
-    if (new_alpha) {
-        s.alpha = nrm;
-        s.inv_alpha = s.alpha > 0.0 ? 1.0 / s.alpha : 1.0;   // alpha = 0: v is left unscaled (:696-698)
+    if (WARP) {
+        double nn = 1.0, dd = 1.0;
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+            if (lane == k) { nn = n[k]; dd = d[k]; }
+        const double rr = nn / dd;
+#pragma unroll
+        for (int k = 0; k < K; ++k) r[k] = __shfl_sync(0xffffffffu, rr, k);
+    } else {
+#pragma unroll
+        for (int k = 0; k < K; ++k) r[k] = n[k] / d[k];
     }
-    const double alpha = s.alpha, beta = s.beta;
-    s.g_c3 = (new_alpha && alpha > 0.0) ? s.inv_alpha : 1.0;
-    s.g_c0 = -alpha;
+}
+
+template <bool WARP, int K>
+__device__ __forceinline__ void par_sqrt(int lane, const double (&a)[K], double (&r)[K])
+{
+    if (WARP) {
+        double aa = 1.0;
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+            if (lane == k) aa = a[k];
+        const double rr = sqrt(aa);
+#pragma unroll
+        for (int k = 0; k < K; ++k) r[k] = __shfl_sync(0xffffffffu, rr, k);
+    } else {
+#pragma unroll
+        for (int k = 0; k < K; ++k) r[k] = sqrt(a[k]);
+    }
+}
+
+// d2norm (src/lsqr.f90:1164-1179) in two levels: scale and the two quotients, then scale * sqrt(p^2 + q^2).
+// A zero scale divides by one instead: p = q = 0 and the result is the reference's 0.
+struct Hyp {
+    double scale, den;
+    __device__ __forceinline__ Hyp(double a, double b) : scale(fabs(a) + fabs(b)) { den = scale == 0.0 ? 1.0 : scale; }
+    __device__ __forceinline__ double arg(double p, double q) const { return p * p + q * q; }
+    __device__ __forceinline__ double fin(double root) const { return scale * root; }
+};
+
+// after ||v'||: rotations, estimates and stopping tests, src/lsqr.f90:695-721,724-726,751-810,843-850
+// WARP: called by all 32 lanes of one warp (every lane computes every scalar, lane 0 stores).
+template <bool WARP>
+__device__ __forceinline__ void step_after_atprod_impl(DevState &s, double nrm, bool new_alpha, int lane)
+{
+    const bool writer = !WARP || lane == 0;
+    const double alpha = new_alpha ? nrm : s.alpha;
+    const double beta = s.beta;
+    const double damp = s.damp, wnorm = s.wnorm, anorm = s.anorm, bnorm = s.bnorm;
+    const double rhobar0 = s.rhobar, dnorm0 = s.dnorm, xnorm10 = s.xnorm1, z0 = s.z, sn20 = s.sn2, cs20 = s.cs2;
+    const double res20 = s.res2, atol = s.atol, btol = s.btol, ctol = s.ctol;
+    const int itn = s.itn, itnlim = s.itnlim, damped = s.damped;
+    double phibar = s.phibar, psi = s.psi, inv_alpha = s.inv_alpha;
+    int istop = s.istop, nstop = s.nstop;
+    const bool want_ia = new_alpha && alpha > 0.0;
 
     // plane rotation that removes damp (:703-710)
-    double rhbar1 = s.rhobar;
-    if (s.damped) {
-        rhbar1 = d2norm(s.rhobar, s.damp);
-        const double cs1 = s.rhobar / rhbar1;
-        const double sn1 = s.damp / rhbar1;
-        s.psi = sn1 * s.phibar;
-        s.phibar = cs1 * s.phibar;
+    double rhbar1 = rhobar0;
+    if (damped) {
+        const Hyp h(rhobar0, damp);
+        double r3[3], r1[1], r2[2];
+        par_div<WARP, 3>(lane, {rhobar0, damp, 1.0}, {h.den, h.den, want_ia ? alpha : 1.0}, r3);
+        par_sqrt<WARP, 1>(lane, {h.arg(r3[0], r3[1])}, r1);
+        rhbar1 = h.fin(r1[0]);
+        par_div<WARP, 2>(lane, {rhobar0, damp}, {rhbar1, rhbar1}, r2);
+        const double cs1 = r2[0], sn1 = r2[1];
+        psi = sn1 * phibar;
+        phibar = cs1 * phibar;
+        if (new_alpha) inv_alpha = want_ia ? r3[2] : 1.0;        // alpha = 0: v is left unscaled (:696-698)
     }
 
-    // plane rotation that removes the subdiagonal beta (:714-721)
-    const double rho = d2norm(rhbar1, beta);
-    const double cs = rhbar1 / rho;
-    const double sn = beta / rho;
+    // plane rotation that removes the subdiagonal beta (:714-721); res2 (:778) only needs psi
+    const Hyp hr(rhbar1, beta), hs(res20, psi);
+    double q5[5], w2[2];
+    par_div<WARP, 5>(lane, {rhbar1, beta, res20, psi, 1.0}, {hr.den, hr.den, hs.den, hs.den, (want_ia && !damped) ? alpha : 1.0}, q5);
+    if (new_alpha && !damped) inv_alpha = want_ia ? q5[4] : 1.0;
+    par_sqrt<WARP, 2>(lane, {hr.arg(q5[0], q5[1]), hs.arg(q5[2], q5[3])}, w2);
+    const double rho = hr.fin(w2[0]);
+    const double res2 = hs.fin(w2[1]);
+    double q3[3];
+    par_div<WARP, 3>(lane, {rhbar1, beta, 1.0}, {rho, rho, rho}, q3);
+    const double cs = q3[0], sn = q3[1], t3u = q3[2];
     const double theta = sn * alpha;
-    s.rhobar = -cs * alpha;
-    const double phi = cs * s.phibar;
-    s.phibar = sn * s.phibar;
+    const double rhobar = -cs * alpha;
+    const double phi = cs * phibar;
+    phibar = sn * phibar;
     const double tau = sn * phi;
 
-    // coefficients of the x/w update (:724-726)
-    s.t1 = phi / rho;
-    s.t2 = -theta / rho;
-    s.t3 = 1.0 / rho;
-
     // dknorm = sqrt(sum (t3 w_i)^2) = |t3| ||w||  (:729-751); ||w|| was produced when w was written
-    const double dknorm = fabs(s.t3) * s.wnorm;
-    s.dnorm = d2norm(s.dnorm, dknorm);
+    const double dknorm = fabs(t3u) * wnorm;
     const double dxk = fabs(phi * dknorm);
-    if (s.dxmax < dxk) {
-        s.dxmax = dxk;
-        s.maxdx = s.itn;
-    }
+    // right rotation (:762-766)
+    const double delta = sn20 * rho;
+    const double gambar = -cs20 * rho;
+    const double rhs = phi - delta * z0;
+    // update coefficients (:724-726), zbar, and the quotients of dnorm (:751), gamma (:767), rnorm (:779)
+    const Hyp hd(dnorm0, dknorm), hg(gambar, theta), hn(res2, phibar);
+    double q9[9];
+    par_div<WARP, 9>(lane, {phi, -theta, rhs, dnorm0, dknorm, gambar, theta, res2, phibar},
+                     {rho, rho, gambar, hd.den, hd.den, hg.den, hg.den, hn.den, hn.den}, q9);
+    const double t1u = q9[0], t2u = q9[1], zbar = q9[2];
+    const Hyp hx(xnorm10, zbar);
+    double qx[2], w4[4];
+    par_div<WARP, 2>(lane, {xnorm10, zbar}, {hx.den, hx.den}, qx);
+    par_sqrt<WARP, 4>(lane, {hd.arg(q9[3], q9[4]), hg.arg(q9[5], q9[6]), hn.arg(q9[7], q9[8]), hx.arg(qx[0], qx[1])}, w4);
+    const double dnorm = hd.fin(w4[0]);
+    const double gamma = hg.fin(w4[1]);
+    const double rnorm = hn.fin(w4[2]);
+    const double xnorm = hx.fin(w4[3]);      // estimate of norm(x) (:767)
 
-    // right rotation, estimate of norm(x) (:762-771)
-    const double delta = s.sn2 * rho;
-    const double gambar = -s.cs2 * rho;
-    const double rhs = phi - delta * s.z;
-    const double zbar = rhs / gambar;
-    s.xnorm = d2norm(s.xnorm1, zbar);
-    const double gamma = d2norm(gambar, theta);
-    s.cs2 = gambar / gamma;
-    s.sn2 = theta / gamma;
-    s.z = rhs / gamma;
-    s.xnorm1 = d2norm(s.xnorm1, s.z);
-
-    // estimates (:776-790)
-    s.acond = s.anorm * s.dnorm;
-    s.res2 = d2norm(s.res2, s.psi);
-    s.rnorm = d2norm(s.res2, s.phibar);
-    s.arnorm = alpha * fabs(tau);
-
-    s.alfopt = sqrt(s.rnorm / (s.dnorm * s.xnorm));
-    const double test1 = s.rnorm / s.bnorm;
-    double test2 = 0.0;
-    if (s.rnorm > 0.0) test2 = s.arnorm / (s.anorm * s.rnorm);
-    const double test3 = 1.0 / s.acond;
-    double t1 = test1 / (1.0 + s.anorm * s.xnorm / s.bnorm);
-    const double rtol = s.btol + s.atol * s.anorm * s.xnorm / s.bnorm;
+    // estimates (:776-790) and the quotients of the stopping tests (:791-797)
+    const double acond = anorm * dnorm;
+    const double arnorm = alpha * fabs(tau);
+    const bool has_r = rnorm > 0.0;
+    double q8[8];
+    par_div<WARP, 8>(lane, {gambar, theta, rhs, rnorm, has_r ? arnorm : 1.0, 1.0, rnorm, anorm * xnorm},
+                     {gamma, gamma, gamma, bnorm, has_r ? anorm * rnorm : 1.0, acond, dnorm * xnorm, bnorm}, q8);
+    const double cs2 = q8[0], sn2 = q8[1], z = q8[2];
+    const double test1 = q8[3];
+    const double test2 = has_r ? q8[4] : 0.0;
+    const double test3 = q8[5];
+    const Hyp h1(xnorm10, z);
+    double q4[4], w2b[2];
+    par_div<WARP, 4>(lane, {xnorm10, z, test1, atol * anorm * xnorm}, {h1.den, h1.den, 1.0 + q8[7], bnorm}, q4);
+    par_sqrt<WARP, 2>(lane, {h1.arg(q4[0], q4[1]), q8[6]}, w2b);
+    const double xnorm1 = h1.fin(w2b[0]);
+    const double alfopt = w2b[1];
+    double t1 = q4[2];
+    const double rtol = btol + q4[3];
 
     // stopping tests, later assignments win (:798-810)
     const double t3 = 1.0 + test3;
     const double t2 = 1.0 + test2;
     t1 = 1.0 + t1;
-    int istop = s.istop;
-    if (s.itn >= s.itnlim) istop = 5;
+    if (itn >= itnlim) istop = 5;
     if (t3 <= 1.0) istop = 4;
     if (t2 <= 1.0) istop = 2;
     if (t1 <= 1.0) istop = 1;
-    if (test3 <= s.ctol) istop = 4;
-    if (test2 <= s.atol) istop = 2;
+    if (test3 <= ctol) istop = 4;
+    if (test2 <= atol) istop = 2;
     if (test1 <= rtol) istop = 1;
 
     // nconv = 1 gate (:843-850)
     if (istop == 0) {
-        s.nstop = 0;
+        nstop = 0;
     } else {
         const int nconv = 1;
-        s.nstop = s.nstop + 1;
-        if (s.nstop < nconv && s.itn < s.itnlim) istop = 0;
+        nstop = nstop + 1;
+        if (nstop < nconv && itn < itnlim) istop = 0;
     }
-    s.istop = istop;
+    if (!writer) return;
 
+    if (new_alpha) { s.alpha = alpha; s.inv_alpha = inv_alpha; }
+    s.g_c3 = want_ia ? inv_alpha : 1.0;
+    s.g_c0 = -alpha;
+    s.psi = psi;
+    s.phibar = phibar;
+    s.rhobar = rhobar;
+    s.t1 = t1u;
+    s.t2 = t2u;
+    s.t3 = t3u;
+    s.dnorm = dnorm;
+    if (s.dxmax < dxk) {
+        s.dxmax = dxk;
+        s.maxdx = itn;
+    }
+    s.xnorm = xnorm;
+    s.cs2 = cs2;
+    s.sn2 = sn2;
+    s.z = z;
+    s.xnorm1 = xnorm1;
+    s.acond = acond;
+    s.res2 = res2;
+    s.rnorm = rnorm;
+    s.arnorm = arnorm;
+    s.alfopt = alfopt;
+    s.nstop = nstop;
+    s.istop = istop;
     s.phi = phi;
     s.dknorm = dknorm;
     s.dxk = dxk;
@@ -173,25 +272,37 @@ __device__ __forceinline__ void step_after_atprod(DevState &s, double nrm, bool 
     s.test2 = test2;
 
     // snapshot of this iteration's scalars; x(1) is added when the x/w update has been applied
-    s.rec.itn = (double)s.itn;
+    s.rec.itn = (double)itn;
     s.rec.istop = (double)istop;
-    s.rec.rnorm = s.rnorm;
+    s.rec.rnorm = rnorm;
     s.rec.test1 = test1;
     s.rec.test2 = test2;
-    s.rec.anorm = s.anorm;
-    s.rec.acond = s.acond;
+    s.rec.anorm = anorm;
+    s.rec.acond = acond;
     s.rec.phi = phi;
     s.rec.dknorm = dknorm;
     s.rec.dxk = dxk;
-    s.rec.alfopt = s.alfopt;
+    s.rec.alfopt = alfopt;
     s.rec.alpha = alpha;
     s.rec.beta = beta;
-    s.rec.xnorm = s.xnorm;
-    s.rec.arnorm = s.arnorm;
+    s.rec.xnorm = xnorm;
+    s.rec.arnorm = arnorm;
 
     // coefficients of the next Aprod:  u'' = A (v'/alpha) - alpha (u'/beta)
-    s.ca_mat = s.inv_alpha;
+    s.ca_mat = inv_alpha;
     s.ca_vec = -alpha * s.inv_beta;
+}
+
+// one-thread form (the small kernels of the NCCL, peer and operator-hook paths)
+__device__ __forceinline__ void step_after_atprod(DevState &s, double nrm, bool new_alpha)
+{
+    step_after_atprod_impl<false>(s, nrm, new_alpha, 0);
+}
+
+// warp form: all 32 lanes of one warp call it with the same arguments
+__device__ __forceinline__ void step_after_atprod_warp(DevState &s, double nrm, bool new_alpha, int lane)
+{
+    step_after_atprod_impl<true>(s, nrm, new_alpha, lane);
 }
 
 // after the x/w update of iteration rec.itn: publish its record, close the iteration
@@ -229,10 +340,11 @@ __device__ __forceinline__ void step_after_update(DevState &s, double wnorm, dou
 // accumulator (a register) and its two exceptional accumulators (shared memory, exc[tid] = big,
 // exc[THREADS + tid] = small; see ssq_add).  Every block stores its partial triple in a fixed slot;
 // the block that draws the last ticket sums the slots in index order with a fixed tree, so the
-// result does not depend on block scheduling.  Returns true in thread 0 of the last block only.
+// result does not depend on block scheduling.  Returns true in thread 0 of the last block only (WARP0: in all 32
+// lanes of its first warp, each holding the total, for the lane-parallel scalar step).
 // The exceptional accumulators are only reduced when some thread of the grid used them.
 // =============================================================================================
-template <int THREADS>
+template <int THREADS, bool WARP0 = false>
 __device__ __forceinline__ bool finish_ssq(DevState *st, int cslot, double (*slots)[kMaxPartials],
                                            double med, const double *exc, double *smem, Ssq *total)
 {
@@ -274,6 +386,8 @@ __device__ __forceinline__ bool finish_ssq(DevState *st, int cslot, double (*slo
     if (tid == 0) {
         st->counter[cslot] = 0;
         st->exc_flag[cslot] = 0;
+    }
+    if (tid == 0 || (WARP0 && tid < 32)) {     // block_sum leaves the sum in every lane of warp 0
         total->med = a0; total->big = a1; total->sml = a2;
         return true;
     }

@@ -5,7 +5,7 @@ N=${1:-8}
 mkdir -p gpurun_out
 for peer in 1 0; do
   echo "== bench N=$N peer=$peer"
-  LSQR_B200_PEER_EXCHANGE=$peer LSQR_B200_VERBOSE=1 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node=$N --master-addr 127.0.0.1 --master-port 2966$peer bench.py --gpus $N --steps 3 --warmup 3 \
+  LSQR_B200_PEER_EXCHANGE=$peer LSQR_B200_VERBOSE=1 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node=$N --master-addr 127.0.0.1 --master-port 2966$peer bench.py --gpus $N --steps 10 --warmup 3 --secondary none --no-cpu-baseline \
       > gpurun_out/bench_n${N}_peer$peer.json 2> gpurun_out/bench_n${N}_peer$peer.err; echo "rc=$?"
   python - <<P
 import json

@@ -45,6 +45,17 @@ echo "== full C5, r02 without the scaling test"
 LSQR_B200_LIB=$PWD/lsqr_b200/lib/liblsqr_b200.plainssq.so timeout 600 python bench.py --steps 10 --warmup 3 --secondary none --no-cpu-baseline > gpurun_out/bench_c5_r02plain.json 2> gpurun_out/bench_c5_r02plain.err; echo "rc=$?"; benchline gpurun_out/bench_c5_r02plain.json
 echo "== full C5, r02 per-block launches"
 LSQR_B200_SINGLE_LAUNCH=0 timeout 600 python bench.py --steps 10 --warmup 3 --secondary none --no-cpu-baseline --no-oracle-check > gpurun_out/bench_c5_r02perblock.json 2> gpurun_out/bench_c5_r02perblock.err; echo "rc=$?"; benchline gpurun_out/bench_c5_r02perblock.json
+echo "== C2 scalar step A/B (warp-parallel vs one thread)"
+for rep in 1 2; do
+  timeout 300 python scripts/spmv_bench.py --modes default,pdl --workloads C2:1 --reps 20 > gpurun_out/ab_c2_warpstep_$rep.jsonl 2>/dev/null; show gpurun_out/ab_c2_warpstep_$rep.jsonl
+  LSQR_B200_LIB=$PWD/lsqr_b200/lib/liblsqr_b200.serialstep.so timeout 300 python scripts/spmv_bench.py --modes default --workloads C2:1 --reps 20 > gpurun_out/ab_c2_serialstep_$rep.jsonl 2>/dev/null; show gpurun_out/ab_c2_serialstep_$rep.jsonl
+done
+LSQR_B200_TRACE=1 timeout 300 python bench.py --workload C2 --steps 1 --warmup 3 --secondary none --no-cpu-baseline --no-oracle-check 2> gpurun_out/trace_c2_warpstep.txt > /dev/null; grep "trace\]" gpurun_out/trace_c2_warpstep.txt | sed -n 2,14p
+LSQR_B200_PDL=1 LSQR_B200_TRACE=1 timeout 300 python bench.py --workload C2 --steps 1 --warmup 3 --secondary none --no-cpu-baseline --no-oracle-check 2> gpurun_out/trace_c2_pdl.txt > /dev/null; grep "trace\]" gpurun_out/trace_c2_pdl.txt | sed -n 2,14p
+LSQR_B200_LIB=$PWD/lsqr_b200/lib/liblsqr_b200.serialstep.so LSQR_B200_TRACE=1 timeout 300 python bench.py --workload C2 --steps 1 --warmup 3 --secondary none --no-cpu-baseline --no-oracle-check 2> gpurun_out/trace_c2_serialstep.txt > /dev/null; grep "trace\]" gpurun_out/trace_c2_serialstep.txt | sed -n 2,14p
+echo "== C2 bench with PDL"
+LSQR_B200_PDL=1 timeout 600 python bench.py --workload C2 --secondary none --no-cpu-baseline > gpurun_out/bench_c2_pdl.json 2> gpurun_out/bench_c2_pdl.err; echo "rc=$?"; benchline gpurun_out/bench_c2_pdl.json
+timeout 600 python bench.py --workload C2 --secondary none --no-cpu-baseline > gpurun_out/bench_c2_default.json 2> gpurun_out/bench_c2_default.err; echo "rc=$?"; benchline gpurun_out/bench_c2_default.json
 echo "== hook bench C2"
 timeout 600 python bench.py --workload C2 --via-hook --secondary none --no-cpu-baseline > gpurun_out/bench_c2_hook.json 2> gpurun_out/bench_c2_hook.err; echo "rc=$?"; benchline gpurun_out/bench_c2_hook.json
 tail -3 gpurun_out/*.err | cut -c1-300 | tail -40

@@ -31,6 +31,7 @@ MODES = {
     "guard2": {"LSQR_B200_DRIFT_GUARD": "2"},
     "nooverlap": {"LSQR_B200_OVERLAP_UPDATE": "0"},
     "window": {"LSQR_B200_WINDOW": "1"},
+    "pdl": {"LSQR_B200_PDL": "1"},
 }
 
 
