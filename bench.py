@@ -494,7 +494,7 @@ def run_workload(name, args, steps, world, rank, dev, with_roofline=True):
         prof = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic.json")))
         traffic = prof.get(name, {}).get(dom)
         if traffic is not None:
-            traffic_src = prof.get("_source", "committed ncu capture (profiles/dram_traffic.json)")
+            traffic_src = prof.get(name, {}).get("source") or prof.get("_source", "committed ncu capture (profiles/dram_traffic.json)")
     except Exception:
         pass
     roofline = {
@@ -525,7 +525,8 @@ def run_workload(name, args, steps, world, rank, dev, with_roofline=True):
     torch.cuda.empty_cache()
     value = bytes_iter * itn / (ms * 1e-3) / 1e9
     e2e_value = bytes_iter * itn_e2e / (ms_e2e * 1e-3) / 1e9
-    workload = (f"{name}: {cfg['kind']} {m}x{n}, nnz={nnz}, damp={cfg['damp']}, via lsqr_solver_ez "
+    api_path = "lsqr_solver%lsqr with the ez matrix as device operator (engine=1: the operator-hook loop)" if args.via_hook else "lsqr_solver_ez"
+    workload = (f"{name}: {cfg['kind']} {m}x{n}, nnz={nnz}, damp={cfg['damp']}, via {api_path} "
                 f"(atol=btol=1e-10, conlim=1e8), row-partitioned over {world} GPU(s)")
     return {
         "workload": workload, "value": value, "ms_per_step": ms / steps, "iters_per_s": itn / (ms * 1e-3),

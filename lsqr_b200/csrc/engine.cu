@@ -1079,6 +1079,7 @@ static int lsqr_with_operator(Work &wk, lsqr_b200_aprod_fn aprod, void *aprod_us
     const int lim = std::max(itnlim, 1);
     int enq = 0, nb = 0, done_batches = 0;
     auto enqueue_batch = [&]() -> int {
+        const int64_t before = wk.launches;
         for (int i = 0; i < B; ++i) {
             LSQRB_TRY(call_aprod(1));                                                  // u += A v           (:682)
             hook_norm_kernel<false, false><<<gm, kThreads, 0, wk.stream>>>(m, u, st);  // beta, anorm       (:683-689)
@@ -1088,6 +1089,7 @@ static int lsqr_with_operator(Work &wk, lsqr_b200_aprod_fn aprod, void *aprod_us
             wk.launches += 3;
             LSQRB_TRY(scale_update(0));                                                // x, w, se (:729-745); v, u rescaled
         }
+        wk.iter_launches = (wk.launches - before) / B;     // ours + the operator's, if it counts its launches here
         LSQRB_CUDA(cudaGetLastError());
         LSQRB_CUDA(cudaEventRecord(wk.ev[nb & 3], wk.stream));
         enq += B;
@@ -1205,6 +1207,7 @@ static int ez_solve_through_hook(lsqr_b200_ez *me, const double *b, double damp,
     if (wantse && n > 0) LSQRB_CUDA(cudaMemcpyAsync(se, me->se, sizeof(double) * (size_t)n, cudaMemcpyDefault, wk.stream));
     LSQRB_CUDA(cudaStreamSynchronize(wk.stream));
     me->times.total_launches = wk.launches;
+    me->times.iteration_launches = wk.iter_launches;
     return LSQR_B200_OK;
 }
 

@@ -115,6 +115,7 @@ struct Work {
     int max_grid = kNumSMs * 8;
     int sms = kNumSMs;
     int64_t launches = 0;
+    int64_t iter_launches = 0;   // operator-hook loop: launches per iteration of the last solve
     int pdl = 0;             // LSQR_B200_PDL: programmatic dependent launch of the A v kernel behind the A'u kernel
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 
