@@ -202,7 +202,7 @@ typedef struct lsqr_b200_plan_info {
     int32_t single_launch;      /* one persistent launch walks every block of a product                         */
     int32_t peer_exchange;      /* multi-GPU: exchange over NVLink peer memory instead of one NCCL all-reduce   */
     int32_t entries_per_lane;   /* kernel flavour: 4 (gather-bound matrices) or 8 (matrices with local gathers)  */
-    int32_t reserved;
+    int32_t flavour;            /* kernel flavour: 0 = local gathers, 1 = staged gather windows, 2 = random columns */
     double  lines_per_gather;   /* 128-byte lines spanned by 32 consecutive stored entries (32 = no locality)   */
 } lsqr_b200_plan_info;
 LSQR_B200_API int lsqr_b200_ez_plan(const lsqr_b200_ez *me, int32_t which, lsqr_b200_plan_info *out);

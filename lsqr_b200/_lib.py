@@ -55,7 +55,7 @@ class PlanInfo(C.Structure):
         ("windowed_fraction", C.c_double), ("imbalance", C.c_double),
         ("span_median", C.c_int64), ("span_max", C.c_int64),
         ("single_launch", C.c_int32), ("peer_exchange", C.c_int32),
-        ("entries_per_lane", C.c_int32), ("reserved", C.c_int32), ("lines_per_gather", C.c_double),
+        ("entries_per_lane", C.c_int32), ("flavour", C.c_int32), ("lines_per_gather", C.c_double),
     ]
 
 

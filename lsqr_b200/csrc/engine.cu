@@ -322,7 +322,7 @@ static int ez_initialize_impl(lsqr_b200_ez *me, int64_t nnz, const double *a, co
             fprintf(stderr, "[lsqr_b200] %s: blocks=%lld (block size %lld) tiles=%d (%llu work units) grid=%d CTAs x %d/SM  window=%d doubles "
                             "(%.1f%% of the entries staged; piece span median %u, max %u) lines/gather %.1f%s%s imbalance %.3f\n",
                     name, (long long)M.nblocks, (long long)M.block_rows, P.ntiles, (unsigned long long)P.tile, P.ctas, P.ctas / std::max(1, me->wk.sms), P.win_cap,
-                    100.0 * P.windowed, P.span_p50, P.span_max, P.lines_per_gather, "", P.order ? " LPT" : "", P.imbalance);
+                    100.0 * P.windowed, P.span_p50, P.span_max, P.lines_per_gather, P.win_cap > 0 ? " [window flavour]" : (P.gather_bound ? " [gather-bound flavour]" : " [local flavour]"), P.order ? " LPT" : "", P.imbalance);
         };
         fprintf(stderr, "[lsqr_b200] m=%d n=%d nnz=%lld single_launch=%d guard=%d\n", me->m, me->n, (long long)me->nnz, (int)me->single_launch, (int)me->guard);
         say("A ", me->A, me->planA);
@@ -472,6 +472,7 @@ int lsqr_b200_ez_plan(const lsqr_b200_ez *me, int32_t which, lsqr_b200_plan_info
     out->peer_exchange = me->peer;
     out->entries_per_lane = P.epl;
     out->lines_per_gather = P.lines_per_gather;
+    out->flavour = P.win_cap > 0 ? 1 : (P.gather_bound ? 2 : 0);
     return LSQR_B200_OK;
 }
 

@@ -32,6 +32,7 @@ struct TilePlan {
     double windowed = 0.0;       // fraction of the stored entries whose gathers are served from shared memory
     int resident_checked = 0;    // 1: the probe found the first grid co-resident, -1: the grid had to shrink
     double lines_per_gather = 32.0;   // 128-byte lines that 32 consecutive stored entries span (32 = no locality)
+    int gather_bound = 0;        // kernel flavour: 1 = random columns (FLAV_GATHER), 0 = local gathers (FLAV_LOCAL)
     unsigned long long *stat = nullptr;   // device scratch of the locality measurement
     uint32_t span_p50 = 0, span_max = 0;   // gather span (entries of the dense vector) of the pieces: median, maximum
 };
@@ -76,16 +77,21 @@ static int spmv_configure(bool windows, int *ctas_per_sm)
         occ = std::min(occ, n);
         return LSQR_B200_OK;
     };
-    LSQRB_TRY(one(spmv_kernel<FIN_NONE, kEpl, false>));
-    LSQRB_TRY(one(spmv_kernel<FIN_APROD, kEpl, false>));
-    LSQRB_TRY(one(spmv_kernel<FIN_ATPROD, kEpl, false>));
-    LSQRB_TRY(one(spmv_kernel<FIN_INIT_ATPROD, kEpl, false>));
-    LSQRB_TRY(one(spmv_kernel<FIN_PUSH, kEpl, false>));
-    LSQRB_TRY(one(spmv_kernel<FIN_NONE, kEpl, true>));
-    LSQRB_TRY(one(spmv_kernel<FIN_APROD, kEpl, true>));
-    LSQRB_TRY(one(spmv_kernel<FIN_ATPROD, kEpl, true>));
-    LSQRB_TRY(one(spmv_kernel<FIN_INIT_ATPROD, kEpl, true>));
-    LSQRB_TRY(one(spmv_kernel<FIN_PUSH, kEpl, true>));
+    LSQRB_TRY(one(spmv_kernel<FIN_NONE, kEpl, FLAV_LOCAL>));
+    LSQRB_TRY(one(spmv_kernel<FIN_APROD, kEpl, FLAV_LOCAL>));
+    LSQRB_TRY(one(spmv_kernel<FIN_ATPROD, kEpl, FLAV_LOCAL>));
+    LSQRB_TRY(one(spmv_kernel<FIN_INIT_ATPROD, kEpl, FLAV_LOCAL>));
+    LSQRB_TRY(one(spmv_kernel<FIN_PUSH, kEpl, FLAV_LOCAL>));
+    LSQRB_TRY(one(spmv_kernel<FIN_NONE, kEpl, FLAV_WINDOW>));
+    LSQRB_TRY(one(spmv_kernel<FIN_APROD, kEpl, FLAV_WINDOW>));
+    LSQRB_TRY(one(spmv_kernel<FIN_ATPROD, kEpl, FLAV_WINDOW>));
+    LSQRB_TRY(one(spmv_kernel<FIN_INIT_ATPROD, kEpl, FLAV_WINDOW>));
+    LSQRB_TRY(one(spmv_kernel<FIN_PUSH, kEpl, FLAV_WINDOW>));
+    LSQRB_TRY(one(spmv_kernel<FIN_NONE, kEpl, FLAV_GATHER>));
+    LSQRB_TRY(one(spmv_kernel<FIN_APROD, kEpl, FLAV_GATHER>));
+    LSQRB_TRY(one(spmv_kernel<FIN_ATPROD, kEpl, FLAV_GATHER>));
+    LSQRB_TRY(one(spmv_kernel<FIN_INIT_ATPROD, kEpl, FLAV_GATHER>));
+    LSQRB_TRY(one(spmv_kernel<FIN_PUSH, kEpl, FLAV_GATHER>));
     current_pct = pct;
     if (occ < 1) { set_last_error("spmv kernel does not fit an SM"); return LSQR_B200_ERR_CUDA; }
     *ctas_per_sm = occ;
@@ -254,6 +260,12 @@ static int build_plan(Work &wk, const Csr &M, TilePlan *p, int reserve_sms = 0)
     p->ctas = std::max(1, wk.sms - reserve_sms) * occ;
     LSQRB_TRY(plan_cut(wk, M, p, 0));
     LSQRB_TRY(plan_fetch(wk, *p, &t));
+    // Kernel flavour: a warp-wide gather of a random-column matrix touches ~25-32 lines (C2, C4, C5), of a banded one
+    // ~10 (C3); the two want opposite instruction orders in the chunk loop (spmv.cuh, warp_chunk_core).
+    {
+        const int forced = env_int("LSQR_B200_FLAVOUR", -1);
+        p->gather_bound = forced >= 0 ? (forced == 2) : (p->lines_per_gather >= (double)env_int("LSQR_B200_GATHER_LINES", 20));
+    }
     const int forced_cap = env_int("LSQR_B200_WINDOW_CAP", 0);
     if (M.nnz > 0 && want_window) {
         double f = 0;
@@ -352,8 +364,9 @@ static int launch_piece(Work &wk, const TilePlan &P, const SpmvArgs &a)
         cfg.attrs = attr;
         cfg.numAttrs = 1;
     }
-    if (P.win_cap > 0) LSQRB_CUDA(cudaLaunchKernelEx(&cfg, spmv_kernel<FIN, kEpl, true>, a));
-    else               LSQRB_CUDA(cudaLaunchKernelEx(&cfg, spmv_kernel<FIN, kEpl, false>, a));
+    if (P.win_cap > 0)      LSQRB_CUDA(cudaLaunchKernelEx(&cfg, spmv_kernel<FIN, kEpl, FLAV_WINDOW>, a));
+    else if (P.gather_bound) LSQRB_CUDA(cudaLaunchKernelEx(&cfg, spmv_kernel<FIN, kEpl, FLAV_GATHER>, a));
+    else                    LSQRB_CUDA(cudaLaunchKernelEx(&cfg, spmv_kernel<FIN, kEpl, FLAV_LOCAL>, a));
     wk.launches++;
     LSQRB_CUDA(cudaGetLastError());
     return LSQR_B200_OK;

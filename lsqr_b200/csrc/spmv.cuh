@@ -213,6 +213,20 @@ __device__ __forceinline__ void load_chunk(const SpmvArgs &a, uint32_t cb, int l
     }
 }
 
+// The per-warp row-sum buffer is addressed in the shared state space with a 32-bit address computed once per kernel:
+// with a generic pointer the compiler re-derives the shared window (S2UR SR_CgaCtaId + ULEA) in front of every access
+// inside the chunk loop, two MIO round trips per chunk on the critical path of the row-end pass.
+__device__ __forceinline__ void sts_f64x2(uint32_t addr, double x, double y)
+{
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(x), "d"(y) : "memory");
+}
+__device__ __forceinline__ double lds_f64(uint32_t addr)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
+    return v;
+}
+
 template <int FIN>
 struct WarpTileState {
     uint32_t wb, woff;     // window base row, lanes below woff are finished rows
@@ -220,10 +234,10 @@ struct WarpTileState {
     double carry;          // running sum of the row that is open at the chunk boundary
 };
 
-// Reduces the chunk [base, base + 32 EPL): t[] = the lane's EPL products (stored value * gathered vector entry).
-template <int FIN, int EPL, int MODE>
-__device__ __forceinline__ void warp_chunk_core(const SpmvArgs &a, const BlockCtx &bc, Epilogue<FIN> &epi, double *su,
-                                                WarpTileState<FIN> &ts, double (&t)[EPL],
+// Reduces the chunk [base, base + 32 EPL): t[] = the lane's EPL gathered vector entries, cv[] = its stored values.
+template <int FIN, int EPL, int MODE, bool LATE>
+__device__ __forceinline__ void warp_chunk_core(const SpmvArgs &a, const BlockCtx &bc, Epilogue<FIN> &epi, uint32_t su,
+                                                WarpTileState<FIN> &ts, double (&t)[EPL], const double (&cv)[EPL],
                                                 uint32_t base, uint32_t r1, uint32_t e1, int lane)
 {
     constexpr uint32_t kC = 32u * EPL;
@@ -254,6 +268,16 @@ __device__ __forceinline__ void warp_chunk_core(const SpmvArgs &a, const BlockCt
     for (int k = 1; k < EPL; ++k) mw = ((uint32_t)lane * EPL) / 32u == (uint32_t)k ? m[k] : mw;
     const uint32_t f = (mw >> (((uint32_t)lane * EPL) & 31u)) & ((1u << EPL) - 1u);
 
+    // ---- products, gather-bound flavour (LATE).  First use of the gathered values: it comes AFTER the head mask so
+    // that the mask's ~70 instructions and MIO round trips overlap the gather latency (with the multiply in front of
+    // the mask every warp stalled there on a cold gather: 4 % on the random-column families).  Matrices whose gathers
+    // hit L1 (banded) want the opposite -- the multiplies in flight while the mask's REDUX results travel -- and
+    // measured 12 % slower with the late multiply, so warp_chunk multiplies for them.
+    if (LATE) {
+#pragma unroll
+        for (int k = 0; k < EPL; ++k) t[k] *= cv[k];
+    }
+
     // ---- segmented running sums inside the lane (t_k = sum of the lane's entries of the segment that entry k
     // belongs to, up to and including k)
     if (lane == 0 && !(f & 1u)) t[0] = ts.carry + t[0];    // row that began in an earlier chunk
@@ -264,11 +288,18 @@ __device__ __forceinline__ void warp_chunk_core(const SpmvArgs &a, const BlockCt
     const uint32_t hb = __ballot_sync(0xffffffffu, f != 0u);
     const uint32_t below = hb & (0xffffffffu >> (31 - lane));
     const int reach = lane - (below ? 31 - __clz(below) : 0);   // how far down this lane's open segment extends
+    // A step of distance d adds nothing when no lane's segment reaches d lanes down: short rows (20 entries = 5
+    // lanes) skip the steps of 8 and 16 lanes.  Shuffles share the L1TEX data stage with the gathers, which is the
+    // saturated unit of this kernel, so the skipped steps are throughput, not only latency.
+    // (gather-bound flavour only: on the banded family the extra reduction and branches cost 3-5 %)
+    const int span = LATE ? (int)__reduce_max_sync(0xffffffffu, (unsigned)reach) : 31;
     double vs = t[EPL - 1];
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-        const double y = __shfl_up_sync(0xffffffffu, vs, d);
-        if (d <= reach) vs += y;
+        if (d <= span) {                                   // warp-uniform
+            const double y = __shfl_up_sync(0xffffffffu, vs, d);
+            if (d <= reach) vs += y;
+        }
     }
     double cin = __shfl_up_sync(0xffffffffu, vs, 1);
     if (lane == 0) cin = 0.0;
@@ -278,14 +309,14 @@ __device__ __forceinline__ void warp_chunk_core(const SpmvArgs &a, const BlockCt
         if (!(f & ((2u << k) - 1u))) t[k] += cin;
     ts.carry = __shfl_sync(0xffffffffu, t[EPL - 1], 31);
 #pragma unroll
-    for (int k = 0; k < EPL; k += 2) *reinterpret_cast<double2 *>(su + EPL * lane + k) = make_double2(t[k], t[k + 1]);
+    for (int k = 0; k < EPL; k += 2) sts_f64x2(su + 8u * (uint32_t)(EPL * lane + k), t[k], t[k + 1]);
     __syncwarp();
 
     // ---- rows that end in this chunk: lane j finishes row wb+j (the sentinel of absent rows never ends)
     for (;;) {
         const bool ends = (uint32_t)lane >= ts.woff && ts.win.PE <= endp;
         if (ends) {
-            const double s = (ts.win.PE != ts.win.P) ? su[ts.win.PE - 1u - base] : 0.0;
+            const double s = (ts.win.PE != ts.win.P) ? lds_f64(su + 8u * (ts.win.PE - 1u - base)) : 0.0;
             epi.template apply<MODE>(a, ts.wb + (uint32_t)lane, s, ts.win.O, ts.win.G);
         }
         ts.woff += (uint32_t)__popc(__ballot_sync(0xffffffffu, ends));
@@ -308,8 +339,8 @@ __device__ __forceinline__ void warp_chunk_core(const SpmvArgs &a, const BlockCt
 
 // Processes the chunk [base, base + 32 EPL) held in `cur`; `nxt` receives the following chunk, whose loads stay in
 // flight while this one is reduced.  WIN: the gathers are reads of the warp's staged window.
-template <int FIN, bool WIN, int EPL, int MODE>
-__device__ __forceinline__ void warp_chunk(const SpmvArgs &a, const BlockCtx &bc, Epilogue<FIN> &epi, double *su,
+template <int FIN, bool WIN, int EPL, int MODE, bool LATE>
+__device__ __forceinline__ void warp_chunk(const SpmvArgs &a, const BlockCtx &bc, Epilogue<FIN> &epi, uint32_t su,
                                            const double *xw /* WIN: window - win_lo */, WarpTileState<FIN> &ts,
                                            const ChunkRegs<EPL> &cur, ChunkRegs<EPL> &nxt, uint32_t base, uint32_t r1,
                                            uint32_t e0, uint32_t e1, int32_t safe, int lane,
@@ -319,13 +350,15 @@ __device__ __forceinline__ void warp_chunk(const SpmvArgs &a, const BlockCtx &bc
 #pragma unroll
     for (int k = 0; k < EPL; ++k) t[k] = WIN ? xw[cur.c[k]] : ldg_keep_f64(a.x + cur.c[k], pol_keep);
     load_chunk<EPL>(a, base + 32u * EPL, lane, e0, e1, safe, pol_stream, nxt);
+    if (!LATE) {
 #pragma unroll
-    for (int k = 0; k < EPL; ++k) t[k] *= cur.v[k];
-    warp_chunk_core<FIN, EPL, MODE>(a, bc, epi, su, ts, t, base, r1, e1, lane);
+        for (int k = 0; k < EPL; ++k) t[k] *= cur.v[k];
+    }
+    warp_chunk_core<FIN, EPL, MODE, LATE>(a, bc, epi, su, ts, t, cur.v, base, r1, e1, lane);
 }
 
-template <int FIN, bool WIN, int EPL, int MODE>
-__device__ __forceinline__ void warp_tile_loop(const SpmvArgs &a, const BlockCtx &bc, Epilogue<FIN> &epi, double *su,
+template <int FIN, bool WIN, int EPL, int MODE, bool LATE>
+__device__ __forceinline__ void warp_tile_loop(const SpmvArgs &a, const BlockCtx &bc, Epilogue<FIN> &epi, uint32_t su,
                                                const double *xw, uint32_t r0, uint32_t r1, uint32_t e0, uint32_t e1,
                                                int32_t safe, int lane, uint64_t pol_stream, uint64_t pol_keep)
 {
@@ -340,18 +373,18 @@ __device__ __forceinline__ void warp_tile_loop(const SpmvArgs &a, const BlockCtx
     // two chunks per trip so that the register double buffer needs no copies; at least one chunk is processed
     // even for a piece without entries, so that its (empty) rows still get their epilogue
     for (uint32_t base = a0;;) {
-        warp_chunk<FIN, WIN, EPL, MODE>(a, bc, epi, su, xw, ts, ra, rb, base, r1, e0, e1, safe, lane, pol_stream, pol_keep);
+        warp_chunk<FIN, WIN, EPL, MODE, LATE>(a, bc, epi, su, xw, ts, ra, rb, base, r1, e0, e1, safe, lane, pol_stream, pol_keep);
         base += 32u * EPL;
         if (base >= e1) break;
-        warp_chunk<FIN, WIN, EPL, MODE>(a, bc, epi, su, xw, ts, rb, ra, base, r1, e0, e1, safe, lane, pol_stream, pol_keep);
+        warp_chunk<FIN, WIN, EPL, MODE, LATE>(a, bc, epi, su, xw, ts, rb, ra, base, r1, e0, e1, safe, lane, pol_stream, pol_keep);
         base += 32u * EPL;
         if (base >= e1) break;
     }
 }
 
 // One piece: stage the gather window if the piece has one, then stream its chunks.
-template <int FIN, int EPL, bool WINS>
-__device__ __forceinline__ void warp_tile(const SpmvArgs &a, const BlockCtx &bc, Epilogue<FIN> &epi, double *su, double *wbuf,
+template <int FIN, int EPL, bool WINS, bool LATE>
+__device__ __forceinline__ void warp_tile(const SpmvArgs &a, const BlockCtx &bc, Epilogue<FIN> &epi, uint32_t su, double *wbuf,
                                           const TileDesc &d0, const TileDesc &d1, int lane,
                                           uint64_t pol_stream, uint64_t pol_keep)
 {
@@ -365,18 +398,18 @@ __device__ __forceinline__ void warp_tile(const SpmvArgs &a, const BlockCtx &bc,
         const double *xw = wbuf - d0.win_lo;
         const int32_t safe = (int32_t)d0.win_lo;
         if (FIN != FIN_NONE && bc.mode == BM_FINAL)
-            warp_tile_loop<FIN, true, EPL, BM_FINAL>(a, bc, epi, su, xw, d0.row, d1.row, d0.entry, d1.entry, safe, lane, pol_stream, pol_keep);
+            warp_tile_loop<FIN, true, EPL, BM_FINAL, LATE>(a, bc, epi, su, xw, d0.row, d1.row, d0.entry, d1.entry, safe, lane, pol_stream, pol_keep);
         else if (bc.mode == BM_ACC)
-            warp_tile_loop<FIN, true, EPL, BM_ACC>(a, bc, epi, su, xw, d0.row, d1.row, d0.entry, d1.entry, safe, lane, pol_stream, pol_keep);
+            warp_tile_loop<FIN, true, EPL, BM_ACC, LATE>(a, bc, epi, su, xw, d0.row, d1.row, d0.entry, d1.entry, safe, lane, pol_stream, pol_keep);
         else
-            warp_tile_loop<FIN, true, EPL, BM_STORE>(a, bc, epi, su, xw, d0.row, d1.row, d0.entry, d1.entry, safe, lane, pol_stream, pol_keep);
+            warp_tile_loop<FIN, true, EPL, BM_STORE, LATE>(a, bc, epi, su, xw, d0.row, d1.row, d0.entry, d1.entry, safe, lane, pol_stream, pol_keep);
     } else {
         if (FIN != FIN_NONE && bc.mode == BM_FINAL)
-            warp_tile_loop<FIN, false, EPL, BM_FINAL>(a, bc, epi, su, nullptr, d0.row, d1.row, d0.entry, d1.entry, 0, lane, pol_stream, pol_keep);
+            warp_tile_loop<FIN, false, EPL, BM_FINAL, LATE>(a, bc, epi, su, nullptr, d0.row, d1.row, d0.entry, d1.entry, 0, lane, pol_stream, pol_keep);
         else if (bc.mode == BM_ACC)
-            warp_tile_loop<FIN, false, EPL, BM_ACC>(a, bc, epi, su, nullptr, d0.row, d1.row, d0.entry, d1.entry, 0, lane, pol_stream, pol_keep);
+            warp_tile_loop<FIN, false, EPL, BM_ACC, LATE>(a, bc, epi, su, nullptr, d0.row, d1.row, d0.entry, d1.entry, 0, lane, pol_stream, pol_keep);
         else
-            warp_tile_loop<FIN, false, EPL, BM_STORE>(a, bc, epi, su, nullptr, d0.row, d1.row, d0.entry, d1.entry, 0, lane, pol_stream, pol_keep);
+            warp_tile_loop<FIN, false, EPL, BM_STORE, LATE>(a, bc, epi, su, nullptr, d0.row, d1.row, d0.entry, d1.entry, 0, lane, pol_stream, pol_keep);
     }
 }
 
@@ -385,12 +418,18 @@ __device__ __forceinline__ void warp_tile(const SpmvArgs &a, const BlockCtx &bc,
 // WINS: the flavour for plans with staged gather windows (opt-in).  The default flavour does not carry the second
 // copy of the chunk loop: the kernel is a third smaller, which measured 2-4 % on the gather-bound families (the
 // unrolled chunk loops of both paths together overflow the instruction cache next to each other).
-template <int FIN, int EPL, bool WINS>
+// FLAV: kernel flavour, chosen per plan (plan.cuh): FLAV_LOCAL = gathers that mostly hit L1 (banded matrices),
+// FLAV_WINDOW = staged gather windows (opt-in), FLAV_GATHER = random columns (late multiply, adaptive scan depth).
+enum SpmvFlavour { FLAV_LOCAL = 0, FLAV_WINDOW = 1, FLAV_GATHER = 2 };
+
+template <int FIN, int EPL, int FLAV>
 __global__ void __launch_bounds__(kWThreads, EPL == 4 ? 4 : 2)
 spmv_kernel(SpmvArgs a)
 {
+    constexpr bool WINS = FLAV == FLAV_WINDOW;
+    constexpr bool LATE = FLAV == FLAV_GATHER;
     constexpr bool kFused = (FIN == FIN_APROD || FIN == FIN_ATPROD || FIN == FIN_INIT_ATPROD);
-    extern __shared__ __align__(16) double s_dyn[];          // per warp: su[32 EPL] | gather window[win_cap]
+    extern __shared__ __align__(128) double s_dyn[];         // per warp: su[32 EPL] | gather window[win_cap]; 128-byte aligned: a warp-wide STS.128 then touches 4 lines, not 5
     __shared__ double s_red[kWWarps];
     __shared__ double s_exc[2 * kWThreads];
 
@@ -452,8 +491,10 @@ spmv_kernel(SpmvArgs a)
         const uint64_t pol_keep = l2_policy_evict_last();
         const int lane = tid & 31, wib = tid >> 5;
         const int nw = (int)gridDim.x * kWWarps;
-        double *su = s_dyn + (size_t)wib * (32u * EPL + (WINS ? (size_t)a.win_cap : (size_t)0));   // (no window: a constant the compiler can rematerialise)
-        double *wbuf = su + 32 * EPL;
+        double *su_g = s_dyn + (size_t)wib * (32u * EPL + (WINS ? (size_t)a.win_cap : (size_t)0));
+        double *wbuf = su_g + 32 * EPL;
+        uint32_t su = (uint32_t)__cvta_generic_to_shared(su_g);
+        asm volatile("" : "+r"(su));     // opaque from here on: kept in a register, not re-derived from %tid in the loop
         const uint32_t *__restrict__ order = a.order;
         const int nslots = order ? a.nslots : a.ntiles;
         for (int b = 0; b < a.nblocks; ++b) {
@@ -486,7 +527,7 @@ spmv_kernel(SpmvArgs a)
                 if (t == kNoTile) break;                        // this warp's list is exhausted
                 const TileDesc d0 = tiles[t], d1 = tiles[t + 1];
                 if (d0.row == d1.row) continue;                 // no row starts in this tile (inside a long row)
-                warp_tile<FIN, EPL, WINS>(a, bc, epi, su, wbuf, d0, d1, lane, pol_stream, pol_keep);
+                warp_tile<FIN, EPL, WINS, LATE>(a, bc, epi, su, wbuf, d0, d1, lane, pol_stream, pol_keep);
             }
             if (a.guard && b + 1 < a.nblocks) {
                 __syncthreads();                                // every warp of this CTA has finished block b

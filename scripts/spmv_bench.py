@@ -32,6 +32,8 @@ MODES = {
     "nooverlap": {"LSQR_B200_OVERLAP_UPDATE": "0"},
     "window": {"LSQR_B200_WINDOW": "1"},
     "pdl": {"LSQR_B200_PDL": "1"},
+    "local": {"LSQR_B200_FLAVOUR": "0"},
+    "gather": {"LSQR_B200_FLAVOUR": "2"},
     "carve28": {"LSQR_B200_SMEM_CARVEOUT_PCT": "28"},
     "carve24": {"LSQR_B200_SMEM_CARVEOUT_PCT": "24"},
     "carve35": {"LSQR_B200_SMEM_CARVEOUT_PCT": "35"},

@@ -30,6 +30,8 @@ KERNEL_MODES = {
     "guard2": {"LSQR_B200_DRIFT_GUARD": "2"},
     "window": {"LSQR_B200_WINDOW": "1"},                   # shared-memory gather window where the pieces are narrow (opt-in)
     "smallwindow": {"LSQR_B200_WINDOW": "1", "LSQR_B200_WINDOW_CAP": "208"},   # staged and global pieces mixed
+    "local": {"LSQR_B200_FLAVOUR": "0"},                   # kernel flavour for local gathers forced (early multiply, full scan)
+    "gather": {"LSQR_B200_FLAVOUR": "2"},                  # kernel flavour for random columns forced (late multiply, adaptive scan)
     "pdl": {"LSQR_B200_PDL": "1"},                         # A v kernel launched as a programmatic dependent of the A'u kernel
     "pdl_perblock": {"LSQR_B200_PDL": "1", "LSQR_B200_SINGLE_LAUNCH": "0"},
 }
@@ -241,7 +243,7 @@ def test_solve_parity_scaled_configs(lb, name, scale, shuffle, tol):
 
 
 @pytest.mark.parametrize("name,scale", [("C2", 10), ("C3", 100), ("C4", 100)])
-@pytest.mark.parametrize("mode", ["perblock", "noguard", "guard2", "window", "smallwindow", "pdl", "pdl_perblock"])
+@pytest.mark.parametrize("mode", ["perblock", "noguard", "guard2", "window", "smallwindow", "local", "gather", "pdl", "pdl_perblock"])
 def test_solve_parity_kernel_modes(lb, name, scale, mode, monkeypatch):
     """The A/B switches of the SpMV kernel against the oracle and against the default mode.  Every mode adds the same
     terms in the same order (the plan fixes the order; the mode only changes how the blocks are launched and where a
