@@ -308,42 +308,18 @@ __device__ __forceinline__ void warp_chunk_core(const SpmvArgs &a, const BlockCt
     for (int k = 0; k < EPL; ++k)
         if (!(f & ((2u << k) - 1u))) t[k] += cin;
     ts.carry = __shfl_sync(0xffffffffu, t[EPL - 1], 31);
-    // ---- rows that end in this chunk: lane j finishes row wb+j (the sentinel of absent rows never ends).  The sum of
-    // a row is the running sum at its last entry, i.e. t[(PE-1-base) % EPL] of lane (PE-1-base) / EPL.  When at most
-    // two rows (with entries) end here -- every chunk of a matrix with long rows -- their sums travel lane to lane
-    // (three shuffles each); otherwise the running sums go through the warp's shared buffer once.  Either way the
-    // traffic is L1TEX work, the unit this kernel saturates: half the chunks of a 200-entries-per-row product end no
-    // row at all and used to pay two STS.128 for nothing.
-    bool stored = false;
+#pragma unroll
+    for (int k = 0; k < EPL; k += 2) sts_f64x2(su + 8u * (uint32_t)(EPL * lane + k), t[k], t[k + 1]);
+    __syncwarp();
+
+    // ---- rows that end in this chunk: lane j finishes row wb+j (the sentinel of absent rows never ends)
     for (;;) {
         const bool ends = (uint32_t)lane >= ts.woff && ts.win.PE <= endp;
-        const bool fetch = ends && ts.win.PE != ts.win.P;
-        const unsigned eb = __ballot_sync(0xffffffffu, ends);
-        unsigned em = __ballot_sync(0xffffffffu, fetch);
-        double s = 0.0;
-        if (!stored && __popc(em) <= 2) {
-            while (em) {                                           // warp-uniform
-                const int j = __ffs(em) - 1;
-                em &= em - 1u;
-                const uint32_t pos = __shfl_sync(0xffffffffu, ts.win.PE - 1u - base, j);
-                const uint32_t kk = pos % (uint32_t)EPL;
-                double v = t[0];
-#pragma unroll
-                for (int k = 1; k < EPL; ++k) v = kk == (uint32_t)k ? t[k] : v;
-                v = __shfl_sync(0xffffffffu, v, (int)(pos / (uint32_t)EPL));
-                if (lane == j) s = v;
-            }
-        } else {
-            if (!stored) {
-#pragma unroll
-                for (int k = 0; k < EPL; k += 2) sts_f64x2(su + 8u * (uint32_t)(EPL * lane + k), t[k], t[k + 1]);
-                __syncwarp();
-                stored = true;
-            }
-            if (fetch) s = lds_f64(su + 8u * (ts.win.PE - 1u - base));
+        if (ends) {
+            const double s = (ts.win.PE != ts.win.P) ? lds_f64(su + 8u * (ts.win.PE - 1u - base)) : 0.0;
+            epi.template apply<MODE>(a, ts.wb + (uint32_t)lane, s, ts.win.O, ts.win.G);
         }
-        if (ends) epi.template apply<MODE>(a, ts.wb + (uint32_t)lane, s, ts.win.O, ts.win.G);
-        ts.woff += (uint32_t)__popc(eb);
+        ts.woff += (uint32_t)__popc(__ballot_sync(0xffffffffu, ends));
         if (ts.woff >= 32u && ts.wb + 32u < r1) {          // window exhausted: more rows may end here
             ts.wb += 32u;
             ts.woff = 0;
@@ -352,7 +328,7 @@ __device__ __forceinline__ void warp_chunk_core(const SpmvArgs &a, const BlockCt
         }
         break;
     }
-    if (stored) __syncwarp();                              // the next chunk rewrites the buffer
+    __syncwarp();
     // keep the window ahead of the stream: the reload is in flight during the next chunk
     if (endp < e1 && ts.woff >= 16u && ts.wb + ts.woff < r1) {
         ts.wb += ts.woff;
