@@ -4,16 +4,21 @@
 // gathered coordinate (column blocks of A / row blocks of A', so that the gathered slice of the dense vector stays
 // in L2).  The rows are cut into row-aligned tiles, the SAME row ranges in every block; a warp owns the same tiles
 // in every block and walks the blocks in order, so "block b+1 accumulates onto what block b stored" is program
-// order inside one warp and needs neither atomics nor a grid barrier.  A soft guard keeps the warps of a launch
-// within two blocks of each other, so the gathered working set stays at two L2-sized slices at most.
+// order inside one warp and needs no atomics.  A guard on the GATHERED side makes block b start when every CTA has
+// finished block b-1 (one thread per CTA polls a counter), so exactly one L2-sized slice of the dense vector is live;
+// the grid is proven co-resident at initialize (probe mode below, plan.cuh).
+//
+// Three flavours of the same kernel (template parameter FLAV, chosen per plan): FLAV_GATHER for random columns
+// (first use of the gathered values behind the head mask, scan depth adapted to the chunk), FLAV_LOCAL for banded
+// matrices whose gathers hit L1 (multiply early, full scan), FLAV_WINDOW for the opt-in staged gather windows.
 //
 // A tile of one block (a "piece") is consumed in chunks of 128 stored entries, 4 per lane:
 //   * val[] / idx[] of chunk c+1 are fetched with one 256-bit and one 128-bit streaming load per lane (evict-first)
 //     while chunk c is reduced (register double buffer);
-//   * x[idx]: if the piece's gathered indices span a window that fits the warp's shared-memory buffer (banded /
-//     local matrices; the span is recorded per piece at initialize), the window is staged into shared memory with
-//     coalesced loads and the gathers are shared-memory reads (conflict-bound, ~5x the L1TEX rate of a divergent
-//     global gather); otherwise 4 independent global gathers per lane through L1/L2 (evict-last);
+//   * x[idx]: 4 independent global gathers per lane through L1/L2 (evict-last); FLAV_WINDOW only: if the piece's
+//     gathered indices span a window that fits the warp's shared-memory buffer (the span is recorded per piece at
+//     initialize), the window is staged with coalesced loads and the gathers are shared-memory reads (measured
+//     bank-conflict-bound and no faster on the banded family: opt-in);
 //   * row heads inside the chunk come from a 32-row window of ptr[] held in registers (lane j <-> row wb+j), turned
 //     into a 128-bit head mask with warp-wide OR reductions;
 //   * a segmented scan (4 entries in the lane, then 5 shuffle steps over lanes) forms the running row sums; a row
@@ -163,14 +168,11 @@ struct Epilogue {
     }
 };
 
-// One lane's share of a chunk: EPL consecutive stored entries (a chunk is 32 * EPL entries).
-//   EPL = 4: 24 registers of double buffer, 4 CTAs / 32 warps per SM -- the flavour for gather-bound matrices
-//            (uniformly random columns: the L1TEX tag stage is the limit, warps are what hides its latency);
-//   EPL = 8: the per-chunk work that does not depend on the chunk length (head mask, warp scan, row-end pass, window
-//            upkeep: ~2/3 of the instructions at EPL = 4) is spent once per 256 entries.  On matrices whose gathers are
-//            cheap (banded / local: shared-memory window or a few lines per gather) the kernel is bound by instruction
-//            issue, and this flavour (2 CTAs / 16 warps per SM, <= 128 registers, the same bytes and gathers in flight)
-//            is the faster one.
+// One lane's share of a chunk: EPL consecutive stored entries (a chunk is 32 * EPL entries).  Only EPL = 4 is
+// instantiated (plan.cuh: kEpl): 24 registers of double buffer, 4 CTAs / 32 warps per SM -- the L1TEX pipe is the
+// limit and warps are what hides its latency.  An EPL = 8 build (the per-chunk overhead once per 256 entries, 2 CTAs /
+// 16 warps per SM, <= 128 registers) was measured on all four families and was slower or equal everywhere
+// (profiles/r02/run5/spmv_bench_epl_window_ab.jsonl); the template stays generic in EPL.
 template <int EPL>
 struct ChunkRegs {
     double v[EPL];
@@ -413,11 +415,7 @@ __device__ __forceinline__ void warp_tile(const SpmvArgs &a, const BlockCtx &bc,
     }
 }
 
-// EPL: stored entries per lane and chunk (see ChunkRegs); EPL = 4 runs 4 CTAs per SM (<= 64 registers), EPL = 8 runs 2
-// (<= 128 registers, room for wide gather windows).
-// WINS: the flavour for plans with staged gather windows (opt-in).  The default flavour does not carry the second
-// copy of the chunk loop: the kernel is a third smaller, which measured 2-4 % on the gather-bound families (the
-// unrolled chunk loops of both paths together overflow the instruction cache next to each other).
+// EPL: stored entries per lane and chunk (see ChunkRegs).
 // FLAV: kernel flavour, chosen per plan (plan.cuh): FLAV_LOCAL = gathers that mostly hit L1 (banded matrices),
 // FLAV_WINDOW = staged gather windows (opt-in), FLAV_GATHER = random columns (late multiply, adaptive scan depth).
 enum SpmvFlavour { FLAV_LOCAL = 0, FLAV_WINDOW = 1, FLAV_GATHER = 2 };
@@ -507,7 +505,7 @@ spmv_kernel(SpmvArgs a)
                 // is live in L2 (measured: a warp that runs ahead touches the whole next slice within microseconds --
                 // random gathers -- and two 48 MB slices do not fit; C5/4 Atprod 7.3 ms vs 5.4 ms).  guard = 2: one
                 // block of slack.  One thread per CTA polls (4736 polling warps stole L1TEX cycles from the stragglers
-                // they were waiting for: 6 % on C5/4); the launch is cooperative, so the grid is co-resident.
+                // they were waiting for: 6 % on C5/4); the grid was proven co-resident by the probe at initialize (plan.cuh).
                 if (tid == 0) {
                     const volatile unsigned int *done = &st->blk_done[b - a.guard];
                     const unsigned long long t0 = globaltimer_ns();

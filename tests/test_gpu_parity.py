@@ -261,6 +261,32 @@ def test_solve_parity_kernel_modes(lb, name, scale, mode, monkeypatch):
     assert np.array_equal(np.asarray(r1.x), np.asarray(r3.x))
 
 
+def test_kernel_flavour_follows_the_gather_locality(lb, monkeypatch):
+    """The plan measures at initialize how many 128-byte lines a warp-wide gather touches and picks the kernel flavour
+    from it: banded C3 (~12 lines) -> local flavour (0), uniformly random C2 (32 lines) -> gather-bound
+    flavour (2); gather windows (opt-in) -> window flavour (1).  LSQR_B200_FLAVOUR overrides."""
+    from lsqr_b200 import synth
+    set_kernel_mode(monkeypatch, "default")
+    for name, scale, want in (("C3", 50, 0), ("C2", 10, 2)):
+        cfg = synth.scaled(name, scale)
+        irow, icol, a = synth.coo_block(cfg["kind"], cfg["seed"], cfg["m"], cfg["n"], cfg["k"])
+        s = lb.LsqrSolverEz().initialize(cfg["m"], cfg["n"], a, irow, icol)
+        pa, pat = s.plan(False), s.plan(True)
+        s.destroy()
+        assert pa["flavour"] == want and pat["flavour"] == want, (name, pa, pat)
+        assert (pa["lines_per_gather"] >= 20) == (want == 2), (name, pa)
+    cfg = synth.scaled("C3", 50)
+    irow, icol, a = synth.coo_block(cfg["kind"], cfg["seed"], cfg["m"], cfg["n"], cfg["k"])
+    set_kernel_mode(monkeypatch, "gather")
+    s = lb.LsqrSolverEz().initialize(cfg["m"], cfg["n"], a, irow, icol)
+    assert s.plan(False)["flavour"] == 2
+    s.destroy()
+    set_kernel_mode(monkeypatch, "window")
+    s = lb.LsqrSolverEz().initialize(cfg["m"], cfg["n"], a, irow, icol)
+    assert s.plan(False)["flavour"] == 1 and s.plan(True)["flavour"] == 0       # A staged, A' too wide: local
+    s.destroy()
+
+
 def test_banded_matrix_gathers_from_the_shared_window(lb, monkeypatch):
     """C3 family, north_star (2) "shared-memory staging of the dense x-vector": with LSQR_B200_WINDOW=1 every piece of A
     touches a narrow span of v (~230 entries) and gathers from a staged shared-memory window; the pieces of A' span
