@@ -213,6 +213,9 @@ def reference_main(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": res["steps_done"], "warmup": res["warmup_done"], "ms_per_step": res["ms_per_step"],
+        # a step is one full solve of the 1/10-scale sample (~50 s on one core): the arm runs as many of the requested
+        # steps as fit its time budget (150 s timed, 60 s warm-up) and reports the counts it actually ran
+        "steps_requested": args.steps, "warmup_requested": args.warmup,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "iters_per_s": res["iters_per_s"],
         "config": {"workload": name, "sample": res["sample"], "sample_scale": res["sample_scale"],

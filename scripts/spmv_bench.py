@@ -33,6 +33,11 @@ MODES = {
     "window": {"LSQR_B200_WINDOW": "1"},
     "pdl": {"LSQR_B200_PDL": "1"},
     "local": {"LSQR_B200_FLAVOUR": "0"},
+    "tile4k": {"LSQR_B200_WARP_TILE": "4096"},
+    "tile16k": {"LSQR_B200_WARP_TILE": "16384"},
+    "tile32k": {"LSQR_B200_WARP_TILE": "32768"},
+    "roww2": {"LSQR_B200_TILE_ROW_WEIGHT": "2"},
+    "roww8": {"LSQR_B200_TILE_ROW_WEIGHT": "8"},
     "gather": {"LSQR_B200_FLAVOUR": "2"},
     "carve28": {"LSQR_B200_SMEM_CARVEOUT_PCT": "28"},
     "carve24": {"LSQR_B200_SMEM_CARVEOUT_PCT": "24"},
