@@ -229,6 +229,18 @@ __device__ __forceinline__ double lds_f64(uint32_t addr)
     return v;
 }
 
+// Byte offset of the running sum of chunk entry e (= EPL * lane + k) in the warp's buffer.  The buffer is laid out in
+// EPL/2 planes of 32 x 16 bytes -- plane k/2 holds the pair (t[k], t[k+1]) of every lane, lane-contiguous -- so that each
+// warp-wide STS.128 writes 512 CONTIGUOUS bytes: 4 conflict-free wavefronts.  The natural layout (entry e at 8 e) puts
+// the lanes' 16-byte pieces 32 bytes apart, which ncu counted as 9.4 wavefronts per STS.128 (profiles/r02/final/
+// c5q_gather_counters.txt: 18.7 store wavefronts per chunk), on the L1TEX data stage this kernel saturates.
+template <int EPL>
+__device__ __forceinline__ uint32_t row_sum_slot(uint32_t e)
+{
+    const uint32_t lane = e / (uint32_t)EPL, k = e % (uint32_t)EPL;
+    return (k >> 1) * 512u + lane * 16u + (k & 1u) * 8u;
+}
+
 template <int FIN>
 struct WarpTileState {
     uint32_t wb, woff;     // window base row, lanes below woff are finished rows
@@ -311,14 +323,14 @@ __device__ __forceinline__ void warp_chunk_core(const SpmvArgs &a, const BlockCt
         if (!(f & ((2u << k) - 1u))) t[k] += cin;
     ts.carry = __shfl_sync(0xffffffffu, t[EPL - 1], 31);
 #pragma unroll
-    for (int k = 0; k < EPL; k += 2) sts_f64x2(su + 8u * (uint32_t)(EPL * lane + k), t[k], t[k + 1]);
+    for (int k = 0; k < EPL; k += 2) sts_f64x2(su + row_sum_slot<EPL>((uint32_t)(EPL * lane + k)), t[k], t[k + 1]);
     __syncwarp();
 
     // ---- rows that end in this chunk: lane j finishes row wb+j (the sentinel of absent rows never ends)
     for (;;) {
         const bool ends = (uint32_t)lane >= ts.woff && ts.win.PE <= endp;
         if (ends) {
-            const double s = (ts.win.PE != ts.win.P) ? lds_f64(su + 8u * (ts.win.PE - 1u - base)) : 0.0;
+            const double s = (ts.win.PE != ts.win.P) ? lds_f64(su + row_sum_slot<EPL>(ts.win.PE - 1u - base)) : 0.0;
             epi.template apply<MODE>(a, ts.wb + (uint32_t)lane, s, ts.win.O, ts.win.G);
         }
         ts.woff += (uint32_t)__popc(__ballot_sync(0xffffffffu, ends));
