@@ -223,6 +223,19 @@ def test_options_struct_layout_agrees_in_c_python_and_fortran(tmp_path):
         d = getattr(Options, f)
         assert (d.offset, d.size) == c_layout[f], (f, d.offset, d.size, c_layout[f])
     assert sizes == [C.sizeof(Options), C.sizeof(KernelTimes), C.sizeof(PlanInfo), C.sizeof(IterRecord)]
+    # the three output structs field by field as well (names, offsets, sizes)
+    for cname, cls in (("lsqr_b200_kernel_times", KernelTimes), ("lsqr_b200_plan_info", PlanInfo), ("lsqr_b200_iter_record", IterRecord)):
+        names = [f[0] for f in cls._fields_]
+        src2 = tmp_path / (cname + ".c")
+        src2.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "lsqr_b200.h"\nint main(void) {\n' +
+                        "".join('printf("%s %%zu %%zu\\n", offsetof(%s, %s), sizeof(((%s *)0)->%s));\n' % (f, cname, f, cname, f) for f in names) +
+                        'return 0; }\n')
+        exe2 = tmp_path / cname
+        subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src2), "-o", str(exe2)], check=True)
+        for line, f in zip(subprocess.run([str(exe2)], capture_output=True, text=True, check=True).stdout.strip().split("\n"), names):
+            t = line.split()
+            d = getattr(cls, f)
+            assert t[0] == f and (d.offset, d.size) == (int(t[1]), int(t[2])), (cname, f, d.offset, d.size, t)
     # Fortran: same names, same order, interoperable kinds of the same size
     fort = _fortran_bind_c_fields("lsqr_b200_options")
     assert [n for n, _ in fort] == fields
