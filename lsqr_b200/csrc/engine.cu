@@ -376,10 +376,12 @@ int lsqr_b200_ez_initialize(lsqr_b200_ez **out, int32_t m, int32_t n,
     if (me->opt.world_size < 1) me->opt.world_size = 1;
     me->m = m; me->n = n; me->nnz = size_a;
     memset(&me->times, 0, sizeof me->times);
-    {   // iterations per enqueue: enough to cover ~300 us of device time, so that the host's per-batch work (graph
-        // launch, event wait, record drain) stays hidden, but not more: iterations enqueued past the stop are waste
+    {   // iterations per enqueue (= per CUDA-graph launch): enough to cover ~1 ms of device time.  Consecutive graph
+        // launches leave ~15 us between them (2 us between the kernels inside a graph), which a small problem feels
+        // (C2, 125 us per iteration: 131 / 123 / 121 us with 1 / 3 / 8 iterations per graph, profiles/r02/run19);
+        // iterations enqueued past the stop are empty kernels, so not more than 8
         const double est_iter_us = 24.0 * (double)size_a / 2.5e6 + 20.0;   // ~2.5 TB/s effective + launch floor
-        int dflt = (int)std::ceil(300.0 / est_iter_us);
+        int dflt = (int)std::ceil(1000.0 / est_iter_us);
         dflt = std::max(1, std::min(dflt, 8));
         me->batch = std::max(1, std::min(env_int("LSQR_B200_BATCH", dflt), kRingSize / 4));
     }

@@ -33,6 +33,11 @@ MODES = {
     "window": {"LSQR_B200_WINDOW": "1"},
     "pdl": {"LSQR_B200_PDL": "1"},
     "local": {"LSQR_B200_FLAVOUR": "0"},
+    "batch1": {"LSQR_B200_BATCH": "1"},
+    "batch2": {"LSQR_B200_BATCH": "2"},
+    "batch5": {"LSQR_B200_BATCH": "5"},
+    "batch8": {"LSQR_B200_BATCH": "8"},
+    "batch12": {"LSQR_B200_BATCH": "12"},
     "tile4k": {"LSQR_B200_WARP_TILE": "4096"},
     "tile16k": {"LSQR_B200_WARP_TILE": "16384"},
     "tile32k": {"LSQR_B200_WARP_TILE": "32768"},
